@@ -1,0 +1,186 @@
+/*
+ * ucfp_cuda.h -- C ABI of libucfp_cuda.so, the B200 (sm_100a) implementation of
+ * UCFP's data-parallel fingerprint hot path.
+ *
+ * This is the boundary the reference's Rust host binds over FFI (crate
+ * `ucfp-cuda`, see INTEGRATION.md and rust/ucfp-cuda/).  Plain pointers and
+ * sizes only: no C++ types, no torch types, no ownership transfer.  Every
+ * entry point returns 0 (UCFP_OK) or a negative UCFP_E_* code and never throws
+ * or aborts (the reference builds with panic = "abort", Cargo.toml:180, so
+ * nothing may unwind across this line).  The message for the last error on the
+ * calling thread is available from ucfp_last_error().
+ *
+ * Buffers may live in host memory (pageable or pinned) or in device memory of
+ * the context's GPU; the library inspects each pointer
+ * (cudaPointerGetAttributes) and stages host buffers itself.  All work is
+ * enqueued on the context's stream (ucfp_ctx_set_stream lets a host that
+ * already owns a CUDA stream, e.g. a torch stream in the test harness, share
+ * it).  Calls that take host output buffers synchronise that stream before
+ * returning; calls whose outputs are all device buffers return asynchronously.
+ *
+ * There is NO CPU fallback: without a usable sm_100 device every call fails
+ * with UCFP_E_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   hashing seam  src/modality/image.rs:68-70   ImageFingerprinter::fingerprint_with_preprocess
+ *                 src/modality/image.rs:175-179 FingerprinterContext::fingerprint_with_algorithm_and_preprocess
+ *   scan seam     src/index/mod.rs:29-35        IndexBackend::knn
+ *                 src/index/embedded/mod.rs:268-360 EmbeddedBackend::knn (+ :454-495 helpers)
+ *   new (absent from the reference): Hamming and MinHash-Jaccard top-k.
+ */
+#ifndef UCFP_CUDA_H
+#define UCFP_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define UCFP_API
+#else
+#define UCFP_API __attribute__((visibility("default")))
+#endif
+
+#define UCFP_ABI_VERSION 1
+
+/* ---- status codes (map onto src/error.rs:9-61 on the Rust side) ---------- */
+enum {
+    UCFP_OK = 0,
+    UCFP_E_INVALID = -1,     /* bad argument -> Error::Modality / Error::Index           */
+    UCFP_E_CUDA = -2,        /* CUDA runtime / driver failure, or no sm_100 device       */
+    UCFP_E_OOM = -3,         /* device or host allocation failed                         */
+    UCFP_E_UNSUPPORTED = -4, /* valid request this build cannot serve -> Error::Unsupported */
+    UCFP_E_STATE = -5,       /* object used in the wrong state (e.g. wrong corpus kind)  */
+    UCFP_E_CAPACITY = -6     /* append beyond the corpus capacity                        */
+};
+
+/* id returned in unused result slots (fewer than k rows matched) */
+#define UCFP_ID_NONE UINT64_MAX
+
+typedef struct ucfp_ctx ucfp_ctx;       /* one per (process, GPU) */
+typedef struct ucfp_corpus ucfp_corpus; /* one per (tenant, kind, dim): HBM-resident rows */
+
+/* ---- context -------------------------------------------------------------- */
+
+/* Binds a context to CUDA device `device`.  Fails with UCFP_E_CUDA when the
+ * device is missing or is not compute capability 10.x. */
+UCFP_API int ucfp_init(int device, ucfp_ctx **out);
+UCFP_API void ucfp_destroy(ucfp_ctx *ctx);
+/* Use the caller's cudaStream_t (passed as void*) for all subsequent work; NULL
+ * restores the context's own non-blocking stream. */
+UCFP_API int ucfp_ctx_set_stream(ucfp_ctx *ctx, void *cuda_stream);
+/* Blocks until everything enqueued by this context has finished. */
+UCFP_API int ucfp_ctx_synchronize(ucfp_ctx *ctx);
+UCFP_API int ucfp_abi_version(void);
+/* Thread-local, never NULL, valid until the next failing call on this thread. */
+UCFP_API const char *ucfp_last_error(void);
+/* Number of kernels this library has launched on `ctx` since creation (bench.py's gpu_launches). */
+UCFP_API uint64_t ucfp_ctx_kernel_launches(const ucfp_ctx *ctx);
+
+/* ---- image hashing seam ---------------------------------------------------
+ * Replaces the calls into imgfprint at src/modality/image.rs:68-70 and
+ * :175-179 AFTER host-side decode.  The host keeps: decoding, EXIF orientation,
+ * the size/dimension guards of build_image_preprocess
+ * (src/server/handlers.rs:307-319), BLAKE3 `exact`, and assembling the
+ * 168-byte ImageFingerprint / 536-byte MultiHashFingerprint structs. */
+
+enum { UCFP_ALGO_AHASH = 1u, UCFP_ALGO_PHASH = 2u, UCFP_ALGO_DHASH = 4u, UCFP_ALGO_MULTI = 7u };
+
+typedef struct ucfp_image_desc {
+    const uint8_t *pixels; /* interleaved RGB8, host or device memory      */
+    uint32_t width;        /* pixels, 4 <= width                            */
+    uint32_t height;       /* pixels, 4 <= height                           */
+    uint64_t stride;       /* bytes between rows, >= 3 * width              */
+} ucfp_image_desc;
+
+/* One algorithm's hashes for one image: the `global_hash` and `block_hashes`
+ * fields of imgfprint's ImageFingerprint (layout documented in
+ * web/src/lib/components/charts/ImageHashView.svelte:2-5).  Block 4r+c covers
+ * rows [r*h/4,(r+1)*h/4) x columns [c*w/4,(c+1)*w/4). */
+typedef struct ucfp_hash17 {
+    uint64_t global_hash;
+    uint64_t block_hashes[16];
+} ucfp_hash17;
+
+/* The three algorithms in MultiHashFingerprint order (ahash, phash, dhash;
+ * web/src/lib/components/charts/AlgorithmView.svelte:30-37).  Algorithms not
+ * selected by algo_mask are left zero. */
+typedef struct ucfp_image_hashes {
+    ucfp_hash17 ahash;
+    ucfp_hash17 phash;
+    ucfp_hash17 dhash;
+} ucfp_image_hashes; /* 408 bytes */
+
+/* Hash `n` decoded images.  `out` (n entries) and `status` (n entries, may be
+ * NULL) may be host or device memory.  A bad image (NULL pixels, dimension
+ * below 4, stride too small, or a shape the kernels cannot stage) sets its
+ * status to a UCFP_E_* code and zeroes its output without failing the batch;
+ * the call's own return value reports only batch-level failures. */
+UCFP_API int ucfp_image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *imgs, size_t n, uint32_t algo_mask,
+                                   ucfp_image_hashes *out, int32_t *status);
+
+/* Same, for `n` equally-sized images laid out `image_stride` bytes apart starting
+ * at `pixels` (the batch-ingest layout; one descriptor for the whole batch). */
+UCFP_API int ucfp_image_hash_uniform(ucfp_ctx *ctx, const uint8_t *pixels, size_t n, uint32_t width, uint32_t height,
+                                     uint64_t row_stride, uint64_t image_stride, uint32_t algo_mask,
+                                     ucfp_image_hashes *out);
+
+/* ---- corpus ---------------------------------------------------------------- */
+
+enum {
+    UCFP_KIND_HAMMING64 = 1,  /* row = one u64 code (global_hash @32 of ImageFingerprint) */
+    UCFP_KIND_MINHASH128 = 2, /* row = 128 u64 slots (payload @8 of txtfp MinHashSig<128>, src/modality/text.rs:200-204) */
+    UCFP_KIND_COSINE = 3      /* row = dim f32 (Record::embedding, src/core/mod.rs:58)     */
+};
+
+/* Allocates HBM for up to `capacity` rows.  `dim` is used by UCFP_KIND_COSINE only. */
+UCFP_API int ucfp_corpus_create(ucfp_ctx *ctx, int kind, uint32_t dim, uint64_t capacity, ucfp_corpus **out);
+UCFP_API void ucfp_corpus_destroy(ucfp_corpus *c);
+/* Appends n rows (copied).  ids == NULL means record_id = id_base + row index, where id_base is the
+ * value set by ucfp_corpus_set_id_base (default 0) -- the layout a range-sharded index uses; a corpus is
+ * either all-explicit or all-implicit.  UCFP_ID_NONE is not a valid record id. */
+UCFP_API int ucfp_corpus_append(ucfp_corpus *c, const uint64_t *ids, const void *rows, uint64_t n);
+UCFP_API int ucfp_corpus_set_id_base(ucfp_corpus *c, uint64_t id_base);
+UCFP_API int ucfp_corpus_clear(ucfp_corpus *c);
+UCFP_API uint64_t ucfp_corpus_size(const ucfp_corpus *c);
+/* Bench/test support: appends n synthetic rows generated on the device with the counter PRNG of
+ * docs/HASH_SPEC.md section 8 (row r, word j = splitmix64(seed, (start_row + r) * words_per_row + j)),
+ * implicit ids.  HAMMING64 and MINHASH128 only. */
+UCFP_API int ucfp_corpus_append_synthetic(ucfp_corpus *c, uint64_t seed, uint64_t start_row, uint64_t n);
+/* Device pointer to the resident rows (read-only view for tests/bench planting), or NULL. */
+UCFP_API void *ucfp_corpus_device_rows(ucfp_corpus *c);
+
+/* ---- scans ------------------------------------------------------------------
+ * All results are ordered best first with the total order stated; slots beyond
+ * the number of matching rows hold UCFP_ID_NONE and the sentinel given.  nq == 0
+ * or k == 0 is a successful no-op, as in EmbeddedBackend::knn
+ * (src/index/embedded/mod.rs:275). */
+
+/* dist = popcount(q ^ code); order (dist asc, record_id asc); sentinel dist = UINT32_MAX. */
+UCFP_API int ucfp_scan_hamming(ucfp_corpus *c, const uint64_t *queries, size_t nq, size_t k,
+                               uint64_t *ids_out, uint32_t *dist_out);
+/* matches = #{i < 128 : q[i] == row[i]}; order (matches desc, record_id asc); sentinel UINT32_MAX.
+ * queries = nq x 128 u64. */
+UCFP_API int ucfp_scan_jaccard(ucfp_corpus *c, const uint64_t *queries, size_t nq, size_t k,
+                               uint64_t *ids_out, uint32_t *matches_out);
+/* score = dot(q, v) / (|q| * |v|) in f32 as EmbeddedBackend::knn; order (score desc, record_id asc);
+ * rows and queries with zero norm never match (:284, :328); sentinel score = -inf.  queries = nq x dim f32. */
+UCFP_API int ucfp_scan_cosine(ucfp_corpus *c, const float *queries, size_t nq, size_t k,
+                              uint64_t *ids_out, float *score_out);
+
+/* Merges `parts` per-shard result lists (each nq x k, best first, as written by a scan) into one
+ * nq x k list under the same total order: the step after the NCCL all-gather of per-rank candidates.
+ * ids_in / keys_in are laid out [part][query][k].  descending = 0 for Hamming distances, 1 for Jaccard
+ * matches.  Every rank running this on the same gathered buffer gets byte-identical output. */
+UCFP_API int ucfp_merge_topk_u32(ucfp_ctx *ctx, const uint64_t *ids_in, const uint32_t *keys_in, size_t parts,
+                                 size_t nq, size_t k, int descending, uint64_t *ids_out, uint32_t *keys_out);
+UCFP_API int ucfp_merge_topk_f32(ucfp_ctx *ctx, const uint64_t *ids_in, const float *scores_in, size_t parts,
+                                 size_t nq, size_t k, uint64_t *ids_out, float *scores_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UCFP_CUDA_H */

@@ -1,0 +1,86 @@
+"""ctypes binding of libucfp_cuda.so -- the same C ABI (include/ucfp_cuda.h) the reference's Rust host
+binds through the `ucfp-cuda` crate (rust/ucfp-cuda/src/lib.rs).
+
+There is no CPU fallback: if the shared library is missing, or no sm_100 GPU is present when a context is
+created, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libucfp_cuda.so")
+
+OK, E_INVALID, E_CUDA, E_OOM, E_UNSUPPORTED, E_STATE, E_CAPACITY = 0, -1, -2, -3, -4, -5, -6
+KIND_HAMMING64, KIND_MINHASH128, KIND_COSINE = 1, 2, 3
+ALGO_AHASH, ALGO_PHASH, ALGO_DHASH, ALGO_MULTI = 1, 2, 4, 7
+ID_NONE = 2**64 - 1
+
+_CODE_NAMES = {E_INVALID: "UCFP_E_INVALID", E_CUDA: "UCFP_E_CUDA", E_OOM: "UCFP_E_OOM",
+               E_UNSUPPORTED: "UCFP_E_UNSUPPORTED", E_STATE: "UCFP_E_STATE", E_CAPACITY: "UCFP_E_CAPACITY"}
+
+
+class UcfpError(RuntimeError):
+    """A negative status from the C ABI.  `.code` is the UCFP_E_* value."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{_CODE_NAMES.get(code, code)}: {message}")
+        self.code = code
+        self.message = message
+
+
+class ImageDesc(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("stride", C.c_uint64)]
+
+
+# every symbol include/ucfp_cuda.h declares: name -> (restype, argtypes)
+_vp, _sz, _u64, _u32, _int = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int
+PROTOTYPES = {
+    "ucfp_init": (_int, [_int, C.POINTER(_vp)]),
+    "ucfp_destroy": (None, [_vp]),
+    "ucfp_ctx_set_stream": (_int, [_vp, _vp]),
+    "ucfp_ctx_synchronize": (_int, [_vp]),
+    "ucfp_abi_version": (_int, []),
+    "ucfp_last_error": (C.c_char_p, []),
+    "ucfp_ctx_kernel_launches": (_u64, [_vp]),
+    "ucfp_image_hash_batch": (_int, [_vp, C.POINTER(ImageDesc), _sz, _u32, _vp, _vp]),
+    "ucfp_image_hash_uniform": (_int, [_vp, _vp, _sz, _u32, _u32, _u64, _u64, _u32, _vp]),
+    "ucfp_corpus_create": (_int, [_vp, _int, _u32, _u64, C.POINTER(_vp)]),
+    "ucfp_corpus_destroy": (None, [_vp]),
+    "ucfp_corpus_append": (_int, [_vp, _vp, _vp, _u64]),
+    "ucfp_corpus_set_id_base": (_int, [_vp, _u64]),
+    "ucfp_corpus_clear": (_int, [_vp]),
+    "ucfp_corpus_size": (_u64, [_vp]),
+    "ucfp_corpus_append_synthetic": (_int, [_vp, _u64, _u64, _u64]),
+    "ucfp_corpus_device_rows": (_vp, [_vp]),
+    "ucfp_scan_hamming": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
+    "ucfp_scan_jaccard": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
+    "ucfp_scan_cosine": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
+    "ucfp_merge_topk_u32": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _int, _vp, _vp]),
+    "ucfp_merge_topk_f32": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads libucfp_cuda.so.  Raises if it has not been built -- there is nothing to fall back to."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m ucfp_b200.build` (nvcc, sm_100a). "
+                "ucfp_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)  # AttributeError if the ABI and the header drift apart
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise UcfpError(rc, lib().ucfp_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,154 @@
+// common.cuh -- shared plumbing of libucfp_cuda.so: context/corpus objects, error
+// reporting, host<->device staging.  No torch types; CUDA runtime only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ucfp_cuda.h"
+
+namespace ucfp {
+
+// ---- error reporting -------------------------------------------------------
+void set_error(const char *fmt, ...);
+
+#define UCFP_CUDA_TRY(expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::ucfp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return _e == cudaErrorMemoryAllocation ? UCFP_E_OOM : UCFP_E_CUDA;               \
+        }                                                                                    \
+    } while (0)
+
+#define UCFP_TRY(expr)              \
+    do {                            \
+        int _rc = (expr);           \
+        if (_rc != UCFP_OK) return _rc; \
+    } while (0)
+
+#define UCFP_REQUIRE(cond, code, ...)      \
+    do {                                   \
+        if (!(cond)) {                     \
+            ::ucfp::set_error(__VA_ARGS__); \
+            return (code);                 \
+        }                                  \
+    } while (0)
+
+// ---- device scratch that grows on demand -----------------------------------
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t want) {
+        if (want <= bytes) return UCFP_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; bytes = 0;
+        size_t rounded = (want + 255) & ~size_t(255);
+        UCFP_CUDA_TRY(cudaMalloc(&ptr, rounded));
+        bytes = rounded;
+        return UCFP_OK;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+struct PinnedBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t want) {
+        if (want <= bytes) return UCFP_OK;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr; bytes = 0;
+        UCFP_CUDA_TRY(cudaMallocHost(&ptr, want));
+        bytes = want;
+        return UCFP_OK;
+    }
+    void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; bytes = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+}  // namespace ucfp
+
+// ---- the opaque objects of the C ABI ----------------------------------------
+struct ucfp_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;                 // serialises entry points that share scratch
+    uint64_t launches = 0;         // kernels launched (gpu_launches in bench.py)
+    // scratch shared by all scans of this context
+    ucfp::DevBuf q_dev, out_ids_dev, out_keys_dev, cand, cand_count, qstate, flags, misc;
+    ucfp::DevBuf img_desc_dev, img_out_dev, img_status_dev, img_tables_dev, img_stage_dev;
+    ucfp::PinnedBuf pin_a, pin_b;
+};
+
+struct ucfp_corpus {
+    ucfp_ctx *ctx = nullptr;
+    int kind = 0;
+    uint32_t dim = 0;
+    uint64_t capacity = 0;
+    uint64_t size = 0;
+    uint64_t id_base = 0;
+    int id_mode = 0;               // 0 undecided, 1 explicit ids, 2 implicit (id_base + row)
+    void *rows = nullptr;          // HAMMING64: u64[cap]; MINHASH128: u64[cap][128]; COSINE: f32[cap][dim]
+    uint64_t *ids = nullptr;       // u64[cap] when id_mode == 1
+    // kind-specific side arrays
+    uint8_t *mh_sketch = nullptr;  // MINHASH128: u8[cap][128], low byte of every slot (prefilter)
+    void *cos_bf16 = nullptr;      // COSINE: bf16[cap][dim_pad] rows scaled to unit norm, for the tensor-core pass
+    float *cos_inv_norm = nullptr; // COSINE: 1/|v| in f32 (0 for zero rows)
+    uint32_t dim_pad = 0;
+};
+
+namespace ucfp {
+
+enum class Mem { Host, Device };
+
+// Classifies a user pointer.  Device = memory of ANY CUDA device or managed memory.
+inline Mem classify(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return Mem::Host; }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? Mem::Device : Mem::Host;
+}
+
+inline void count_launch(ucfp_ctx *ctx, uint64_t n = 1) { ctx->launches += n; }
+
+inline int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("kernel launch %s failed: %s", what, cudaGetErrorString(e)); return UCFP_E_CUDA; }
+    return UCFP_OK;
+}
+
+// ---- kernels-side entry points implemented in the per-path .cu files -------
+int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, uint32_t *dist_out_dev);
+int jaccard_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, uint32_t *m_out_dev);
+int jaccard_on_append(ucfp_corpus *c, uint64_t first_row, uint64_t n);
+int cosine_scan(ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, float *score_out_dev);
+int cosine_on_append(ucfp_corpus *c, uint64_t first_row, uint64_t n);
+int merge_u32(ucfp_ctx *ctx, const uint64_t *ids_in, const uint32_t *keys_in, size_t parts, size_t nq, size_t k,
+              int descending, uint64_t *ids_out, uint32_t *keys_out);
+int merge_f32(ucfp_ctx *ctx, const uint64_t *ids_in, const float *keys_in, size_t parts, size_t nq, size_t k,
+              uint64_t *ids_out, float *keys_out);
+int synth_fill_u64(ucfp_ctx *ctx, uint64_t *dst_dev, uint64_t nwords, uint64_t seed, uint64_t start_word);
+int image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *descs_host, size_t n, uint32_t algo_mask,
+                     ucfp_image_hashes *out_dev, int32_t *status_host);
+
+// splitmix64 counter PRNG of docs/HASH_SPEC.md section 8
+__host__ __device__ inline uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__host__ __device__ inline uint64_t splitmix64(uint64_t seed, uint64_t index) {
+    return mix64(seed ^ ((index + 1) * 0x9E3779B97F4A7C15ULL));
+}
+
+}  // namespace ucfp

@@ -1,0 +1,181 @@
+"""Thin object layer over the C ABI: Context (one per GPU) and Corpus (HBM-resident rows).
+
+Buffers may be numpy arrays (host) or torch CUDA tensors (device); only raw pointers cross the ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import check
+
+try:  # torch is plumbing (device memory, streams); the library itself never sees it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _ptr(buf) -> int:
+    if buf is None:
+        return 0
+    if isinstance(buf, np.ndarray):
+        if not buf.flags["C_CONTIGUOUS"]:
+            raise ValueError("buffer must be C-contiguous")
+        return buf.ctypes.data
+    if torch is not None and isinstance(buf, torch.Tensor):
+        if not buf.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return buf.data_ptr()
+    if isinstance(buf, int):
+        return buf
+    raise TypeError(f"unsupported buffer type {type(buf)}")
+
+
+def _is_device(buf) -> bool:
+    return torch is not None and isinstance(buf, torch.Tensor) and buf.is_cuda
+
+
+class Context:
+    """ucfp_ctx: binds one CUDA device.  Raises UcfpError(UCFP_E_CUDA) without an sm_100 GPU."""
+
+    def __init__(self, device: int = 0, use_torch_stream: bool = True):
+        self._L = _ffi.lib()
+        h = C.c_void_p()
+        check(self._L.ucfp_init(device, C.byref(h)))
+        self._h = h
+        self.device = device
+        if use_torch_stream and torch is not None and torch.cuda.is_available():
+            self.set_stream(torch.cuda.current_stream(device).cuda_stream)
+
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        check(self._L.ucfp_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self) -> None:
+        check(self._L.ucfp_ctx_synchronize(self._h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._L.ucfp_ctx_kernel_launches(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.ucfp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- image hashing --------------------------------------------------------------------
+    def image_hash_uniform(self, pixels, n: int, width: int, height: int, algo_mask: int = _ffi.ALGO_MULTI,
+                           row_stride: Optional[int] = None, image_stride: Optional[int] = None, out=None):
+        """n equally sized RGB8 images -> (n, 51) u64: ahash[17] | phash[17] | dhash[17]."""
+        row_stride = row_stride or 3 * width
+        image_stride = image_stride or row_stride * height
+        if out is None:
+            out = (torch.zeros((n, 51), dtype=torch.int64, device=pixels.device) if _is_device(pixels)
+                   else np.zeros((n, 51), dtype=np.uint64))
+        check(self._L.ucfp_image_hash_uniform(self._h, _ptr(pixels), n, width, height, row_stride, image_stride,
+                                              algo_mask, _ptr(out)))
+        return out
+
+    def image_hash_batch(self, images, algo_mask: int = _ffi.ALGO_MULTI) -> Tuple[np.ndarray, np.ndarray]:
+        """images: list of (h, w, 3) u8 numpy arrays (any sizes).  Returns ((n, 51) u64, (n,) i32 status)."""
+        n = len(images)
+        descs = (_ffi.ImageDesc * max(n, 1))()
+        keep = []
+        for i, im in enumerate(images):
+            if im is None:
+                descs[i] = _ffi.ImageDesc(None, 0, 0, 0)
+                continue
+            a = np.ascontiguousarray(im, dtype=np.uint8)
+            keep.append(a)
+            h, w = (a.shape[0], a.shape[1]) if a.ndim == 3 else (0, 0)
+            descs[i] = _ffi.ImageDesc(a.ctypes.data, w, h, 3 * w)
+        out = np.zeros((n, 51), dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        check(self._L.ucfp_image_hash_batch(self._h, descs, n, algo_mask, _ptr(out), _ptr(status)))
+        return out, status
+
+    # ---- merges ---------------------------------------------------------------------------
+    def merge_topk_u32(self, ids_in, keys_in, parts: int, nq: int, k: int, descending: bool, ids_out, keys_out):
+        check(self._L.ucfp_merge_topk_u32(self._h, _ptr(ids_in), _ptr(keys_in), parts, nq, k, int(descending),
+                                          _ptr(ids_out), _ptr(keys_out)))
+
+    def merge_topk_f32(self, ids_in, scores_in, parts: int, nq: int, k: int, ids_out, scores_out):
+        check(self._L.ucfp_merge_topk_f32(self._h, _ptr(ids_in), _ptr(scores_in), parts, nq, k, _ptr(ids_out),
+                                          _ptr(scores_out)))
+
+
+class Corpus:
+    """ucfp_corpus: rows of one (tenant, kind, dim) resident in HBM."""
+
+    def __init__(self, ctx: Context, kind: int, capacity: int, dim: int = 0):
+        self.ctx, self.kind, self.dim, self.capacity = ctx, kind, dim, capacity
+        self._L = ctx._L
+        h = C.c_void_p()
+        check(self._L.ucfp_corpus_create(ctx._h, kind, dim, capacity, C.byref(h)))
+        self._h = h
+
+    def __len__(self) -> int:
+        return int(self._L.ucfp_corpus_size(self._h))
+
+    def append(self, rows, ids=None) -> None:
+        n = rows.shape[0]
+        check(self._L.ucfp_corpus_append(self._h, _ptr(ids), _ptr(rows), n))
+
+    def append_synthetic(self, seed: int, start_row: int, n: int) -> None:
+        check(self._L.ucfp_corpus_append_synthetic(self._h, seed, start_row, n))
+
+    def set_id_base(self, base: int) -> None:
+        check(self._L.ucfp_corpus_set_id_base(self._h, base))
+
+    def clear(self) -> None:
+        check(self._L.ucfp_corpus_clear(self._h))
+
+    def device_rows_ptr(self) -> int:
+        return int(self._L.ucfp_corpus_device_rows(self._h) or 0)
+
+    def _outs(self, queries, nq, k, key_dtype_np, key_dtype_t, ids_out, keys_out):
+        if ids_out is None:
+            if _is_device(queries):
+                ids_out = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
+                keys_out = torch.empty((nq, k), dtype=key_dtype_t, device=queries.device)
+            else:
+                ids_out = np.empty((nq, k), dtype=np.uint64)
+                keys_out = np.empty((nq, k), dtype=key_dtype_np)
+        return ids_out, keys_out
+
+    def scan_hamming(self, queries, k: int, ids_out=None, dist_out=None):
+        nq = queries.shape[0]
+        ids_out, dist_out = self._outs(queries, nq, k, np.uint32, torch.int32 if torch else None, ids_out, dist_out)
+        check(self._L.ucfp_scan_hamming(self._h, _ptr(queries), nq, k, _ptr(ids_out), _ptr(dist_out)))
+        return ids_out, dist_out
+
+    def scan_jaccard(self, queries, k: int, ids_out=None, matches_out=None):
+        nq = queries.shape[0]
+        ids_out, matches_out = self._outs(queries, nq, k, np.uint32, torch.int32 if torch else None, ids_out, matches_out)
+        check(self._L.ucfp_scan_jaccard(self._h, _ptr(queries), nq, k, _ptr(ids_out), _ptr(matches_out)))
+        return ids_out, matches_out
+
+    def scan_cosine(self, queries, k: int, ids_out=None, score_out=None):
+        nq = queries.shape[0]
+        ids_out, score_out = self._outs(queries, nq, k, np.float32, torch.float32 if torch else None, ids_out, score_out)
+        check(self._L.ucfp_scan_cosine(self._h, _ptr(queries), nq, k, _ptr(ids_out), _ptr(score_out)))
+        return ids_out, score_out
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.ucfp_corpus_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
