@@ -69,9 +69,11 @@ typedef struct ucfp_corpus ucfp_corpus; /* one per (tenant, kind, dim): HBM-resi
  * device is missing or is not compute capability 10.x. */
 UCFP_API int ucfp_init(int device, ucfp_ctx **out);
 UCFP_API void ucfp_destroy(ucfp_ctx *ctx);
-/* Use the caller's cudaStream_t (passed as void*) for all subsequent work; NULL
- * restores the context's own non-blocking stream. */
+/* Use the caller's cudaStream_t (passed as void*) for all subsequent work.  NULL
+ * is CUDA's default stream, exactly as in the runtime API. */
 UCFP_API int ucfp_ctx_set_stream(ucfp_ctx *ctx, void *cuda_stream);
+/* Go back to the context's own non-blocking stream (the state after ucfp_init). */
+UCFP_API int ucfp_ctx_reset_stream(ucfp_ctx *ctx);
 /* Blocks until everything enqueued by this context has finished. */
 UCFP_API int ucfp_ctx_synchronize(ucfp_ctx *ctx);
 UCFP_API int ucfp_abi_version(void);
@@ -79,6 +81,16 @@ UCFP_API int ucfp_abi_version(void);
 UCFP_API const char *ucfp_last_error(void);
 /* Number of kernels this library has launched on `ctx` since creation (bench.py's gpu_launches). */
 UCFP_API uint64_t ucfp_ctx_kernel_launches(const ucfp_ctx *ctx);
+
+/* Per-kernel timing for roofline reports.  Between _begin and _end the library brackets every launch of
+ * its dominant kernels with CUDA events on the context's stream.  _end synchronises and returns, for
+ * one kernel class, the summed device time, the summed ALGORITHMIC bytes (Hamming: 8 B x rows x queries
+ * of each launch; Jaccard: 1024 B x rows x queries; image: 3*w*h + 408 B per image) or flops (cosine:
+ * 2 x rows x dim x queries) and the number of launches. */
+enum { UCFP_PROF_HAMMING_SCAN = 1, UCFP_PROF_JACCARD_SCAN = 2, UCFP_PROF_COSINE_SCAN = 3, UCFP_PROF_IMAGE_HASH = 4 };
+UCFP_API int ucfp_ctx_profile_begin(ucfp_ctx *ctx);
+UCFP_API int ucfp_ctx_profile_end(ucfp_ctx *ctx, int kernel_class, double *kernel_ms, double *alg_units,
+                                  uint64_t *launches);
 
 /* ---- image hashing seam ---------------------------------------------------
  * Replaces the calls into imgfprint at src/modality/image.rs:68-70 and

@@ -136,11 +136,14 @@ static void iscan_range(void *arg, int tid, size_t lo, size_t hi) {
             ikey_t *buf = s->partial + ((size_t)tid * s->nq + qi) * s->k;
             size_t *len = s->partial_len + (size_t)tid * s->nq + qi;
             if (s->kind == 0) {
-                uint64_t qc = s->q[qi];
+                const uint64_t qc = s->q[qi];
+                /* thr = worst key currently kept (65 while the buffer is not full): rows with d > thr cannot enter */
+                uint32_t thr = *len == s->k ? buf[s->k - 1].key : 65u;
                 for (size_t r = b; r < e; ++r) {
                     uint32_t d = (uint32_t)__builtin_popcountll(qc ^ s->rows[r]);
-                    if (*len == s->k && d > buf[s->k - 1].key) continue;
+                    if (__builtin_expect(d > thr, 1)) continue;
                     itopk_insert(buf, len, s->k, d, s->ids ? s->ids[r] : s->id_base + r);
+                    thr = *len == s->k ? buf[s->k - 1].key : 65u;
                 }
             } else {
                 const uint64_t *qs = s->q + qi * 128;

@@ -119,7 +119,13 @@ void ucfp_destroy(ucfp_ctx *ctx) {
 
 int ucfp_ctx_set_stream(ucfp_ctx *ctx, void *cuda_stream) {
     UCFP_GUARD(ctx);
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    return UCFP_OK;
+}
+
+int ucfp_ctx_reset_stream(ucfp_ctx *ctx) {
+    UCFP_GUARD(ctx);
+    ctx->stream = ctx->own_stream;
     return UCFP_OK;
 }
 
@@ -130,6 +136,36 @@ int ucfp_ctx_synchronize(ucfp_ctx *ctx) {
 }
 
 uint64_t ucfp_ctx_kernel_launches(const ucfp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static void prof_clear(ucfp_ctx *ctx) {
+    for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    ctx->prof.clear();
+}
+
+int ucfp_ctx_profile_begin(ucfp_ctx *ctx) {
+    UCFP_GUARD(ctx);
+    prof_clear(ctx);
+    ctx->profiling = true;
+    return UCFP_OK;
+}
+
+int ucfp_ctx_profile_end(ucfp_ctx *ctx, int kernel_class, double *kernel_ms, double *alg_units, uint64_t *launches) {
+    UCFP_GUARD(ctx);
+    UCFP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    double ms = 0, units = 0; uint64_t n = 0;
+    for (auto &r : ctx->prof) {
+        if (r.kind != kernel_class) continue;
+        float t = 0;
+        UCFP_CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
+        ms += t; units += r.units; n++;
+    }
+    if (kernel_ms) *kernel_ms = ms;
+    if (alg_units) *alg_units = units;
+    if (launches) *launches = n;
+    ctx->profiling = false;
+    prof_clear(ctx);
+    return UCFP_OK;
+}
 
 // ---- corpus -------------------------------------------------------------------------------
 

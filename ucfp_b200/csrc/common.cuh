@@ -85,6 +85,9 @@ struct ucfp_ctx {
     cudaStream_t stream = nullptr;
     std::mutex mu;                 // serialises entry points that share scratch
     uint64_t launches = 0;         // kernels launched (gpu_launches in bench.py)
+    bool profiling = false;        // ucfp_ctx_profile_begin/_end
+    struct ProfRec { cudaEvent_t a, b; double units; int kind; };
+    std::vector<ProfRec> prof;
     // scratch shared by all scans of this context
     ucfp::DevBuf q_dev, out_ids_dev, out_keys_dev, cand, cand_count, qstate, flags, misc;
     ucfp::DevBuf img_desc_dev, img_out_dev, img_status_dev, img_tables_dev, img_stage_dev;
@@ -120,6 +123,21 @@ inline Mem classify(const void *p) {
 }
 
 inline void count_launch(ucfp_ctx *ctx, uint64_t n = 1) { ctx->launches += n; }
+
+// Brackets one launch of a dominant kernel with events when profiling is on (no-ops otherwise).
+struct ProfScope {
+    ucfp_ctx *ctx; cudaEvent_t a = nullptr, b = nullptr; double units; int kind;
+    ProfScope(ucfp_ctx *c, int kind_, double units_) : ctx(c), units(units_), kind(kind_) {
+        if (!ctx->profiling) return;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; cudaGetLastError(); return; }
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->prof.push_back(ucfp_ctx::ProfRec{a, b, units, kind});
+    }
+};
 
 inline int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();

@@ -263,8 +263,11 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
             uint64_t ntiles = (n + kTileCodes - 1) / kTileCodes;
             uint64_t grid = (uint64_t)ctx->sm_count * scan_occ;
             if (grid > ntiles) grid = ntiles;
-            hamming_scan_kernel<<<(unsigned)grid, kScanThreads, sizeof(QSlot) * nqp, st>>>(
-                codes, ids, c->id_base, pos, n, slots, kth, nqp, cand, count, cap);
+            {
+                ProfScope ps(ctx, UCFP_PROF_HAMMING_SCAN, 8.0 * (double)n * nqp);
+                hamming_scan_kernel<<<(unsigned)grid, kScanThreads, sizeof(QSlot) * nqp, st>>>(
+                    codes, ids, c->id_base, pos, n, slots, kth, nqp, cand, count, cap);
+            }
             count_launch(ctx);
             pos += n;
             compact(pos == N);

@@ -51,7 +51,11 @@ class Context:
             self.set_stream(torch.cuda.current_stream(device).cuda_stream)
 
     def set_stream(self, cuda_stream: Optional[int]) -> None:
-        check(self._L.ucfp_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """cuda_stream: a cudaStream_t handle (0 = CUDA's default stream); None = the context's own stream."""
+        if cuda_stream is None:
+            check(self._L.ucfp_ctx_reset_stream(self._h))
+        else:
+            check(self._L.ucfp_ctx_set_stream(self._h, C.c_void_p(cuda_stream)))
 
     def synchronize(self) -> None:
         check(self._L.ucfp_ctx_synchronize(self._h))
@@ -59,6 +63,15 @@ class Context:
     @property
     def kernel_launches(self) -> int:
         return int(self._L.ucfp_ctx_kernel_launches(self._h))
+
+    def profile_begin(self) -> None:
+        check(self._L.ucfp_ctx_profile_begin(self._h))
+
+    def profile_end(self, kernel_class: int):
+        """-> (kernel_ms, algorithmic bytes or flops, launches) of one kernel class since profile_begin."""
+        ms, units, n = C.c_double(0), C.c_double(0), C.c_uint64(0)
+        check(self._L.ucfp_ctx_profile_end(self._h, kernel_class, C.byref(ms), C.byref(units), C.byref(n)))
+        return ms.value, units.value, int(n.value)
 
     def close(self) -> None:
         if getattr(self, "_h", None):
