@@ -1,6 +1,584 @@
+// image.cu -- batched perceptual hashing of decoded RGB8 images (sm_100a): the multi bundle
+// AHash + PHash + DHash, each as 1 global + 16 block hashes (docs/HASH_SPEC.md sections 1-5).
+// Replaces the calls into imgfprint at src/modality/image.rs:68-70,175-179 of the reference.
+//
+// Compiled with -fmad=false: the spec fixes separately rounded f32 multiply and add in a fixed
+// summation order, so that hash bits are identical on every implementation.
+//
+// Two kernels, one CTA per image:
+//   image_stream_kernel<CPT>  -- the fast path for ordinary shapes.  Every thread owns CPT adjacent
+//       columns and walks the image top to bottom exactly once (the only HBM traffic: 3*w*h bytes).
+//       Per pixel: integer luma, then the four vertical Triangle passes (whole->32, whole->8,
+//       block->32, block->8) as sliding accumulators in registers -- a row contributes to at most three
+//       output rows of a pass.  A finished vertical row goes to a shared-memory row buffer; at the end of
+//       each band of rows the CTA runs the horizontal passes (->32, ->9, ->8) over the buffered rows and
+//       keeps only the u8 grids (17 regions x (32x32 + 9x8 + 8x8) bytes) in shared memory.
+//   image_generic_kernel     -- any shape (tiny, up-scaling, extreme aspect, very wide): output-major
+//       passes over a gray plane in global scratch.
+// Both end in hash_regions(): 17 x {8x32 . 32x32 . 32x8 partial DCT-II, median, mean, gradient, ballot}.
+#include <map>
+
 #include "common.cuh"
+#include "dct_table.h"
+
 namespace ucfp {
-int image_hash_batch(ucfp_ctx *, const ucfp_image_desc *, size_t, uint32_t, ucfp_image_hashes *, int32_t *) {
-    set_error("image hashing not built yet"); return UCFP_E_UNSUPPORTED;
+namespace {
+
+__constant__ float c_dct_cos[8][32] = { UCFP_DCT_VALUES };  // same literals as the host table
+
+constexpr int kRegions = 17;                 // whole image + 4x4 blocks
+constexpr int kHOuts = 49;                   // 32 + 9 + 8 horizontal outputs per region column set
+constexpr int kVOuts = 40;                   // 32 + 8 vertical outputs per region row set
+constexpr size_t kRowBufBudget = 64 * 1024;  // bytes of shared memory for buffered vertical rows
+constexpr int kMaxBandRows = 64;
+
+struct Taps { int left, n, woff; };                         // one output sample of a 1-D Triangle pass
+struct __align__(16) VEntry { float w[3]; uint8_t n_active, n_finish; uint16_t pad; };
+struct FinDesc { uint8_t stream, o, r, pad; };               // stream: 0 whole->32, 1 whole->8, 2 block->32, 3 block->8
+
+struct ShapeDev {
+    int w, h;
+    int by[5], bx[5];
+    const Taps *hout;      // [5][49]: column set 0 = whole width, 1 + c = block column c; absolute x
+    const Taps *vout;      // [5][40]: row set 0 = whole height, 1 + r = block row r; absolute y
+    const float *wts;
+    const VEntry *vtab;    // [4][h] (stream kernel)
+    const FinDesc *fin;    // finished rows in emission order
+    const int *band_off;   // [nbands + 1] into fin
+    int band_rows, nbands, max_fin;
+};
+
+struct ImgDev { const uint8_t *pixels; uint64_t stride; uint32_t out_index; uint32_t aligned4; };
+
+// ---------------------------------------------------------------------------------------------
+// Host: tap tables.  Same f32 arithmetic as `image` 0.25 imageops::sample (spec section 2).
+// ---------------------------------------------------------------------------------------------
+struct HostTaps { int left, n; std::vector<float> w; };
+
+std::vector<HostTaps> make_taps(int src, int dst) {
+    std::vector<HostTaps> t(dst);
+    volatile float ratio = (float)src / (float)dst;  // volatile: keep every step rounded to binary32
+    float sratio = ratio < 1.0f ? 1.0f : ratio;
+    float support = 1.0f * sratio;
+    for (int o = 0; o < dst; ++o) {
+        volatile float in = ((float)o + 0.5f) * ratio;
+        long long left = (long long)floorf(in - support);
+        if (left < 0) left = 0;
+        if (left > src - 1) left = src - 1;
+        long long right = (long long)ceilf(in + support);
+        if (right < left + 1) right = left + 1;
+        if (right > src) right = src;
+        volatile float inc = in - 0.5f;
+        int n = (int)(right - left);
+        t[o].left = (int)left; t[o].n = n; t[o].w.resize(n);
+        volatile float sum = 0.0f;
+        for (int i = 0; i < n; ++i) {
+            volatile float x = ((float)(left + i) - inc) / sratio;
+            float a = fabsf(x);
+            float wv = a < 1.0f ? 1.0f - a : 0.0f;
+            t[o].w[i] = wv;
+            sum = sum + wv;
+        }
+        for (int i = 0; i < n; ++i) { volatile float q = t[o].w[i] / sum; t[o].w[i] = q; }
+    }
+    return t;
 }
+
+struct ShapeTables {
+    ShapeDev dev{};
+    void *blob = nullptr;
+    bool streamable = false;
+    int threads = 0, cpt = 0;
+    size_t stream_smem = 0;
+};
+
+struct ShapeCache { std::map<uint64_t, ShapeTables> m; };
+std::map<ucfp_ctx *, ShapeCache> g_cache;  // guarded by ctx->mu (every caller holds it)
+
+int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
+    std::vector<Taps> hout(5 * kHOuts), vout(5 * kVOuts);
+    std::vector<float> wts;
+    ShapeDev &d = st.dev;
+    d.w = w; d.h = h;
+    for (int i = 0; i <= 4; ++i) { d.by[i] = (int)((long long)i * h / 4); d.bx[i] = (int)((long long)i * w / 4); }
+    auto emit = [&](std::vector<Taps> &dst, int base, const std::vector<HostTaps> &t, int offset) {
+        for (size_t o = 0; o < t.size(); ++o) {
+            dst[base + o] = Taps{t[o].left + offset, t[o].n, (int)wts.size()};
+            wts.insert(wts.end(), t[o].w.begin(), t[o].w.end());
+        }
+    };
+    // vertical tap sets (also the source of the streaming tables)
+    std::vector<std::vector<HostTaps>> vsets(10);  // [set][0: ->32, 1: ->8]
+    for (int s = 0; s < 5; ++s) {
+        int y0 = s == 0 ? 0 : d.by[s - 1], len = s == 0 ? h : d.by[s] - d.by[s - 1];
+        vsets[2 * s] = make_taps(len, 32);
+        vsets[2 * s + 1] = make_taps(len, 8);
+        emit(vout, s * kVOuts, vsets[2 * s], y0);
+        emit(vout, s * kVOuts + 32, vsets[2 * s + 1], y0);
+    }
+    for (int s = 0; s < 5; ++s) {
+        int x0 = s == 0 ? 0 : d.bx[s - 1], len = s == 0 ? w : d.bx[s] - d.bx[s - 1];
+        emit(hout, s * kHOuts, make_taps(len, 32), x0);
+        emit(hout, s * kHOuts + 32, make_taps(len, 9), x0);
+        emit(hout, s * kHOuts + 41, make_taps(len, 8), x0);
+    }
+
+    // ---- streaming tables: per row and pass, the <= 3 active outputs and how many finish
+    std::vector<VEntry> vtab((size_t)4 * h);
+    std::vector<FinDesc> fin_rows;
+    std::vector<int> fin_row_y;
+    bool ok = w >= 32 && h >= 32;
+    for (int stream = 0; stream < 4 && ok; ++stream) {
+        for (int seg = 0; seg < (stream < 2 ? 1 : 4) && ok; ++seg) {
+            int set = stream < 2 ? 0 : 1 + seg;
+            const std::vector<HostTaps> &t = vsets[2 * set + (stream & 1)];
+            int y0 = set == 0 ? 0 : d.by[set - 1], len = set == 0 ? h : d.by[set] - d.by[set - 1];
+            int nout = (int)t.size();
+            for (int o = 1; o < nout; ++o)  // windows must advance monotonically
+                if (t[o].left < t[o - 1].left || t[o].left + t[o].n < t[o - 1].left + t[o - 1].n) ok = false;
+            int o0 = 0;
+            for (int yl = 0; yl < len && ok; ++yl) {
+                while (o0 < nout && t[o0].left + t[o0].n <= yl) o0++;
+                VEntry e{};
+                int n = 0;
+                for (int o = o0; o < nout && t[o].left <= yl; ++o) {
+                    if (n == 3) { ok = false; break; }
+                    e.w[n++] = t[o].w[yl - t[o].left];
+                }
+                // every output below the active range must already be complete, and active ones contiguous
+                for (int o = o0; o < o0 + n; ++o) if (!(t[o].left <= yl && yl < t[o].left + t[o].n)) ok = false;
+                int nf = 0;
+                for (int o = o0; o < o0 + n; ++o) if (t[o].left + t[o].n - 1 == yl) nf++;
+                for (int j = 0; j < nf; ++j) if (t[o0 + j].left + t[o0 + j].n - 1 != yl) ok = false;  // lowest finish first
+                e.n_active = (uint8_t)n; e.n_finish = (uint8_t)nf;
+                vtab[(size_t)stream * h + y0 + yl] = e;
+            }
+            if (ok) {  // every output must start no earlier than all lower outputs are accounted for
+                for (int o = 0; o < nout; ++o) if (t[o].n < 1) ok = false;
+            }
+        }
+    }
+    std::vector<int> band_off;
+    int band_rows = 0, max_fin = 0;
+    if (ok) {
+        // emission order: y ascending, stream ascending, finishing outputs ascending
+        std::vector<int> next_out(4 * 5, 0);
+        for (int y = 0; y < h; ++y)
+            for (int stream = 0; stream < 4; ++stream) {
+                int r = 0;
+                if (stream >= 2) { while (r < 3 && y >= d.by[r + 1]) r++; }
+                int key = stream * 5 + (stream >= 2 ? 1 + r : 0);
+                for (int f = 0; f < vtab[(size_t)stream * h + y].n_finish; ++f) {
+                    fin_rows.push_back(FinDesc{(uint8_t)stream, (uint8_t)next_out[key]++, (uint8_t)r, 0});
+                    fin_row_y.push_back(y);
+                }
+            }
+        if ((int)fin_rows.size() != 32 + 8 + 4 * 40) ok = false;
+        for (int cand = kMaxBandRows; cand >= 1 && ok; cand >>= 1) {
+            int nb = (h + cand - 1) / cand, mx = 0;
+            std::vector<int> cnt(nb, 0);
+            for (int y : fin_row_y) cnt[y / cand]++;
+            for (int c : cnt) mx = c > mx ? c : mx;
+            if ((size_t)mx * w * 4 <= kRowBufBudget || cand == 1) {
+                if ((size_t)mx * w * 4 > kRowBufBudget) { ok = false; break; }
+                band_rows = cand; max_fin = mx;
+                band_off.assign(nb + 1, 0);
+                for (int b = 0; b < nb; ++b) band_off[b + 1] = band_off[b] + cnt[b];
+                break;
+            }
+        }
+    }
+    int cpt = w <= 512 ? 1 : (w <= 1024 ? 4 : 8);
+    int threads = ((w + cpt - 1) / cpt + 31) / 32 * 32;
+    if (threads > 512) ok = false;  // wider than 4096 px: generic kernel
+    if (threads < 128) threads = 128;
+    st.streamable = ok; st.threads = threads; st.cpt = cpt;
+
+    // ---- upload one blob
+    auto align16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+    size_t off_h = 0, off_v = align16(off_h + hout.size() * sizeof(Taps)), off_w = align16(off_v + vout.size() * sizeof(Taps));
+    size_t off_t = align16(off_w + wts.size() * 4), off_f = align16(off_t + (ok ? vtab.size() * sizeof(VEntry) : 0));
+    size_t off_b = align16(off_f + (ok ? fin_rows.size() * sizeof(FinDesc) : 0));
+    size_t total = align16(off_b + (ok ? band_off.size() * 4 : 0)) + 16;
+    std::vector<uint8_t> host(total, 0);
+    memcpy(&host[off_h], hout.data(), hout.size() * sizeof(Taps));
+    memcpy(&host[off_v], vout.data(), vout.size() * sizeof(Taps));
+    memcpy(&host[off_w], wts.data(), wts.size() * 4);
+    if (ok) {
+        memcpy(&host[off_t], vtab.data(), vtab.size() * sizeof(VEntry));
+        memcpy(&host[off_f], fin_rows.data(), fin_rows.size() * sizeof(FinDesc));
+        memcpy(&host[off_b], band_off.data(), band_off.size() * 4);
+    }
+    UCFP_CUDA_TRY(cudaMalloc(&st.blob, total));
+    UCFP_CUDA_TRY(cudaMemcpyAsync(st.blob, host.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+    UCFP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // `host` dies at return
+    uint8_t *b = static_cast<uint8_t *>(st.blob);
+    d.hout = reinterpret_cast<const Taps *>(b + off_h);
+    d.vout = reinterpret_cast<const Taps *>(b + off_v);
+    d.wts = reinterpret_cast<const float *>(b + off_w);
+    d.vtab = ok ? reinterpret_cast<const VEntry *>(b + off_t) : nullptr;
+    d.fin = ok ? reinterpret_cast<const FinDesc *>(b + off_f) : nullptr;
+    d.band_off = ok ? reinterpret_cast<const int *>(b + off_b) : nullptr;
+    d.band_rows = band_rows; d.nbands = ok ? (h + band_rows - 1) / band_rows : 0; d.max_fin = max_fin;
+    return UCFP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Device: shared pieces
+// ---------------------------------------------------------------------------------------------
+struct RegionGrids {         // shared memory, per CTA
+    uint8_t g32[kRegions][1024];
+    uint8_t g98[kRegions][72];
+    uint8_t g8[kRegions][64];
+    float R[kRegions][32][8];
+    float D[kRegions][64];
+    float C[8][32];
+    float med_lo[kRegions], med_hi[kRegions];
+};
+
+__device__ __forceinline__ uint32_t luma_u8(uint32_t r, uint32_t g, uint32_t b) {
+    // `image` 0.25 rgb_to_luma: (2126 R + 7152 G + 722 B) / 10000, truncating.  The sum is < 2^22, for
+    // which floor(s / 10000) == (s * 429497) >> 32 exactly (error s * 2704 / 2^32 / 10000 < 1e-4).
+    uint32_t s = 2126u * r + 7152u * g + 722u * b;
+    return __umulhi(s, 429497u);
+}
+
+// One output of a horizontal pass over a row of f32 vertical sums: sequential sum, clamp, round half away.
+__device__ __forceinline__ uint8_t hsample(const float *row, Taps t, const float *__restrict__ wts) {
+    float acc = 0.0f;
+    const float *wp = wts + t.woff;
+    const float *rp = row + t.left;
+    for (int i = 0; i < t.n; ++i) acc = acc + rp[i] * __ldg(wp + i);
+    acc = acc < 0.0f ? 0.0f : acc;
+    acc = acc > 255.0f ? 255.0f : acc;
+    float fl = truncf(acc);
+    if (acc - fl >= 0.5f) fl += 1.0f;
+    return (uint8_t)fl;
+}
+
+// Horizontal passes for one finished vertical row.  `item` enumerates the outputs of that row:
+// whole->32 rows: 32 items; whole->8 rows: 9 + 8; block rows: x4 block columns.
+__device__ __forceinline__ int fin_items(int stream) { return stream == 0 ? 32 : stream == 1 ? 17 : stream == 2 ? 128 : 68; }
+
+__device__ __forceinline__ void hpass_item(RegionGrids &G, const ShapeDev &S, FinDesc f, int item, const float *row) {
+    int colset = 0, sub = item;
+    if (f.stream >= 2) { int per = f.stream == 2 ? 32 : 17; colset = 1 + item / per; sub = item % per; }
+    int region = f.stream < 2 ? 0 : 1 + 4 * f.r + (colset - 1);
+    const Taps *ho = S.hout + colset * kHOuts;
+    if ((f.stream & 1) == 0) {
+        G.g32[region][f.o * 32 + sub] = hsample(row, ho[sub], S.wts);
+    } else if (sub < 9) {
+        G.g98[region][f.o * 9 + sub] = hsample(row, ho[32 + sub], S.wts);
+    } else {
+        G.g8[region][f.o * 8 + (sub - 9)] = hsample(row, ho[41 + (sub - 9)], S.wts);
+    }
+}
+
+// PHash / AHash / DHash of the 17 regions from the u8 grids in shared memory (spec sections 3-5).
+__device__ void hash_regions(RegionGrids &G, uint32_t algo_mask, uint64_t *out /* 51 words */) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < 256; i += nt) G.C[i >> 5][i & 31] = c_dct_cos[i >> 5][i & 31];
+    __syncthreads();
+    if (algo_mask & UCFP_ALGO_PHASH) {
+        for (int it = tid; it < kRegions * 256; it += nt) {       // R[y][v] = sum_x g[y][x] * C[v][x]
+            int reg = it >> 8, y = (it >> 3) & 31, v = it & 7;
+            const uint8_t *g = &G.g32[reg][y * 32];
+            float t = 0.0f;
+#pragma unroll 8
+            for (int x = 0; x < 32; ++x) t = t + (float)g[x] * G.C[v][x];
+            G.R[reg][y][v] = t;
+        }
+        __syncthreads();
+        for (int it = tid; it < kRegions * 64; it += nt) {        // D[u][v] = sum_y C[u][y] * R[y][v]
+            int reg = it >> 6, u = (it >> 3) & 7, v = it & 7;
+            float t = 0.0f;
+#pragma unroll 8
+            for (int y = 0; y < 32; ++y) t = t + G.C[u][y] * G.R[reg][y][v];
+            G.D[reg][it & 63] = t;
+        }
+        __syncthreads();
+        for (int it = tid; it < kRegions * 64; it += nt) {        // ranks 31 and 32 of the 64 coefficients
+            int reg = it >> 6, i = it & 63;
+            float val = G.D[reg][i];
+            int rank = 0;
+            for (int j = 0; j < 64; ++j) { float o = G.D[reg][j]; rank += (o < val) || (o == val && j < i); }
+            if (rank == 31) G.med_lo[reg] = val;
+            if (rank == 32) G.med_hi[reg] = val;
+        }
+        __syncthreads();
+    }
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+    for (int reg = warp; reg < kRegions; reg += nwarps) {
+        uint64_t a = 0, p = 0, dh = 0;
+        if (algo_mask & UCFP_ALGO_AHASH) {
+            uint32_t v0 = G.g8[reg][lane], v1 = G.g8[reg][lane + 32];
+            uint32_t sum = v0 + v1;
+            for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+            uint32_t lo = __ballot_sync(0xffffffffu, 64u * v0 > sum), hi = __ballot_sync(0xffffffffu, 64u * v1 > sum);
+            a = (uint64_t)hi << 32 | lo;
+        }
+        if (algo_mask & UCFP_ALGO_PHASH) {
+            float med = (G.med_lo[reg] + G.med_hi[reg]) * 0.5f;
+            uint32_t lo = __ballot_sync(0xffffffffu, G.D[reg][lane] > med), hi = __ballot_sync(0xffffffffu, G.D[reg][lane + 32] > med);
+            p = (uint64_t)hi << 32 | lo;
+        }
+        if (algo_mask & UCFP_ALGO_DHASH) {
+            int i0 = lane, i1 = lane + 32;  // bit 8r+c compares g[r][c] > g[r][c+1] on the 9-wide grid
+            const uint8_t *g = G.g98[reg];
+            uint32_t lo = __ballot_sync(0xffffffffu, g[(i0 >> 3) * 9 + (i0 & 7)] > g[(i0 >> 3) * 9 + (i0 & 7) + 1]);
+            uint32_t hi = __ballot_sync(0xffffffffu, g[(i1 >> 3) * 9 + (i1 & 7)] > g[(i1 >> 3) * 9 + (i1 & 7) + 1]);
+            dh = (uint64_t)hi << 32 | lo;
+        }
+        if (lane == 0) { out[reg] = a; out[17 + reg] = p; out[34 + reg] = dh; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic kernel: gray plane and vertical sums in global scratch, output-major everywhere.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+image_generic_kernel(ShapeDev S, const ImgDev *__restrict__ imgs, uint32_t n, uint32_t algo_mask, uint8_t *scratch,
+                     size_t scratch_per_cta, uint64_t *out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RegionGrids &G = *reinterpret_cast<RegionGrids *>(smem_raw);
+    const int w = S.w, h = S.h, tid = threadIdx.x, nt = blockDim.x;
+    uint8_t *gray = scratch + (size_t)blockIdx.x * scratch_per_cta;
+    float *T = reinterpret_cast<float *>(gray + (((size_t)w * h + 15) & ~size_t(15)));  // [5][40][w]
+    for (uint32_t im = blockIdx.x; im < n; im += gridDim.x) {
+        const ImgDev I = imgs[im];
+        for (size_t p = tid; p < (size_t)w * h; p += nt) {
+            int y = (int)(p / w), x = (int)(p % w);
+            const uint8_t *px = I.pixels + (size_t)y * I.stride + 3 * (size_t)x;
+            gray[p] = (uint8_t)luma_u8(px[0], px[1], px[2]);
+        }
+        __syncthreads();
+        for (size_t it = tid; it < (size_t)5 * kVOuts * w; it += nt) {   // vertical passes
+            int x = (int)(it % w), vo = (int)(it / w);
+            Taps t = S.vout[vo];
+            float acc = 0.0f;
+            for (int i = 0; i < t.n; ++i) acc = acc + (float)gray[(size_t)(t.left + i) * w + x] * __ldg(S.wts + t.woff + i);
+            T[it] = acc;
+        }
+        __syncthreads();
+        for (int it = tid; it < 5 * kVOuts * 128; it += nt) {             // horizontal passes
+            int vo = it >> 7, item = it & 127, set = vo / kVOuts, o = vo % kVOuts;
+            FinDesc f;
+            f.stream = (uint8_t)((set ? 2 : 0) + (o >= 32 ? 1 : 0));
+            f.o = (uint8_t)(o >= 32 ? o - 32 : o);
+            f.r = (uint8_t)(set ? set - 1 : 0); f.pad = 0;
+            if (item < fin_items(f.stream)) hpass_item(G, S, f, item, T + (size_t)vo * w);
+        }
+        __syncthreads();
+        hash_regions(G, algo_mask, out + (size_t)I.out_index * 51);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streaming kernel: one pass over the pixels, vertical sums in registers.
+// ---------------------------------------------------------------------------------------------
+template <int CPT, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+image_stream_kernel(ShapeDev S, const ImgDev *__restrict__ imgs, uint32_t algo_mask, uint64_t *out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RegionGrids &G = *reinterpret_cast<RegionGrids *>(smem_raw);
+    float *rowbuf = reinterpret_cast<float *>(smem_raw + ((sizeof(RegionGrids) + 15) & ~size_t(15)));  // [max_fin][w]
+    const int w = S.w, h = S.h, tid = threadIdx.x, nt = blockDim.x;
+    const ImgDev I = imgs[blockIdx.x];
+    const int x0 = tid * CPT;
+    const bool have = x0 < w;
+
+    float acc[4][3][CPT];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) acc[s][j][c] = 0.0f;
+
+    for (int band = 0; band < S.nbands; ++band) {
+        const int y_lo = band * S.band_rows, y_hi = min(h, y_lo + S.band_rows);
+        int slot = 0;
+        if (have) {
+            for (int y = y_lo; y < y_hi; ++y) {
+                float v[CPT];
+                const uint8_t *px = I.pixels + (size_t)y * I.stride + 3 * (size_t)x0;
+                if (CPT % 4 == 0 && I.aligned4 && x0 + CPT <= w) {
+                    const uint32_t *p32 = reinterpret_cast<const uint32_t *>(px);
+#pragma unroll
+                    for (int g = 0; g < CPT / 4; ++g) {  // 4 pixels = 12 bytes = 3 words
+                        uint32_t a = __ldg(p32 + 3 * g), b = __ldg(p32 + 3 * g + 1), c2 = __ldg(p32 + 3 * g + 2);
+                        v[(4 * g) % CPT] = (float)luma_u8(a & 255u, (a >> 8) & 255u, (a >> 16) & 255u);
+                        v[(4 * g + 1) % CPT] = (float)luma_u8(a >> 24, b & 255u, (b >> 8) & 255u);
+                        v[(4 * g + 2) % CPT] = (float)luma_u8((b >> 16) & 255u, b >> 24, c2 & 255u);
+                        v[(4 * g + 3) % CPT] = (float)luma_u8((c2 >> 8) & 255u, (c2 >> 16) & 255u, c2 >> 24);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) {
+                        v[c] = 0.0f;
+                        if (x0 + c < w) v[c] = (float)luma_u8(__ldg(px + 3 * c), __ldg(px + 3 * c + 1), __ldg(px + 3 * c + 2));
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(S.vtab + (size_t)s * h + y));  // uniform
+                    const float w0 = __uint_as_float(raw.x), w1 = __uint_as_float(raw.y), w2 = __uint_as_float(raw.z);
+                    const int n_active = raw.w & 255, n_finish = (raw.w >> 8) & 255;
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) {
+                        acc[s][0][c] = acc[s][0][c] + v[c] * w0;
+                        acc[s][1][c] = acc[s][1][c] + v[c] * w1;
+                    }
+                    if (n_active == 3) {
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) acc[s][2][c] = acc[s][2][c] + v[c] * w2;
+                    }
+                    for (int f = 0; f < n_finish; ++f) {  // uniform: the lowest active output of this pass is complete
+                        float *dst = rowbuf + (size_t)slot * w + x0;
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) {
+                            if (x0 + c < w) dst[c] = acc[s][0][c];
+                            acc[s][0][c] = acc[s][1][c]; acc[s][1][c] = acc[s][2][c]; acc[s][2][c] = 0.0f;
+                        }
+                        slot++;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // horizontal passes over the rows finished in this band
+        const int f_lo = S.band_off[band], f_hi = S.band_off[band + 1];
+        int base = 0;
+        for (int fi = f_lo; fi < f_hi; ++fi) {
+            const FinDesc f = S.fin[fi];
+            const int items = fin_items(f.stream);
+            // threads [base, base + items) modulo nt take this row's outputs: rows of a band run side by side
+            for (int it = (tid - base % nt + nt) % nt; it < items; it += nt)
+                hpass_item(G, S, f, it, rowbuf + (size_t)(fi - f_lo) * w);
+            base += items;
+        }
+        __syncthreads();
+    }
+    hash_regions(G, algo_mask, out + (size_t)I.out_index * 51);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Host driver
+// ---------------------------------------------------------------------------------------------
+int image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *descs, size_t n, uint32_t algo_mask, ucfp_image_hashes *out_dev,
+                     int32_t *status) {
+    cudaStream_t st = ctx->stream;
+    UCFP_CUDA_TRY(cudaMemsetAsync(out_dev, 0, sizeof(ucfp_image_hashes) * n, st));
+    static_assert(sizeof(ucfp_image_hashes) == 51 * 8, "bundle layout");
+
+    // ---- validate, stage host pixels, group by shape
+    struct Item { size_t idx; const uint8_t *dev_pixels; uint64_t stride; };
+    std::map<uint64_t, std::vector<Item>> groups;
+    size_t stage_bytes = 0;
+    std::vector<size_t> stage_off(n, SIZE_MAX);
+    std::vector<uint64_t> pitch(n, 0);
+    for (size_t i = 0; i < n; ++i) {
+        const ucfp_image_desc &d = descs[i];
+        status[i] = UCFP_OK;
+        if (!d.pixels || d.width < 4 || d.height < 4 || d.stride < 3ull * d.width || d.width > 65535 || d.height > 65535) {
+            status[i] = UCFP_E_INVALID;
+            continue;
+        }
+        if (classify(d.pixels) != Mem::Device) {
+            pitch[i] = (3ull * d.width + 15) & ~15ull;
+            stage_off[i] = stage_bytes;
+            stage_bytes += pitch[i] * d.height;
+        }
+    }
+    const size_t kStageLimit = size_t(3) << 30;  // larger host batches are hashed in slices
+    if (stage_bytes > kStageLimit && n > 1) {
+        size_t half = n / 2;
+        UCFP_TRY(image_hash_batch(ctx, descs, half, algo_mask, out_dev, status));
+        UCFP_CUDA_TRY(cudaStreamSynchronize(st));
+        return image_hash_batch(ctx, descs + half, n - half, algo_mask, out_dev + half, status + half);
+    }
+    if (stage_bytes) UCFP_TRY(ctx->img_stage_dev.reserve(stage_bytes));
+    for (size_t i = 0; i < n; ++i) {
+        if (status[i] != UCFP_OK) continue;
+        const ucfp_image_desc &d = descs[i];
+        Item it{i, d.pixels, d.stride};
+        if (stage_off[i] != SIZE_MAX) {
+            uint8_t *dst = ctx->img_stage_dev.as<uint8_t>() + stage_off[i];
+            // runs of tightly packed, contiguous host images of one shape go up as a single 2-D copy
+            size_t run = 1;
+            if (d.stride == 3ull * d.width) {
+                while (i + run < n && status[i + run] == UCFP_OK && stage_off[i + run] != SIZE_MAX &&
+                       descs[i + run].width == d.width && descs[i + run].height == d.height &&
+                       descs[i + run].stride == d.stride &&
+                       descs[i + run].pixels == d.pixels + run * d.stride * d.height)
+                    run++;
+            }
+            UCFP_CUDA_TRY(cudaMemcpy2DAsync(dst, pitch[i], d.pixels, d.stride, 3ull * d.width, (size_t)d.height * run,
+                                            cudaMemcpyHostToDevice, st));
+            for (size_t j = 0; j < run; ++j) {
+                Item jt{i + j, dst + j * pitch[i] * d.height, pitch[i]};
+                groups[(uint64_t)d.width << 32 | d.height].push_back(jt);
+            }
+            i += run - 1;
+            continue;
+        }
+        groups[(uint64_t)d.width << 32 | d.height].push_back(it);
+    }
+
+    ShapeCache &cache = g_cache[ctx];
+    for (auto &kv : groups) {
+        const int w = (int)(kv.first >> 32), h = (int)(kv.first & 0xffffffffu);
+        auto found = cache.m.find(kv.first);
+        if (found == cache.m.end()) {
+            ShapeTables stb;
+            UCFP_TRY(build_shape(ctx, w, h, stb));
+            found = cache.m.emplace(kv.first, stb).first;
+        }
+        ShapeTables &T = found->second;
+        std::vector<Item> &items = kv.second;
+        std::vector<ImgDev> hostdesc(items.size());
+        for (size_t j = 0; j < items.size(); ++j) {
+            bool al = ((uintptr_t)items[j].dev_pixels % 4 == 0) && (items[j].stride % 4 == 0);
+            hostdesc[j] = ImgDev{items[j].dev_pixels, items[j].stride, (uint32_t)items[j].idx, al ? 1u : 0u};
+        }
+        // one descriptor buffer per group: the copy below must finish before the vector dies
+        DevBuf descbuf;
+        UCFP_TRY(descbuf.reserve(sizeof(ImgDev) * items.size()));
+        UCFP_CUDA_TRY(cudaMemcpyAsync(descbuf.ptr, hostdesc.data(), sizeof(ImgDev) * items.size(), cudaMemcpyHostToDevice, st));
+        uint64_t *out_words = reinterpret_cast<uint64_t *>(out_dev);
+        double units = (3.0 * w * h + 408.0) * (double)items.size();
+        if (T.streamable) {
+            size_t smem = ((sizeof(RegionGrids) + 15) & ~size_t(15)) + (size_t)T.dev.max_fin * w * 4;
+            ProfScope ps(ctx, UCFP_PROF_IMAGE_HASH, units);
+            auto launch = [&](auto kern) -> int {
+                UCFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+                kern<<<(unsigned)items.size(), T.threads, smem, st>>>(T.dev, descbuf.as<ImgDev>(), algo_mask, out_words);
+                return UCFP_OK;
+            };
+            if (T.cpt == 1) UCFP_TRY(launch(image_stream_kernel<1, 512>));
+            else if (T.cpt == 4) UCFP_TRY(launch(image_stream_kernel<4, 256>));
+            else UCFP_TRY(launch(image_stream_kernel<8, 512>));
+        } else {
+            size_t per = (((size_t)w * h + 15) & ~size_t(15)) + (size_t)5 * kVOuts * w * 4 + 256;
+            size_t grid = items.size();
+            size_t budget = size_t(1) << 30;
+            if (grid * per > budget) grid = budget / per ? budget / per : 1;
+            if (grid > (size_t)ctx->sm_count * 4) grid = (size_t)ctx->sm_count * 4;
+            UCFP_TRY(ctx->img_tables_dev.reserve(grid * per));
+            UCFP_CUDA_TRY(cudaFuncSetAttribute(image_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionGrids)));
+            ProfScope ps(ctx, UCFP_PROF_IMAGE_HASH, units);
+            image_generic_kernel<<<(unsigned)grid, 256, sizeof(RegionGrids), st>>>(T.dev, descbuf.as<ImgDev>(), (uint32_t)items.size(),
+                                                                                  algo_mask, ctx->img_tables_dev.as<uint8_t>(), per, out_words);
+        }
+        count_launch(ctx);
+        UCFP_TRY(check_launch("image hash"));
+        UCFP_CUDA_TRY(cudaStreamSynchronize(st));  // descbuf and hostdesc are released here
+        descbuf.release();
+    }
+    return UCFP_OK;
+}
+
+}  // namespace ucfp
