@@ -140,8 +140,8 @@ def main() -> int:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--codes", type=float, default=1e9, help="total corpus rows over all ranks")
     ap.add_argument("--queries", type=int, default=1024)
-    ap.add_argument("--cpu-sample-rows", type=float, default=1e8)
-    ap.add_argument("--cpu-sample-queries", type=int, default=128)
+    ap.add_argument("--cpu-sample-rows", type=float, default=2e8)
+    ap.add_argument("--cpu-sample-queries", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -291,7 +291,9 @@ def main() -> int:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = k_bytes / (k_ms / 1e3) / 1e9 if k_ms else None
     traffic_path = os.path.join(ROOT, "profiles", "hamming_scan_traffic.json")
-    traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch") if os.path.exists(traffic_path) else None
+    # ncu-measured DRAM bytes per scanned row (profiles/), scaled to this run's rows per launch
+    traffic = (json.load(open(traffic_path))["dram_bytes_per_row"] * shard * args.steps / k_n
+               if os.path.exists(traffic_path) and k_n else None)
 
     if rank == 0:
         cb = None
