@@ -18,7 +18,7 @@
 //   compact   after every chunk (tightens thr); the last one writes the results.
 // A list that overflows its capacity (adversarial duplicates with descending ids) is
 // flagged; flagged queries are recomputed by the exact multi-pass selection in
-// hamming_exact.cuh (histogram of distances + radix select on ids), so the result is
+// topk_select.cuh (histogram of distances + radix select on ids), so the result is
 // exact for every input.
 #include <cooperative_groups.h>
 
@@ -28,12 +28,13 @@ namespace ucfp {
 
 namespace {
 
+#include "topk_select.cuh"
+
 constexpr int kScanThreads = 256;
 constexpr int kCodesPerThread = 8;                 // 4 x LDG.128 in flight per thread
 constexpr int kTileCodes = kScanThreads * kCodesPerThread;
 constexpr uint32_t kSeedRows = 2048;               // multiple of 2 (keeps 16-byte alignment of chunk starts)
 constexpr uint32_t kMaxQueriesPerPass = 2048;      // 16 B/query of shared memory
-constexpr uint64_t kRowMask = (1ULL << 40) - 1;    // candidate = dist << 40 | row
 constexpr uint64_t kMaxChunkRows = 1ULL << 28;
 
 struct __align__(16) QSlot { uint32_t lo, hi, thr, pad; };
@@ -138,67 +139,17 @@ hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restri
     }
 }
 
-__device__ __forceinline__ bool cand_before(uint64_t dra, uint64_t ida, uint64_t drb, uint64_t idb) {
-    uint32_t da = (uint32_t)(dra >> 40), db = (uint32_t)(drb >> 40);
-    return da < db || (da == db && ida < idb);
-}
-
-// One CTA per query: sort the candidate list by (dist, id), keep k, publish the new threshold.
-__global__ void hamming_compact_kernel(uint64_t *cand, uint32_t *count, uint32_t cap, uint32_t k,
-                                       const uint64_t *__restrict__ ids, uint64_t id_base, QSlot *slots,
-                                       uint64_t *kth_id, uint32_t *flags, int final_pass, uint64_t *ids_out,
-                                       uint32_t *dist_out) {
-    extern __shared__ uint64_t sm[];
-    const uint32_t q = blockIdx.x;
-    uint32_t n_raw = count[q];
-    uint32_t n = min(n_raw, cap);
-    uint32_t P = 1;
-    while (P < n) P <<= 1;
-    uint64_t *s_id = sm, *s_dr = sm + P;
-    uint64_t *list = cand + (size_t)q * cap;
-    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
-        uint64_t e = UINT64_MAX, id = UINT64_MAX;
-        if (i < n) { e = list[i]; uint64_t r = e & kRowMask; id = ids ? ids[r] : id_base + r; }
-        s_id[i] = id; s_dr[i] = e;
+// exact-selection key for flagged queries: the true distance of one row
+struct HammingKey {
+    const uint64_t *codes; const QSlot *slots; uint32_t lo, hi;
+    __device__ void load_query(uint32_t q) { QSlot s = slots[q]; lo = s.lo; hi = s.hi; }
+    __device__ uint32_t key(uint64_t r) const {
+        uint64_t c = codes[r];
+        return __popc((uint32_t)c ^ lo) + __popc((uint32_t)(c >> 32) ^ hi);
     }
-    __syncthreads();
-    for (uint32_t size = 2; size <= P; size <<= 1) {
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
-                uint32_t i = 2 * t - (t & (stride - 1));  // lower index of the pair
-                uint32_t j = i + stride;
-                bool up = ((i & size) == 0);
-                uint64_t di = s_dr[i], ii = s_id[i], dj = s_dr[j], ij = s_id[j];
-                bool swap = up ? cand_before(dj, ij, di, ii) : cand_before(di, ii, dj, ij);
-                if (swap) { s_dr[i] = dj; s_id[i] = ij; s_dr[j] = di; s_id[j] = ii; }
-            }
-            __syncthreads();
-        }
-    }
-    const uint32_t m = min(n, k);
-    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) list[i] = s_dr[i];
-    if (final_pass) {
-        for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
-            bool ok = i < m;
-            ids_out[(size_t)q * k + i] = ok ? s_id[i] : UINT64_MAX;
-            dist_out[(size_t)q * k + i] = ok ? (uint32_t)(s_dr[i] >> 40) : UINT32_MAX;
-        }
-    }
-    if (threadIdx.x == 0) {
-        count[q] = m;
-        if (n_raw > cap) flags[q] = 1;
-        if (n >= k) { slots[q].thr = (uint32_t)(s_dr[k - 1] >> 40); kth_id[q] = s_id[k - 1]; }
-    }
-}
-
-__global__ void fill_sentinel_u32_kernel(uint64_t *ids_out, uint32_t *key_out, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { ids_out[i] = UINT64_MAX; key_out[i] = UINT32_MAX; }
-}
+};
 
 }  // namespace
-
-#include "hamming_exact.cuh"
 
 int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev,
                  uint32_t *dist_out_dev) {
@@ -220,7 +171,7 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
 
     static bool attr_done = false;
     if (!attr_done) {
-        UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
+        UCFP_CUDA_TRY(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
         attr_done = true;
     }
     int scan_occ = 0;
@@ -247,10 +198,11 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
         hamming_seed_kernel<<<dim3((seed + 255) / 256, nqp), 256, 0, st>>>(codes, seed, slots, cand, count, cap);
         count_launch(ctx, 2);
 
+        SelectState sel{cand, count, &slots[0].thr, 4, kth, flags, cap};
         auto compact = [&](bool final_pass) {
             // smem: 16 B per element of the padded list; lists hold <= cap entries
-            hamming_compact_kernel<<<nqp, 512, 16 * (size_t)cap, st>>>(cand, count, cap, (uint32_t)k, ids, c->id_base, slots,
-                                                                      kth, flags, final_pass ? 1 : 0, ids_out, dist_out);
+            compact_kernel<<<nqp, 512, 16 * (size_t)cap, st>>>(sel, (uint32_t)k, ids, c->id_base, final_pass ? 1 : 0, 0u,
+                                                              ids_out, dist_out);
             count_launch(ctx);
         };
         compact(seed == N);
@@ -275,7 +227,7 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
         }
         UCFP_TRY(check_launch("hamming scan"));
         // exact recomputation of any query whose candidate list overflowed (device-side decision, no host sync)
-        UCFP_TRY(hamming_exact_fallback(c, slots, flags, nqp, (uint32_t)k, ids_out, dist_out));
+        UCFP_TRY(exact_select_fallback(c, HammingKey{codes, slots, 0, 0}, flags, nqp, (uint32_t)k, 0u, ids_out, dist_out));
     }
     return UCFP_OK;
 }

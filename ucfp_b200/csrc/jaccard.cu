@@ -1,7 +1,242 @@
+// jaccard.cu -- MinHash-128 signature-equality Jaccard top-k over an HBM-resident corpus (sm_100a).
+//
+// Semantics (docs/HASH_SPEC.md section 7; absent from the reference):
+//   matches(q, r) = #{i < 128 : q.slot[i] == r.slot[i]},  J^ = matches / 128
+//   per query the k best under the total order (matches desc, record_id asc).
+// Rows are the 1024-byte slot payload of txtfp's MinHashSig<128> (src/modality/text.rs:200-204).
+//
+// A brute-force pass reads 1 KiB per row.  Instead the corpus keeps, next to the rows, a 128-byte SKETCH per
+// row -- the low byte of every slot -- built once at append time.  byte_matches(q, r) >= matches(q, r), so
+// the scan streams only the sketches (8x less HBM traffic), counts equal bytes with SWAR arithmetic
+// (4 slots per 32-bit word), and only rows whose upper bound can still enter the query's top-k are
+// verified against the full 1 KiB row by the whole warp.  Results are exact.
+// Selection (thresholds that tighten chunk by chunk, compaction, overflow fallback) is shared with the
+// Hamming scan: topk_select.cuh, key = 128 - matches.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
 namespace ucfp {
-int jaccard_on_append(ucfp_corpus *, uint64_t, uint64_t) { return UCFP_OK; }
-int jaccard_scan(ucfp_corpus *, const uint64_t *, size_t, size_t, uint64_t *, uint32_t *) {
-    set_error("jaccard scan not built yet"); return UCFP_E_UNSUPPORTED;
+namespace {
+
+#include "topk_select.cuh"
+
+constexpr int kSlots = 128;
+constexpr int kSketchWords = 32;                 // 128 slots x 1 byte
+constexpr int kScanThreads = 256;
+constexpr uint32_t kSeedRows = 1024;
+constexpr uint32_t kMaxQueriesPerPass = 256;     // 128 B of sketch + 4 B bound per query in shared memory
+constexpr uint64_t kMaxChunkRows = 1ULL << 26;
+
+// Sketch layout: tiles of 32 rows; word j (slots 4j..4j+3) of row r lives at
+// (r / 32) * 1024 + j * 32 + (r % 32), so that a warp reads word j of 32 consecutive rows as one 128-byte line.
+__device__ __forceinline__ size_t sketch_index(uint64_t row, int j) { return (row >> 5) * 1024 + (size_t)j * 32 + (row & 31); }
+
+__global__ void sketch_build_kernel(const uint64_t *__restrict__ sigs, uint32_t *sketch, uint64_t first, uint64_t n) {
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * kSketchWords) return;
+    uint64_t row = first + idx / kSketchWords;
+    int j = (int)(idx % kSketchWords);
+    const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(sigs + row * kSlots + 4 * j);
+    ulonglong2 a = p[0], b = p[1];
+    uint32_t w = (uint32_t)(a.x & 255) | (uint32_t)(a.y & 255) << 8 | (uint32_t)(b.x & 255) << 16 | (uint32_t)(b.y & 255) << 24;
+    sketch[sketch_index(row, j)] = w;
 }
+
+// query sketches, row-major [q][32], plus per-query selection state
+__global__ void jaccard_init_kernel(const uint64_t *__restrict__ q, uint32_t nq, uint32_t *qsketch, uint32_t *thr, uint64_t *kth_id,
+                                    uint32_t *count, uint32_t *flags) {
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nq * kSketchWords) return;
+    uint32_t qi = idx / kSketchWords, j = idx % kSketchWords;
+    const uint64_t *p = q + (size_t)qi * kSlots + 4 * j;
+    qsketch[idx] = (uint32_t)(p[0] & 255) | (uint32_t)(p[1] & 255) << 8 | (uint32_t)(p[2] & 255) << 16 | (uint32_t)(p[3] & 255) << 24;
+    if (j == 0) { thr[qi] = 128; kth_id[qi] = UINT64_MAX; count[qi] = 0; flags[qi] = 0; }
 }
+
+// exact matches of one (query, row) pair, computed by a full warp: lane l compares slots 4l..4l+3
+__device__ __forceinline__ uint32_t warp_matches(const uint64_t *__restrict__ row, const uint64_t *__restrict__ qsig, int lane) {
+    const ulonglong2 *rp = reinterpret_cast<const ulonglong2 *>(row + 4 * lane);
+    const ulonglong2 *qp = reinterpret_cast<const ulonglong2 *>(qsig + 4 * lane);
+    ulonglong2 r0 = __ldg(rp), r1 = __ldg(rp + 1), q0 = __ldg(qp), q1 = __ldg(qp + 1);
+    uint32_t m = (r0.x == q0.x) + (r0.y == q0.y) + (r1.x == q1.x) + (r1.y == q1.y);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m += __shfl_xor_sync(0xffffffffu, m, s);
+    return m;
+}
+
+// grid (ceil(rows / 8), nq), 256 threads: every warp scores one of the first `rows` rows exhaustively.
+__global__ void jaccard_seed_kernel(const uint64_t *__restrict__ sigs, uint32_t rows, const uint64_t *__restrict__ q,
+                                    uint64_t *cand, uint32_t *count, uint32_t cap) {
+    const uint32_t qi = blockIdx.y, lane = threadIdx.x & 31;
+    const uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r < rows) {
+        uint32_t m = warp_matches(sigs + (size_t)r * kSlots, q + (size_t)qi * kSlots, lane);
+        if (lane == 0) cand[(size_t)qi * cap + r] = ((uint64_t)(128u - m) << 40) | r;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) count[qi] = rows;
+}
+
+// number of equal bytes in two packed words: SWAR zero-byte detection on a ^ b
+__device__ __forceinline__ uint32_t eq_bytes_flags(uint32_t a, uint32_t b) {
+    uint32_t x = a ^ b;
+    uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | x | 0x7F7F7F7Fu);  // 0x80 in every byte where a and b agree
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint64_t *__restrict__ sigs, const uint64_t *__restrict__ ids,
+                    uint64_t id_base, uint64_t row0, uint64_t nrows, const uint64_t *__restrict__ q,
+                    const uint32_t *__restrict__ qsketch, uint32_t nq, SelectState S) {
+    extern __shared__ uint32_t smem[];
+    uint32_t *sq = smem;                        // [nq][32] query sketches
+    uint32_t *sthr = smem + (size_t)nq * kSketchWords;  // [nq] admission bound (key = 128 - matches)
+    uint64_t *skid = reinterpret_cast<uint64_t *>(sthr + ((nq + 1) & ~1u));  // [nq] id of the current k-th result
+    for (uint32_t i = threadIdx.x; i < nq * kSketchWords; i += kScanThreads) sq[i] = qsketch[i];
+    for (uint32_t i = threadIdx.x; i < nq; i += kScanThreads) { sthr[i] = S.thr[(size_t)i * S.thr_stride]; skid[i] = S.kth_id[i]; }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const uint64_t row_end = row0 + nrows;
+    const uint64_t ntiles = (nrows + kScanThreads - 1) / kScanThreads;   // row0 is a multiple of 32
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t row = row0 + tile * kScanThreads + threadIdx.x;
+        const bool valid = row < row_end;
+        uint32_t w[kSketchWords];
+        const uint32_t *sp = sketch + sketch_index(row & ~31ULL, 0) + lane;  // padded allocation: always readable
+#pragma unroll
+        for (int j = 0; j < kSketchWords; ++j) w[j] = __ldg(sp + j * 32);
+        const uint64_t id = valid ? (ids ? ids[row] : id_base + row) : UINT64_MAX;
+
+        for (uint32_t qi = 0; qi < nq; ++qi) {
+            const uint4 *qv = reinterpret_cast<const uint4 *>(sq + (size_t)qi * kSketchWords);
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j4 = 0; j4 < kSketchWords / 4; ++j4) {
+                uint4 v = qv[j4];  // broadcast LDS.128
+                acc += eq_bytes_flags(w[4 * j4], v.x) >> 7;
+                acc += eq_bytes_flags(w[4 * j4 + 1], v.y) >> 7;
+                acc += eq_bytes_flags(w[4 * j4 + 2], v.z) >> 7;
+                acc += eq_bytes_flags(w[4 * j4 + 3], v.w) >> 7;
+            }
+            const uint32_t bm = (acc * 0x01010101u) >> 24;  // byte matches: an upper bound on slot matches
+            const uint32_t thr = sthr[qi];
+            const uint32_t lower = 128u - bm;               // lower bound on the key
+            const uint64_t kid = skid[qi];
+            // (key, id) can beat the current k-th only if (lower, id) < (thr, kth_id)
+            unsigned hits = __ballot_sync(0xffffffffu, valid && (lower < thr || (lower == thr && id < kid)));
+            if (hits) {  // rare: verify against the full rows, one survivor at a time, whole warp per row
+                while (hits) {
+                    const int src = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const uint64_t srow = __shfl_sync(0xffffffffu, row, src);
+                    const uint64_t sid = __shfl_sync(0xffffffffu, id, src);
+                    const uint32_t m = warp_matches(sigs + srow * kSlots, q + (size_t)qi * kSlots, lane);
+                    const uint32_t key = 128u - m;
+                    if (lane == 0 && (key < thr || (key == thr && sid < kid))) {
+                        uint32_t pos = atomicAdd(&S.count[qi], 1u);
+                        if (pos < S.cap) S.cand[(size_t)qi * S.cap + pos] = ((uint64_t)key << 40) | srow;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// exact-selection key for flagged queries: true slot matches of one row, one thread per row
+struct JaccardKey {
+    const uint64_t *sigs; const uint64_t *q;
+    const uint64_t *qsig;
+    __device__ void load_query(uint32_t qi) { qsig = q + (size_t)qi * kSlots; }
+    __device__ uint32_t key(uint64_t r) const {
+        const uint64_t *rp = sigs + r * kSlots;
+        uint32_t m = 0;
+        for (int i = 0; i < kSlots; ++i) m += (rp[i] == __ldg(qsig + i));
+        return 128u - m;
+    }
+};
+
+}  // namespace
+
+int jaccard_on_append(ucfp_corpus *c, uint64_t first_row, uint64_t n) {
+    if (n == 0) return UCFP_OK;
+    uint64_t items = n * kSketchWords;
+    sketch_build_kernel<<<(unsigned)((items + 255) / 256), 256, 0, c->ctx->stream>>>(
+        static_cast<const uint64_t *>(c->rows), reinterpret_cast<uint32_t *>(c->mh_sketch), first_row, n);
+    count_launch(c->ctx);
+    return check_launch("sketch_build");
+}
+
+int jaccard_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, uint32_t *m_out_dev) {
+    ucfp_ctx *ctx = c->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint64_t N = c->size;
+    UCFP_REQUIRE(k <= 2048, UCFP_E_UNSUPPORTED, "jaccard scan supports k <= 2048 (got %zu)", k);
+    UCFP_REQUIRE(N <= kRowMask, UCFP_E_UNSUPPORTED, "corpus too large");
+    if (N == 0) {
+        size_t tot = nq * k;
+        fill_sentinel_u32_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ids_out_dev, m_out_dev, tot);
+        count_launch(ctx);
+        return check_launch("fill_sentinel");
+    }
+    uint32_t cap = 4096;
+    while (cap < 4 * k) cap <<= 1;
+    const uint64_t *sigs = static_cast<const uint64_t *>(c->rows);
+    const uint32_t *sketch = reinterpret_cast<const uint32_t *>(c->mh_sketch);
+    const uint64_t *ids = c->id_mode == 1 ? c->ids : nullptr;
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
+    const size_t scan_smem_max = (size_t)kMaxQueriesPerPass * (kSketchWords + 1 + 2) * 4 + 8;
+    int occ = 0;
+    UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jaccard_scan_kernel, kScanThreads, scan_smem_max));
+    if (occ < 1) occ = 1;
+
+    for (size_t q0 = 0; q0 < nq; q0 += kMaxQueriesPerPass) {
+        const uint32_t nqp = (uint32_t)((nq - q0 < kMaxQueriesPerPass) ? nq - q0 : kMaxQueriesPerPass);
+        UCFP_TRY(ctx->qstate.reserve((size_t)nqp * (kSketchWords * 4 + 4 + 8) + 64));
+        UCFP_TRY(ctx->cand.reserve(sizeof(uint64_t) * (size_t)cap * nqp));
+        UCFP_TRY(ctx->cand_count.reserve(sizeof(uint32_t) * nqp));
+        UCFP_TRY(ctx->flags.reserve(sizeof(uint32_t) * (nqp + 1)));
+        uint64_t *kth = ctx->qstate.as<uint64_t>();
+        uint32_t *qsk = reinterpret_cast<uint32_t *>(kth + nqp);
+        uint32_t *thr = qsk + (size_t)nqp * kSketchWords;
+        uint64_t *cand = ctx->cand.as<uint64_t>();
+        uint32_t *count = ctx->cand_count.as<uint32_t>();
+        uint32_t *flags = ctx->flags.as<uint32_t>();
+        const uint64_t *qp = q_dev + q0 * kSlots;
+        uint64_t *ids_out = ids_out_dev + q0 * k;
+        uint32_t *m_out = m_out_dev + q0 * k;
+        SelectState sel{cand, count, thr, 1, kth, flags, cap};
+
+        jaccard_init_kernel<<<(nqp * kSketchWords + 255) / 256, 256, 0, st>>>(qp, nqp, qsk, thr, kth, count, flags);
+        const uint32_t seed = (uint32_t)(N < kSeedRows ? N : kSeedRows);
+        jaccard_seed_kernel<<<dim3((seed + 7) / 8, nqp), 256, 0, st>>>(sigs, seed, qp, cand, count, cap);
+        count_launch(ctx, 2);
+        auto compact = [&](bool final_pass) {
+            compact_kernel<<<nqp, 512, 16 * (size_t)cap, st>>>(sel, (uint32_t)k, ids, c->id_base, final_pass ? 1 : 0, 128u, ids_out, m_out);
+            count_launch(ctx);
+        };
+        compact(seed == N);
+        const uint64_t growth = nqp <= 8 ? 32 : 8;
+        uint64_t pos = seed, chunk = (uint64_t)seed * growth;
+        const size_t smem = (size_t)nqp * (kSketchWords + 1 + 2) * 4 + 8;
+        while (pos < N) {
+            uint64_t n = (N - pos < chunk) ? N - pos : chunk;
+            uint64_t ntiles = (n + kScanThreads - 1) / kScanThreads;
+            uint64_t grid = (uint64_t)ctx->sm_count * occ;
+            if (grid > ntiles) grid = ntiles;
+            {
+                ProfScope ps(ctx, UCFP_PROF_JACCARD_SCAN, 1024.0 * (double)n * nqp);
+                jaccard_scan_kernel<<<(unsigned)grid, kScanThreads, smem, st>>>(sketch, sigs, ids, c->id_base, pos, n, qp, qsk, nqp, sel);
+            }
+            count_launch(ctx);
+            pos += n;
+            compact(pos == N);
+            chunk = chunk * growth < kMaxChunkRows ? chunk * growth : kMaxChunkRows;
+        }
+        UCFP_TRY(check_launch("jaccard scan"));
+        UCFP_TRY(exact_select_fallback(c, JaccardKey{sigs, qp, nullptr}, flags, nqp, (uint32_t)k, 128u, ids_out, m_out));
+    }
+    return UCFP_OK;
+}
+
+}  // namespace ucfp

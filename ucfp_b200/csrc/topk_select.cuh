@@ -1,0 +1,210 @@
+// topk_select.cuh -- the selection machinery shared by the integer-keyed scans (Hamming: key = distance,
+// Jaccard: key = 128 - matches; smaller key is better, ties by record id ascending).
+//
+//   compact_kernel       one CTA per query: bitonic sort of the candidate list by (key, id), keep k, publish
+//                        the new admission bound (thr = key_k, kth_id = id_k); the last call writes results.
+//   exact_select_kernel  cooperative multi-pass exact selection (key histogram + 8-bit radix select on ids)
+//                        for queries whose candidate list overflowed; correct for ANY input with bounded memory.
+//
+// Included inside namespace ucfp { namespace { ... } } by each scan's .cu file.
+#pragma once
+
+constexpr uint64_t kRowMask = (1ULL << 40) - 1;  // candidate = key << 40 | row
+
+struct SelectState {      // per query pass, all device pointers
+    uint64_t *cand;       // [nq][cap] candidate entries
+    uint32_t *count;      // [nq] entries appended (may exceed cap: overflow)
+    uint32_t *thr;        // first query's admission bound; query q at thr[q * thr_stride]
+    uint32_t thr_stride;
+    uint64_t *kth_id;     // [nq]
+    uint32_t *flags;      // [nq] 1 = list overflowed, needs exact_select
+    uint32_t cap;
+};
+
+__device__ __forceinline__ bool cand_before(uint64_t dra, uint64_t ida, uint64_t drb, uint64_t idb) {
+    uint32_t da = (uint32_t)(dra >> 40), db = (uint32_t)(drb >> 40);
+    return da < db || (da == db && ida < idb);
+}
+
+// key_flip: 0 -> the reported value is the key itself; otherwise reported = key_flip - key (Jaccard matches).
+__global__ void compact_kernel(SelectState S, uint32_t k, const uint64_t *__restrict__ ids, uint64_t id_base, int final_pass,
+                               uint32_t key_flip, uint64_t *ids_out, uint32_t *keys_out) {
+    extern __shared__ uint64_t sm[];
+    const uint32_t q = blockIdx.x;
+    const uint32_t n_raw = S.count[q];
+    const uint32_t n = min(n_raw, S.cap);
+    uint32_t P = 1;
+    while (P < n) P <<= 1;
+    uint64_t *s_id = sm, *s_dr = sm + P;
+    uint64_t *list = S.cand + (size_t)q * S.cap;
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+        uint64_t e = UINT64_MAX, id = UINT64_MAX;
+        if (i < n) { e = list[i]; uint64_t r = e & kRowMask; id = ids ? ids[r] : id_base + r; }
+        s_id[i] = id; s_dr[i] = e;
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= P; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                uint32_t i = 2 * t - (t & (stride - 1));  // lower index of the pair
+                uint32_t j = i + stride;
+                bool up = ((i & size) == 0);
+                uint64_t di = s_dr[i], ii = s_id[i], dj = s_dr[j], ij = s_id[j];
+                bool swap = up ? cand_before(dj, ij, di, ii) : cand_before(di, ii, dj, ij);
+                if (swap) { s_dr[i] = dj; s_id[i] = ij; s_dr[j] = di; s_id[j] = ii; }
+            }
+            __syncthreads();
+        }
+    }
+    const uint32_t m = min(n, k);
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) list[i] = s_dr[i];
+    if (final_pass) {
+        for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
+            bool ok = i < m;
+            uint32_t key = ok ? (uint32_t)(s_dr[i] >> 40) : 0;
+            ids_out[(size_t)q * k + i] = ok ? s_id[i] : UINT64_MAX;
+            keys_out[(size_t)q * k + i] = ok ? (key_flip ? key_flip - key : key) : UINT32_MAX;
+        }
+    }
+    if (threadIdx.x == 0) {
+        S.count[q] = m;
+        if (n_raw > S.cap) S.flags[q] = 1;
+        if (n >= k) { S.thr[(size_t)q * S.thr_stride] = (uint32_t)(s_dr[k - 1] >> 40); S.kth_id[q] = s_id[k - 1]; }
+    }
+}
+
+__global__ void fill_sentinel_u32_kernel(uint64_t *ids_out, uint32_t *key_out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { ids_out[i] = UINT64_MAX; key_out[i] = UINT32_MAX; }
+}
+
+// ---- exact selection -------------------------------------------------------------------------------
+// KeyFn: struct with  __device__ void load_query(uint32_t q)  (all threads of the CTA call it, may use
+// shared memory and __syncthreads) and  __device__ uint32_t key(uint64_t row) const  returning 0..kMaxKey.
+struct ExactScratch {
+    unsigned long long hist[256];    // keys 0..255
+    unsigned long long digit[256];   // radix pass histogram
+    unsigned int out_count;
+    unsigned int pad;
+};
+
+template <typename KeyFn>
+__global__ void __launch_bounds__(256)
+exact_select_kernel(KeyFn fn, const uint64_t *__restrict__ ids, uint64_t id_base, uint64_t N,
+                    const uint32_t *__restrict__ flags, uint32_t nq, uint32_t k, uint32_t key_flip, ExactScratch *scr,
+                    uint64_t *out_id, uint32_t *out_key, uint64_t *ids_out, uint32_t *keys_out) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned int s_any;
+    __shared__ unsigned long long s_hist[256];
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) if (flags[i]) s_any = 1;
+    __syncthreads();
+    if (!s_any) return;  // uniform over the grid: every CTA reads the same flags
+
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t gsize = (uint64_t)gridDim.x * blockDim.x;
+
+    for (uint32_t q = 0; q < nq; ++q) {
+        if (!flags[q]) continue;
+        fn.load_query(q);
+        // ---- 1. key histogram
+        if (gtid < 256) scr->hist[gtid] = 0;
+        if (gtid == 0) scr->out_count = 0;
+        s_hist[threadIdx.x] = 0;
+        grid.sync();
+        for (uint64_t r = gtid; r < N; r += gsize) atomicAdd(&s_hist[fn.key(r) & 255], 1ULL);
+        __syncthreads();
+        if (s_hist[threadIdx.x]) atomicAdd(&scr->hist[threadIdx.x], s_hist[threadIdx.x]);
+        grid.sync();
+        uint32_t kstar = 256; uint64_t need = 0;
+        {
+            uint64_t cum = 0;
+            for (uint32_t d = 0; d < 256; ++d) {
+                uint64_t h = scr->hist[d];
+                if (cum + h >= k) { kstar = d; need = k - cum; break; }
+                cum += h;
+            }
+        }
+        uint64_t idstar = UINT64_MAX;  // fewer than k rows in total: take everything
+        if (kstar < 256) {
+            // ---- 2. radix select of the need-th smallest id among rows with key == k*
+            uint64_t prefix = 0; uint64_t want = need;
+            for (int shift = 56; shift >= 0; shift -= 8) {
+                if (gtid < 256) scr->digit[gtid] = 0;
+                s_hist[threadIdx.x] = 0;
+                grid.sync();
+                const uint64_t hi_mask = shift == 56 ? 0 : ~0ULL << (shift + 8);
+                for (uint64_t r = gtid; r < N; r += gsize) {
+                    if (fn.key(r) != kstar) continue;
+                    uint64_t id = ids ? ids[r] : id_base + r;
+                    if ((id & hi_mask) != prefix) continue;
+                    atomicAdd(&s_hist[(id >> shift) & 255], 1ULL);
+                }
+                __syncthreads();
+                if (s_hist[threadIdx.x]) atomicAdd(&scr->digit[threadIdx.x], s_hist[threadIdx.x]);
+                grid.sync();
+                uint64_t cum = 0; uint32_t dig = 255;
+                for (uint32_t b = 0; b < 256; ++b) {
+                    uint64_t h = scr->digit[b];
+                    if (cum + h >= want) { dig = b; break; }
+                    cum += h;
+                }
+                want -= cum;
+                prefix |= (uint64_t)dig << shift;
+                grid.sync();  // everyone has read digit[] before it is cleared again
+            }
+            idstar = prefix;
+        }
+        // ---- 3. collect
+        for (uint64_t r = gtid; r < N; r += gsize) {
+            uint32_t d = fn.key(r);
+            if (d > kstar) continue;
+            uint64_t id = ids ? ids[r] : id_base + r;
+            if (d == kstar && id > idstar) continue;
+            unsigned int pos = atomicAdd(&scr->out_count, 1u);
+            if (pos < k) { out_id[pos] = id; out_key[pos] = d; }
+        }
+        grid.sync();
+        // ---- 4. CTA 0 orders the winners (k <= 2048: rank by counting, O(k^2) on a tiny set)
+        if (blockIdx.x == 0) {
+            uint32_t m = min(scr->out_count, k);
+            for (uint32_t i = threadIdx.x; i < k; i += blockDim.x)
+                if (i >= m) { ids_out[(size_t)q * k + i] = UINT64_MAX; keys_out[(size_t)q * k + i] = UINT32_MAX; }
+            for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                uint64_t id = out_id[i]; uint32_t d = out_key[i];
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < m; ++j) {
+                    uint64_t idj = out_id[j]; uint32_t dj = out_key[j];
+                    rank += (dj < d || (dj == d && (idj < id || (idj == id && j < i))));
+                }
+                ids_out[(size_t)q * k + rank] = id;
+                keys_out[(size_t)q * k + rank] = key_flip ? key_flip - d : d;
+            }
+        }
+        grid.sync();
+    }
+}
+
+template <typename KeyFn>
+static int exact_select_fallback(ucfp_corpus *c, KeyFn fn, const uint32_t *flags, uint32_t nq, uint32_t k, uint32_t key_flip,
+                                 uint64_t *ids_out, uint32_t *keys_out) {
+    ucfp_ctx *ctx = c->ctx;
+    size_t scratch = sizeof(ExactScratch) + (sizeof(uint64_t) + sizeof(uint32_t)) * (size_t)k + 64;
+    UCFP_TRY(ctx->misc.reserve(scratch));
+    ExactScratch *scr = ctx->misc.as<ExactScratch>();
+    uint64_t *out_id = reinterpret_cast<uint64_t *>(scr + 1);
+    uint32_t *out_key = reinterpret_cast<uint32_t *>(out_id + k);
+    int occ = 0;
+    UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exact_select_kernel<KeyFn>, 256, 0));
+    if (occ < 1) occ = 1;
+    if (occ > 4) occ = 4;
+    const uint64_t *ids = c->id_mode == 1 ? c->ids : nullptr;
+    uint64_t id_base = c->id_base, N = c->size;
+    void *args[] = {&fn, &ids, &id_base, &N, &flags, &nq, &k, &key_flip, &scr, &out_id, &out_key, &ids_out, &keys_out};
+    UCFP_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)exact_select_kernel<KeyFn>, dim3(ctx->sm_count * occ), dim3(256), args,
+                                              0, ctx->stream));
+    count_launch(ctx);
+    return UCFP_OK;
+}
