@@ -183,6 +183,10 @@ UCFP_API int ucfp_scan_jaccard(ucfp_corpus *c, const uint64_t *queries, size_t n
 UCFP_API int ucfp_scan_cosine(ucfp_corpus *c, const float *queries, size_t nq, size_t k,
                               uint64_t *ids_out, float *score_out);
 
+/* Diagnostics of the most recent scan on this context (synchronises the stream): how many of its queries
+ * overflowed their candidate list and were recomputed by the exact multi-pass selection.  0 on the fast path. */
+UCFP_API int ucfp_ctx_last_scan_fallbacks(ucfp_ctx *ctx, uint64_t *queries_recomputed);
+
 /* Merges `parts` per-shard result lists (each nq x k, best first, as written by a scan) into one
  * nq x k list under the same total order: the step after the NCCL all-gather of per-rank candidates.
  * ids_in / keys_in are laid out [part][query][k].  descending = 0 for Hamming distances, 1 for Jaccard

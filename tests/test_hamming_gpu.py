@@ -37,6 +37,7 @@ def test_random_corpus_matches_oracle(ctx, n, nq, k):
     codes = oracle.fill_u64(n, 0xC0DE)
     queries = oracle.fill_u64(nq, 0xBEEF)
     _check(ctx, codes, queries, k)
+    assert ctx.last_scan_fallbacks() == 0      # the threshold path, not the exact fallback, produced this
 
 
 def test_explicit_ids_and_id_base(ctx):
@@ -77,6 +78,7 @@ def test_duplicate_flood_takes_exact_fallback(ctx):
     _check(ctx, codes, queries, k, ids=ids)
     codes[::2] ^= U64(1)  # two tie classes
     _check(ctx, codes, queries, 33, ids=ids)
+    assert ctx.last_scan_fallbacks() > 0       # this input must have gone through the exact selection
 
 
 def test_fewer_rows_than_k_pads_with_sentinels(ctx):

@@ -44,6 +44,7 @@ def _check(ctx, sigs, q, k, ids=None, id_base=0):
 def test_planted_corpus_matches_oracle(ctx, n, nq, k):
     sigs, q = synth(n, nq, 11 + n % 7)
     _check(ctx, sigs, q, k)
+    assert ctx.last_scan_fallbacks() == 0      # the threshold path, not the exact fallback, produced this
 
 
 def test_queries_without_any_neighbour(ctx):
@@ -76,6 +77,7 @@ def test_duplicate_flood_takes_exact_fallback(ctx):
     sigs[::3, 5] ^= U64(1)  # two tie classes: 128 and 127 matches
     ids = np.arange(n, 0, -1, dtype=U64) * U64(5)
     _check(ctx, sigs, np.concatenate([q, q ^ U64(1)]), k, ids=ids)
+    assert ctx.last_scan_fallbacks() > 0       # this input must have gone through the exact selection
 
 
 def test_fewer_rows_than_k_and_empty(ctx):

@@ -61,6 +61,7 @@ PROTOTYPES = {
     "ucfp_scan_hamming": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "ucfp_scan_jaccard": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "ucfp_scan_cosine": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
+    "ucfp_ctx_last_scan_fallbacks": (_int, [_vp, C.POINTER(_u64)]),
     "ucfp_merge_topk_u32": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _int, _vp, _vp]),
     "ucfp_merge_topk_f32": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp]),
 }

@@ -19,7 +19,7 @@ SO = os.path.join(HERE, "libucfp_cuda.so")
 SOURCES = ["api.cu", "hamming.cu", "jaccard.cu", "cosine.cu", "image.cu", "merge.cu"]
 # Per-file extra flags.  image.cu must not contract a*b+c into FMA: the hash spec fixes
 # separately rounded mul and add (docs/HASH_SPEC.md section 2).
-EXTRA = {"image.cu": ["-fmad=false"], "cosine.cu": []}
+EXTRA = {"image.cu": ["-fmad=false"], "cosine.cu": ["-fmad=false"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "--expt-relaxed-constexpr"]
 

@@ -110,7 +110,7 @@ void ucfp_destroy(ucfp_ctx *ctx) {
     DeviceGuard dg(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->q_dev, &ctx->out_ids_dev, &ctx->out_keys_dev, &ctx->cand, &ctx->cand_count, &ctx->qstate, &ctx->flags,
-                      &ctx->misc, &ctx->img_desc_dev, &ctx->img_out_dev, &ctx->img_status_dev, &ctx->img_tables_dev, &ctx->img_stage_dev};
+                      &ctx->misc, &ctx->img_desc_dev, &ctx->img_out_dev, &ctx->img_status_dev, &ctx->img_tables_dev, &ctx->img_stage_dev, &ctx->stats};
     for (DevBuf *b : bufs) b->release();
     ctx->pin_a.release(); ctx->pin_b.release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -303,6 +303,7 @@ static int run_scan(ucfp_corpus *c, int want_kind, const void *queries, size_t q
     bool ids_host = false, keys_host = false;
     UCFP_TRY(stage_out(ctx->out_ids_dev, ids_out, 8 * nq * k, &ids_dev, &ids_host));
     UCFP_TRY(stage_out(ctx->out_keys_dev, keys_out, sizeof(Key) * nq * k, &keys_dev, &keys_host));
+    UCFP_TRY(stats_reset(ctx));
     UCFP_TRY(scan(q_dev, static_cast<uint64_t *>(ids_dev), static_cast<Key *>(keys_dev)));
     if (ids_host) UCFP_TRY(copy_back(ctx, ids_out, ids_dev, 8 * nq * k));
     if (keys_host) UCFP_TRY(copy_back(ctx, keys_out, keys_dev, sizeof(Key) * nq * k));
@@ -335,6 +336,16 @@ int ucfp_scan_cosine(ucfp_corpus *c, const float *queries, size_t nq, size_t k, 
 }
 
 }  // extern "C"
+
+extern "C" int ucfp_ctx_last_scan_fallbacks(ucfp_ctx *ctx, uint64_t *queries_recomputed) {
+    UCFP_GUARD(ctx);
+    UCFP_REQUIRE(queries_recomputed != nullptr, UCFP_E_INVALID, "NULL output");
+    *queries_recomputed = 0;
+    if (!ctx->stats.ptr) return UCFP_OK;
+    UCFP_CUDA_TRY(cudaMemcpyAsync(queries_recomputed, ctx->stats.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    UCFP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return UCFP_OK;
+}
 
 template <typename Key, typename MergeFn>
 static int run_merge(ucfp_ctx *ctx, const uint64_t *ids_in, const Key *keys_in, size_t parts, size_t nq, size_t k,

@@ -92,6 +92,7 @@ struct ucfp_ctx {
     ucfp::DevBuf q_dev, out_ids_dev, out_keys_dev, cand, cand_count, qstate, flags, misc;
     ucfp::DevBuf img_desc_dev, img_out_dev, img_status_dev, img_tables_dev, img_stage_dev;
     ucfp::PinnedBuf pin_a, pin_b;
+    ucfp::DevBuf stats;            // u64[4]: [0] queries recomputed by the exact fallback in the last scan
 };
 
 struct ucfp_corpus {
@@ -158,6 +159,9 @@ int merge_f32(ucfp_ctx *ctx, const uint64_t *ids_in, const float *keys_in, size_
 int synth_fill_u64(ucfp_ctx *ctx, uint64_t *dst_dev, uint64_t nwords, uint64_t seed, uint64_t start_word);
 int image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *descs_host, size_t n, uint32_t algo_mask,
                      ucfp_image_hashes *out_dev, int32_t *status_host);
+
+int stats_reset(ucfp_ctx *ctx);
+int stats_add_flags(ucfp_ctx *ctx, const uint32_t *flags_dev, uint32_t nq);
 
 // splitmix64 counter PRNG of docs/HASH_SPEC.md section 8
 __host__ __device__ inline uint64_t mix64(uint64_t z) {

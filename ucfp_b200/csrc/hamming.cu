@@ -141,6 +141,9 @@ hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restri
 
 // exact-selection key for flagged queries: the true distance of one row
 struct HammingKey {
+    static constexpr int kKeyBits = 8;
+    static constexpr uint32_t kInvalidKey = 0xFFFFFFFFu;
+    __device__ static uint32_t report(uint32_t key, uint32_t flip) { return flip ? flip - key : key; }
     const uint64_t *codes; const QSlot *slots; uint32_t lo, hi;
     __device__ void load_query(uint32_t q) { QSlot s = slots[q]; lo = s.lo; hi = s.hi; }
     __device__ uint32_t key(uint64_t r) const {
@@ -227,6 +230,7 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
         }
         UCFP_TRY(check_launch("hamming scan"));
         // exact recomputation of any query whose candidate list overflowed (device-side decision, no host sync)
+        UCFP_TRY(stats_add_flags(ctx, flags, nqp));
         UCFP_TRY(exact_select_fallback(c, HammingKey{codes, slots, 0, 0}, flags, nqp, (uint32_t)k, 0u, ids_out, dist_out));
     }
     return UCFP_OK;

@@ -145,6 +145,9 @@ jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint64_t *__restr
 
 // exact-selection key for flagged queries: true slot matches of one row, one thread per row
 struct JaccardKey {
+    static constexpr int kKeyBits = 8;
+    static constexpr uint32_t kInvalidKey = 0xFFFFFFFFu;
+    __device__ static uint32_t report(uint32_t key, uint32_t flip) { return flip ? flip - key : key; }
     const uint64_t *sigs; const uint64_t *q;
     const uint64_t *qsig;
     __device__ void load_query(uint32_t qi) { qsig = q + (size_t)qi * kSlots; }
@@ -234,6 +237,7 @@ int jaccard_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
             chunk = chunk * growth < kMaxChunkRows ? chunk * growth : kMaxChunkRows;
         }
         UCFP_TRY(check_launch("jaccard scan"));
+        UCFP_TRY(stats_add_flags(ctx, flags, nqp));
         UCFP_TRY(exact_select_fallback(c, JaccardKey{sigs, qp, nullptr}, flags, nqp, (uint32_t)k, 128u, ids_out, m_out));
     }
     return UCFP_OK;

@@ -93,6 +93,26 @@ int merge_f32(ucfp_ctx *ctx, const uint64_t *ids_in, const float *keys_in, size_
     return merge_impl<float>(ctx, ids_in, keys_in, parts, nq, k, 1, -INFINITY, ids_out, keys_out);
 }
 
+// ---- scan diagnostics ------------------------------------------------------------------------
+namespace {
+__global__ void add_flags_kernel(const uint32_t *flags, uint32_t nq, unsigned long long *stats) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq && flags[i]) atomicAdd(&stats[0], 1ULL);
+}
+}  // namespace
+
+int stats_reset(ucfp_ctx *ctx) {
+    UCFP_TRY(ctx->stats.reserve(32));
+    UCFP_CUDA_TRY(cudaMemsetAsync(ctx->stats.ptr, 0, 32, ctx->stream));
+    return UCFP_OK;
+}
+
+int stats_add_flags(ucfp_ctx *ctx, const uint32_t *flags_dev, uint32_t nq) {
+    add_flags_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(flags_dev, nq, ctx->stats.as<unsigned long long>());
+    count_launch(ctx);
+    return check_launch("add_flags");
+}
+
 // ---- synthetic data (bench/test support) ---------------------------------------------------
 namespace {
 __global__ void synth_fill_kernel(uint64_t *dst, uint64_t n, uint64_t seed, uint64_t start) {

@@ -79,8 +79,9 @@ __global__ void fill_sentinel_u32_kernel(uint64_t *ids_out, uint32_t *key_out, s
 }
 
 // ---- exact selection -------------------------------------------------------------------------------
-// KeyFn: struct with  __device__ void load_query(uint32_t q)  (all threads of the CTA call it, may use
-// shared memory and __syncthreads) and  __device__ uint32_t key(uint64_t row) const  returning 0..kMaxKey.
+// KeyFn: struct with  __device__ void load_query(uint32_t q)  (all threads of the CTA call it),
+// __device__ uint32_t key(uint64_t row) const  (smaller is better), static constexpr int kKeyBits (8 or 32:
+// how many low bits of the key are significant) and kInvalidKey (rows with this key never match).
 struct ExactScratch {
     unsigned long long hist[256];    // keys 0..255
     unsigned long long digit[256];   // radix pass histogram
@@ -109,26 +110,36 @@ exact_select_kernel(KeyFn fn, const uint64_t *__restrict__ ids, uint64_t id_base
     for (uint32_t q = 0; q < nq; ++q) {
         if (!flags[q]) continue;
         fn.load_query(q);
-        // ---- 1. key histogram
-        if (gtid < 256) scr->hist[gtid] = 0;
+        // ---- 1. k-th smallest key: MSB-first 8-bit radix select over KeyFn::kKeyBits bits
         if (gtid == 0) scr->out_count = 0;
-        s_hist[threadIdx.x] = 0;
-        grid.sync();
-        for (uint64_t r = gtid; r < N; r += gsize) atomicAdd(&s_hist[fn.key(r) & 255], 1ULL);
-        __syncthreads();
-        if (s_hist[threadIdx.x]) atomicAdd(&scr->hist[threadIdx.x], s_hist[threadIdx.x]);
-        grid.sync();
-        uint32_t kstar = 256; uint64_t need = 0;
-        {
-            uint64_t cum = 0;
-            for (uint32_t d = 0; d < 256; ++d) {
-                uint64_t h = scr->hist[d];
-                if (cum + h >= k) { kstar = d; need = k - cum; break; }
+        uint32_t kprefix = 0; uint64_t need = k; bool have_k = true;
+        for (int shift = KeyFn::kKeyBits - 8; shift >= 0; shift -= 8) {
+            if (gtid < 256) scr->hist[gtid] = 0;
+            s_hist[threadIdx.x] = 0;
+            grid.sync();
+            const uint32_t hi_mask = shift + 8 >= 32 ? 0u : ~0u << (shift + 8);
+            for (uint64_t r = gtid; r < N; r += gsize) {
+                uint32_t key = fn.key(r);
+                if ((key & hi_mask) != kprefix) continue;
+                atomicAdd(&s_hist[(key >> shift) & 255], 1ULL);
+            }
+            __syncthreads();
+            if (s_hist[threadIdx.x]) atomicAdd(&scr->hist[threadIdx.x], s_hist[threadIdx.x]);
+            grid.sync();
+            uint64_t cum = 0; uint32_t dig = 256;
+            for (uint32_t b = 0; b < 256; ++b) {
+                uint64_t h = scr->hist[b];
+                if (cum + h >= need) { dig = b; break; }
                 cum += h;
             }
+            if (dig == 256) { have_k = false; dig = 255; cum = 0; }  // fewer than k rows in total
+            need -= cum;
+            kprefix |= dig << shift;
+            grid.sync();  // everyone has read hist[] before it is cleared again
         }
+        const uint32_t kstar = have_k ? kprefix : 0xFFFFFFFFu;
         uint64_t idstar = UINT64_MAX;  // fewer than k rows in total: take everything
-        if (kstar < 256) {
+        if (have_k) {
             // ---- 2. radix select of the need-th smallest id among rows with key == k*
             uint64_t prefix = 0; uint64_t want = need;
             for (int shift = 56; shift >= 0; shift -= 8) {
@@ -160,7 +171,7 @@ exact_select_kernel(KeyFn fn, const uint64_t *__restrict__ ids, uint64_t id_base
         // ---- 3. collect
         for (uint64_t r = gtid; r < N; r += gsize) {
             uint32_t d = fn.key(r);
-            if (d > kstar) continue;
+            if (d > kstar || d == KeyFn::kInvalidKey) continue;
             uint64_t id = ids ? ids[r] : id_base + r;
             if (d == kstar && id > idstar) continue;
             unsigned int pos = atomicAdd(&scr->out_count, 1u);
@@ -180,7 +191,7 @@ exact_select_kernel(KeyFn fn, const uint64_t *__restrict__ ids, uint64_t id_base
                     rank += (dj < d || (dj == d && (idj < id || (idj == id && j < i))));
                 }
                 ids_out[(size_t)q * k + rank] = id;
-                keys_out[(size_t)q * k + rank] = key_flip ? key_flip - d : d;
+                keys_out[(size_t)q * k + rank] = KeyFn::report(d, key_flip);
             }
         }
         grid.sync();

@@ -64,6 +64,12 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self._L.ucfp_ctx_kernel_launches(self._h))
 
+    def last_scan_fallbacks(self) -> int:
+        """Queries of the most recent scan that overflowed and were recomputed by the exact selection."""
+        n = C.c_uint64(0)
+        check(self._L.ucfp_ctx_last_scan_fallbacks(self._h, C.byref(n)))
+        return int(n.value)
+
     def profile_begin(self) -> None:
         check(self._L.ucfp_ctx_profile_begin(self._h))
 
