@@ -70,3 +70,15 @@ def test_product_never_imports_the_oracle():
                     if re.search(r"^\s*(import|from)\s+oracle\b|#include\s+\"[^\"]*oracle/", text, re.M):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_exact_arithmetic_kernels_contain_no_fma():
+    """docs/HASH_SPEC.md fixes separately rounded mul and add.  ptxas contracts mul.f32x2 + add.f32x2 into FFMA2
+    even with -fmad=false, so the build is checked at the SASS level: no FFMA in the image-hash object."""
+    obj = os.path.join(ROOT, "ucfp_b200", "csrc", "_obj", "image.o")
+    if not os.path.exists(obj):
+        from ucfp_b200 import build
+        build.build(force=True)
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    assert "FMUL" in sass and "FADD" in sass
+    assert not re.search(r"\bFFMA2?\b", sass), "fused multiply-add found in image.o"

@@ -29,7 +29,7 @@ __constant__ float c_dct_cos[8][32] = { UCFP_DCT_VALUES };  // same literals as 
 constexpr int kRegions = 17;                 // whole image + 4x4 blocks
 constexpr int kHOuts = 49;                   // 32 + 9 + 8 horizontal outputs per region column set
 constexpr int kVOuts = 40;                   // 32 + 8 vertical outputs per region row set
-constexpr size_t kRowBufBudget = 64 * 1024;  // bytes of shared memory for buffered vertical rows
+constexpr size_t kRowBufBudget = 32 * 1024;  // bytes of shared memory for buffered vertical rows
 constexpr int kMaxBandRows = 64;
 
 struct Taps { int left, n, woff; };                         // one output sample of a 1-D Triangle pass
@@ -48,7 +48,20 @@ struct ShapeDev {
     int band_rows, nbands, max_fin;
 };
 
-struct ImgDev { const uint8_t *pixels; uint64_t stride; uint32_t out_index; uint32_t aligned4; };
+struct RegionGrids {         // shared memory, per CTA, lives for the whole image
+    uint8_t g32[kRegions][1024];
+    uint8_t g98[kRegions][72];
+    uint8_t g8[kRegions][64];
+};
+struct HashScratch {         // shared memory used only by hash_regions (may alias streaming buffers)
+    float R[kRegions][32][8];
+    float D[kRegions][64];
+    float C[8][32];
+    float med_lo[kRegions], med_hi[kRegions];
+};
+constexpr size_t kGridsBytes = (sizeof(RegionGrids) + 127) & ~size_t(127);
+
+struct ImgDev { const uint8_t *pixels; uint64_t stride; uint32_t out_index; uint32_t aligned4; /* 0 no, 1 = 4 B, 2 = 16 B rows (bulk) */ };
 
 // ---------------------------------------------------------------------------------------------
 // Host: tap tables.  Same f32 arithmetic as `image` 0.25 imageops::sample (spec section 2).
@@ -84,11 +97,14 @@ std::vector<HostTaps> make_taps(int src, int dst) {
     return t;
 }
 
+struct StreamSmem { uint32_t off_rowbuf, off_ring, off_bars, stage_bytes, stages, chunk_rows, row_pitch, row_words; };
+
 struct ShapeTables {
     ShapeDev dev{};
     void *blob = nullptr;
     bool streamable = false;
     int threads = 0, cpt = 0;
+    StreamSmem lay{};
     size_t stream_smem = 0;
 };
 
@@ -101,10 +117,19 @@ int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
     ShapeDev &d = st.dev;
     d.w = w; d.h = h;
     for (int i = 0; i <= 4; ++i) { d.by[i] = (int)((long long)i * h / 4); d.bx[i] = (int)((long long)i * w / 4); }
+    // Identical weight vectors are stored once (for integer ratios every interior output shares one vector), so
+    // that the lanes of a warp working on different outputs read the same addresses (a broadcast).
+    std::map<std::vector<uint32_t>, int> seen;
     auto emit = [&](std::vector<Taps> &dst, int base, const std::vector<HostTaps> &t, int offset) {
         for (size_t o = 0; o < t.size(); ++o) {
-            dst[base + o] = Taps{t[o].left + offset, t[o].n, (int)wts.size()};
-            wts.insert(wts.end(), t[o].w.begin(), t[o].w.end());
+            std::vector<uint32_t> key(t[o].w.size());
+            memcpy(key.data(), t[o].w.data(), key.size() * 4);
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                it = seen.emplace(std::move(key), (int)wts.size()).first;
+                wts.insert(wts.end(), t[o].w.begin(), t[o].w.end());
+            }
+            dst[base + o] = Taps{t[o].left + offset, t[o].n, it->second};
         }
     };
     // vertical tap sets (also the source of the streaming tables)
@@ -179,8 +204,8 @@ int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
             std::vector<int> cnt(nb, 0);
             for (int y : fin_row_y) cnt[y / cand]++;
             for (int c : cnt) mx = c > mx ? c : mx;
-            if ((size_t)mx * w * 4 <= kRowBufBudget || cand == 1) {
-                if ((size_t)mx * w * 4 > kRowBufBudget) { ok = false; break; }
+            if ((size_t)mx * (w + w / 32 + 1) * 4 <= kRowBufBudget || cand == 1) {
+                if ((size_t)mx * (w + w / 32 + 1) * 4 > kRowBufBudget) { ok = false; break; }
                 band_rows = cand; max_fin = mx;
                 band_off.assign(nb + 1, 0);
                 for (int b = 0; b < nb; ++b) band_off[b + 1] = band_off[b] + cnt[b];
@@ -193,6 +218,24 @@ int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
     if (threads > 512) ok = false;  // wider than 4096 px: generic kernel
     if (threads < 128) threads = 128;
     st.streamable = ok; st.threads = threads; st.cpt = cpt;
+    if (ok) {   // shared-memory plan of image_stream_kernel
+        auto up = [](size_t x, size_t a) { return (x + a - 1) / a * a; };
+        StreamSmem &L = st.lay;
+        L.row_pitch = (uint32_t)up(3 * (size_t)w, 16);
+        uint32_t rs = 1;
+        while (rs * 2 <= (uint32_t)band_rows && (size_t)rs * 2 * L.row_pitch <= 24 * 1024) rs *= 2;
+        L.chunk_rows = rs;
+        L.stage_bytes = (uint32_t)up((size_t)rs * L.row_pitch, 128);
+        L.off_rowbuf = (uint32_t)kGridsBytes;
+        L.row_words = (uint32_t)(w + (w >> 5) + 1);       // skewed row: one pad word per 32
+        L.off_ring = (uint32_t)(L.off_rowbuf + up((size_t)max_fin * L.row_words * 4, 128));
+        L.stages = (L.off_ring + 3 * (size_t)L.stage_bytes <= 108 * 1024) ? 3 : 2;
+        L.off_bars = L.off_ring + L.stages * L.stage_bytes;
+        size_t total = L.off_bars + 8 * L.stages;
+        size_t hash_end = L.off_rowbuf + sizeof(HashScratch);
+        st.stream_smem = up(total > hash_end ? total : hash_end, 128);
+        if (st.stream_smem > 200 * 1024) st.streamable = false;
+    }
 
     // ---- upload one blob
     auto align16 = [](size_t x) { return (x + 15) & ~size_t(15); };
@@ -226,15 +269,6 @@ int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
 // ---------------------------------------------------------------------------------------------
 // Device: shared pieces
 // ---------------------------------------------------------------------------------------------
-struct RegionGrids {         // shared memory, per CTA
-    uint8_t g32[kRegions][1024];
-    uint8_t g98[kRegions][72];
-    uint8_t g8[kRegions][64];
-    float R[kRegions][32][8];
-    float D[kRegions][64];
-    float C[8][32];
-    float med_lo[kRegions], med_hi[kRegions];
-};
 
 __device__ __forceinline__ uint32_t luma_u8(uint32_t r, uint32_t g, uint32_t b) {
     // `image` 0.25 rgb_to_luma: (2126 R + 7152 G + 722 B) / 10000, truncating.  The sum is < 2^22, for
@@ -244,11 +278,18 @@ __device__ __forceinline__ uint32_t luma_u8(uint32_t r, uint32_t g, uint32_t b) 
 }
 
 // One output of a horizontal pass over a row of f32 vertical sums: sequential sum, clamp, round half away.
+// kSkew: the row is stored with one pad word per 32 (element x at x + (x >> 5)), so that lanes reading at a
+// constant stride (the resize ratio, usually a power of two) fall into different shared-memory banks.
+__device__ __forceinline__ int skew(int x) { return x + (x >> 5); }
+
+template <bool kSkew>
 __device__ __forceinline__ uint8_t hsample(const float *row, Taps t, const float *__restrict__ wts) {
     float acc = 0.0f;
     const float *wp = wts + t.woff;
-    const float *rp = row + t.left;
-    for (int i = 0; i < t.n; ++i) acc = acc + rp[i] * __ldg(wp + i);
+    for (int i = 0; i < t.n; ++i) {
+        const int x = t.left + i;
+        acc = acc + row[kSkew ? skew(x) : x] * __ldg(wp + i);
+    }
     acc = acc < 0.0f ? 0.0f : acc;
     acc = acc > 255.0f ? 255.0f : acc;
     float fl = truncf(acc);
@@ -260,24 +301,25 @@ __device__ __forceinline__ uint8_t hsample(const float *row, Taps t, const float
 // whole->32 rows: 32 items; whole->8 rows: 9 + 8; block rows: x4 block columns.
 __device__ __forceinline__ int fin_items(int stream) { return stream == 0 ? 32 : stream == 1 ? 17 : stream == 2 ? 128 : 68; }
 
+template <bool kSkew>
 __device__ __forceinline__ void hpass_item(RegionGrids &G, const ShapeDev &S, FinDesc f, int item, const float *row) {
     int colset = 0, sub = item;
     if (f.stream >= 2) { int per = f.stream == 2 ? 32 : 17; colset = 1 + item / per; sub = item % per; }
     int region = f.stream < 2 ? 0 : 1 + 4 * f.r + (colset - 1);
     const Taps *ho = S.hout + colset * kHOuts;
     if ((f.stream & 1) == 0) {
-        G.g32[region][f.o * 32 + sub] = hsample(row, ho[sub], S.wts);
+        G.g32[region][f.o * 32 + sub] = hsample<kSkew>(row, ho[sub], S.wts);
     } else if (sub < 9) {
-        G.g98[region][f.o * 9 + sub] = hsample(row, ho[32 + sub], S.wts);
+        G.g98[region][f.o * 9 + sub] = hsample<kSkew>(row, ho[32 + sub], S.wts);
     } else {
-        G.g8[region][f.o * 8 + (sub - 9)] = hsample(row, ho[41 + (sub - 9)], S.wts);
+        G.g8[region][f.o * 8 + (sub - 9)] = hsample<kSkew>(row, ho[41 + (sub - 9)], S.wts);
     }
 }
 
 // PHash / AHash / DHash of the 17 regions from the u8 grids in shared memory (spec sections 3-5).
-__device__ void hash_regions(RegionGrids &G, uint32_t algo_mask, uint64_t *out /* 51 words */) {
+__device__ void hash_regions(RegionGrids &G, HashScratch &H, uint32_t algo_mask, uint64_t *out /* 51 words */) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < 256; i += nt) G.C[i >> 5][i & 31] = c_dct_cos[i >> 5][i & 31];
+    for (int i = tid; i < 256; i += nt) H.C[i >> 5][i & 31] = c_dct_cos[i >> 5][i & 31];
     __syncthreads();
     if (algo_mask & UCFP_ALGO_PHASH) {
         for (int it = tid; it < kRegions * 256; it += nt) {       // R[y][v] = sum_x g[y][x] * C[v][x]
@@ -285,25 +327,25 @@ __device__ void hash_regions(RegionGrids &G, uint32_t algo_mask, uint64_t *out /
             const uint8_t *g = &G.g32[reg][y * 32];
             float t = 0.0f;
 #pragma unroll 8
-            for (int x = 0; x < 32; ++x) t = t + (float)g[x] * G.C[v][x];
-            G.R[reg][y][v] = t;
+            for (int x = 0; x < 32; ++x) t = t + (float)g[x] * H.C[v][x];
+            H.R[reg][y][v] = t;
         }
         __syncthreads();
         for (int it = tid; it < kRegions * 64; it += nt) {        // D[u][v] = sum_y C[u][y] * R[y][v]
             int reg = it >> 6, u = (it >> 3) & 7, v = it & 7;
             float t = 0.0f;
 #pragma unroll 8
-            for (int y = 0; y < 32; ++y) t = t + G.C[u][y] * G.R[reg][y][v];
-            G.D[reg][it & 63] = t;
+            for (int y = 0; y < 32; ++y) t = t + H.C[u][y] * H.R[reg][y][v];
+            H.D[reg][it & 63] = t;
         }
         __syncthreads();
         for (int it = tid; it < kRegions * 64; it += nt) {        // ranks 31 and 32 of the 64 coefficients
             int reg = it >> 6, i = it & 63;
-            float val = G.D[reg][i];
+            float val = H.D[reg][i];
             int rank = 0;
-            for (int j = 0; j < 64; ++j) { float o = G.D[reg][j]; rank += (o < val) || (o == val && j < i); }
-            if (rank == 31) G.med_lo[reg] = val;
-            if (rank == 32) G.med_hi[reg] = val;
+            for (int j = 0; j < 64; ++j) { float o = H.D[reg][j]; rank += (o < val) || (o == val && j < i); }
+            if (rank == 31) H.med_lo[reg] = val;
+            if (rank == 32) H.med_hi[reg] = val;
         }
         __syncthreads();
     }
@@ -318,8 +360,8 @@ __device__ void hash_regions(RegionGrids &G, uint32_t algo_mask, uint64_t *out /
             a = (uint64_t)hi << 32 | lo;
         }
         if (algo_mask & UCFP_ALGO_PHASH) {
-            float med = (G.med_lo[reg] + G.med_hi[reg]) * 0.5f;
-            uint32_t lo = __ballot_sync(0xffffffffu, G.D[reg][lane] > med), hi = __ballot_sync(0xffffffffu, G.D[reg][lane + 32] > med);
+            float med = (H.med_lo[reg] + H.med_hi[reg]) * 0.5f;
+            uint32_t lo = __ballot_sync(0xffffffffu, H.D[reg][lane] > med), hi = __ballot_sync(0xffffffffu, H.D[reg][lane + 32] > med);
             p = (uint64_t)hi << 32 | lo;
         }
         if (algo_mask & UCFP_ALGO_DHASH) {
@@ -341,6 +383,7 @@ image_generic_kernel(ShapeDev S, const ImgDev *__restrict__ imgs, uint32_t n, ui
                      size_t scratch_per_cta, uint64_t *out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RegionGrids &G = *reinterpret_cast<RegionGrids *>(smem_raw);
+    HashScratch &H = *reinterpret_cast<HashScratch *>(smem_raw + kGridsBytes);
     const int w = S.w, h = S.h, tid = threadIdx.x, nt = blockDim.x;
     uint8_t *gray = scratch + (size_t)blockIdx.x * scratch_per_cta;
     float *T = reinterpret_cast<float *>(gray + (((size_t)w * h + 15) & ~size_t(15)));  // [5][40][w]
@@ -366,10 +409,10 @@ image_generic_kernel(ShapeDev S, const ImgDev *__restrict__ imgs, uint32_t n, ui
             f.stream = (uint8_t)((set ? 2 : 0) + (o >= 32 ? 1 : 0));
             f.o = (uint8_t)(o >= 32 ? o - 32 : o);
             f.r = (uint8_t)(set ? set - 1 : 0); f.pad = 0;
-            if (item < fin_items(f.stream)) hpass_item(G, S, f, item, T + (size_t)vo * w);
+            if (item < fin_items(f.stream)) hpass_item<false>(G, S, f, item, T + (size_t)vo * w);
         }
         __syncthreads();
-        hash_regions(G, algo_mask, out + (size_t)I.out_index * 51);
+        hash_regions(G, H, algo_mask, out + (size_t)I.out_index * 51);
         __syncthreads();
     }
 }
@@ -377,16 +420,86 @@ image_generic_kernel(ShapeDev S, const ImgDev *__restrict__ imgs, uint32_t n, ui
 // ---------------------------------------------------------------------------------------------
 // Streaming kernel: one pass over the pixels, vertical sums in registers.
 // ---------------------------------------------------------------------------------------------
-template <int CPT, int MAXT>
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (UBLKCP in SASS)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+// luma of the 4 pixels packed in the 12 bytes {a, b, c}: two IDP.2A per pixel, no byte extraction
+#define UCFP_W16(lo, hi) ((uint32_t)(lo) | ((uint32_t)(hi) << 16))
+__device__ __forceinline__ float luma_to_f32(uint32_t s) {
+    // floor(s / 10000) as in luma_u8, then u32 -> f32 exactly by the 2^23 trick (value < 256)
+    return __uint_as_float(__umulhi(s, 429497u) | 0x4B000000u) - 8388608.0f;
+}
+__device__ __forceinline__ void luma4(uint32_t a, uint32_t b, uint32_t c, float &v0, float &v1, float &v2, float &v3) {
+    v0 = luma_to_f32(__dp2a_hi(UCFP_W16(722, 0), a, __dp2a_lo(UCFP_W16(2126, 7152), a, 0u)));     // R G B = a0 a1 a2
+    v1 = luma_to_f32(__dp2a_lo(UCFP_W16(7152, 722), b, __dp2a_hi(UCFP_W16(0, 2126), a, 0u)));     //         a3 b0 b1
+    v2 = luma_to_f32(__dp2a_lo(UCFP_W16(722, 0), c, __dp2a_hi(UCFP_W16(2126, 7152), b, 0u)));     //         b2 b3 c0
+    v3 = luma_to_f32(__dp2a_hi(UCFP_W16(7152, 722), c, __dp2a_lo(UCFP_W16(0, 2126), c, 0u)));     //         c1 c2 c3
+}
+
+// {v * w0, v * w1} with one FMUL2.  The products feed SCALAR adds: ptxas contracts mul.f32x2 + add.f32x2 into
+// FFMA2 even for .rn operands and -fmad=false, which would break the spec's separately rounded mul and add.
+__device__ __forceinline__ void mul2(float v, uint64_t w01, float &p0, float &p1) {
+    uint64_t vv, r;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(vv) : "f"(v));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(vv), "l"(w01));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(p0), "=f"(p1) : "l"(r));
+}
+
+template <int CPT, int MAXT, bool BULK>
 __global__ void __launch_bounds__(MAXT)
-image_stream_kernel(ShapeDev S, const ImgDev *__restrict__ imgs, uint32_t algo_mask, uint64_t *out) {
+image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, uint32_t algo_mask, uint64_t *out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RegionGrids &G = *reinterpret_cast<RegionGrids *>(smem_raw);
-    float *rowbuf = reinterpret_cast<float *>(smem_raw + ((sizeof(RegionGrids) + 15) & ~size_t(15)));  // [max_fin][w]
+    float *rowbuf = reinterpret_cast<float *>(smem_raw + L.off_rowbuf);          // [max_fin][row_words], skewed rows
+    unsigned char *ring = smem_raw + L.off_ring;                                 // [stages][chunk_rows * row_pitch]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + L.off_bars);        // [stages]
+    HashScratch &H = *reinterpret_cast<HashScratch *>(smem_raw + L.off_rowbuf);  // aliases the streaming buffers
     const int w = S.w, h = S.h, tid = threadIdx.x, nt = blockDim.x;
     const ImgDev I = imgs[blockIdx.x];
-    const int x0 = tid * CPT;
-    const bool have = x0 < w;
+    // threads past the last column group redo the last group's arithmetic and simply never store
+    const int x0 = min(tid * CPT, ((w - 1) / CPT) * CPT);
+    const bool owner = tid * CPT < w;
+    const int RS = (int)L.chunk_rows, nchunks = (h + RS - 1) / RS, NS = (int)L.stages;
+    const uint32_t row_bytes = 3u * (uint32_t)w;
+    const uint32_t src_pitch = BULK ? (I.stride == row_bytes ? row_bytes : L.row_pitch) : 0;
+    const int row_words = (int)L.row_words;
+
+    auto issue = [&](int c) {            // thread 0: stage chunk c with TMA bulk copies
+        const int s = c % NS, rows = min(RS, h - c * RS);
+        unsigned char *dst = ring + (size_t)s * L.stage_bytes;
+        const uint8_t *src = I.pixels + (size_t)c * RS * I.stride;
+        mbar_expect_tx(&full[s], rows * row_bytes);
+        if (I.stride == row_bytes) bulk_g2s(dst, src, rows * row_bytes, &full[s]);
+        else for (int r = 0; r < rows; ++r) bulk_g2s(dst + (size_t)r * L.row_pitch, src + (size_t)r * I.stride, row_bytes, &full[s]);
+    };
+    if (BULK) {
+        if (tid == 0) {
+            for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) for (int c = 0; c < min(NS, nchunks); ++c) issue(c);
+    }
 
     float acc[4][3][CPT];
 #pragma unroll
@@ -396,71 +509,77 @@ image_stream_kernel(ShapeDev S, const ImgDev *__restrict__ imgs, uint32_t algo_m
 #pragma unroll
             for (int c = 0; c < CPT; ++c) acc[s][j][c] = 0.0f;
 
-    for (int band = 0; band < S.nbands; ++band) {
-        const int y_lo = band * S.band_rows, y_hi = min(h, y_lo + S.band_rows);
-        int slot = 0;
-        if (have) {
-            for (int y = y_lo; y < y_hi; ++y) {
-                float v[CPT];
-                const uint8_t *px = I.pixels + (size_t)y * I.stride + 3 * (size_t)x0;
-                if (CPT % 4 == 0 && I.aligned4 && x0 + CPT <= w) {
-                    const uint32_t *p32 = reinterpret_cast<const uint32_t *>(px);
+    int slot = 0, band = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int y_lo = c * RS, y_hi = min(h, y_lo + RS);
+        if (BULK) mbar_wait(&full[c % NS], (c / NS) & 1);
+        const uint8_t *base = BULK ? ring + (size_t)(c % NS) * L.stage_bytes + 3 * (size_t)x0
+                                   : I.pixels + (size_t)y_lo * I.stride + 3 * (size_t)x0;
+        const size_t pitch = BULK ? src_pitch : I.stride;
+        for (int y = y_lo; y < y_hi; ++y) {
+            float v[CPT];
+            const uint8_t *px = base + (size_t)(y - y_lo) * pitch;
+            if (CPT % 4 == 0 && (BULK || I.aligned4) && w % CPT == 0) {
+                const uint32_t *p32 = reinterpret_cast<const uint32_t *>(px);
 #pragma unroll
-                    for (int g = 0; g < CPT / 4; ++g) {  // 4 pixels = 12 bytes = 3 words
-                        uint32_t a = __ldg(p32 + 3 * g), b = __ldg(p32 + 3 * g + 1), c2 = __ldg(p32 + 3 * g + 2);
-                        v[(4 * g) % CPT] = (float)luma_u8(a & 255u, (a >> 8) & 255u, (a >> 16) & 255u);
-                        v[(4 * g + 1) % CPT] = (float)luma_u8(a >> 24, b & 255u, (b >> 8) & 255u);
-                        v[(4 * g + 2) % CPT] = (float)luma_u8((b >> 16) & 255u, b >> 24, c2 & 255u);
-                        v[(4 * g + 3) % CPT] = (float)luma_u8((c2 >> 8) & 255u, (c2 >> 16) & 255u, c2 >> 24);
-                    }
-                } else {
+                for (int g = 0; g < CPT / 4; ++g)   // 4 pixels = 12 bytes = 3 words
+                    luma4(p32[3 * g], p32[3 * g + 1], p32[3 * g + 2], v[(4 * g) % CPT], v[(4 * g + 1) % CPT], v[(4 * g + 2) % CPT],
+                          v[(4 * g + 3) % CPT]);
+            } else {
 #pragma unroll
-                    for (int c = 0; c < CPT; ++c) {
-                        v[c] = 0.0f;
-                        if (x0 + c < w) v[c] = (float)luma_u8(__ldg(px + 3 * c), __ldg(px + 3 * c + 1), __ldg(px + 3 * c + 2));
-                    }
+                for (int cc = 0; cc < CPT; ++cc) {
+                    const int xc = min(cc, w - 1 - x0);   // CPT > 1 and a ragged last group: repeat the last column
+                    v[cc] = luma_to_f32(2126u * px[3 * xc] + 7152u * px[3 * xc + 1] + 722u * px[3 * xc + 2]);
                 }
+            }
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(S.vtab + (size_t)s * h + y));  // uniform
-                    const float w0 = __uint_as_float(raw.x), w1 = __uint_as_float(raw.y), w2 = __uint_as_float(raw.z);
-                    const int n_active = raw.w & 255, n_finish = (raw.w >> 8) & 255;
+            for (int s = 0; s < 4; ++s) {
+                const ulonglong2 raw = __ldg(reinterpret_cast<const ulonglong2 *>(S.vtab + (size_t)s * h + y));  // uniform
+                const float w2 = __uint_as_float((uint32_t)raw.y);
+                const uint32_t meta = (uint32_t)(raw.y >> 32);
+                const int n_active = meta & 255, n_finish = (meta >> 8) & 255;
 #pragma unroll
-                    for (int c = 0; c < CPT; ++c) {
-                        acc[s][0][c] = acc[s][0][c] + v[c] * w0;
-                        acc[s][1][c] = acc[s][1][c] + v[c] * w1;
+                for (int cc = 0; cc < CPT; ++cc) {
+                    float p0, p1;
+                    mul2(v[cc], raw.x, p0, p1);
+                    acc[s][0][cc] = acc[s][0][cc] + p0;
+                    acc[s][1][cc] = acc[s][1][cc] + p1;
+                }
+                if (n_active == 3) {
+#pragma unroll
+                    for (int cc = 0; cc < CPT; ++cc) acc[s][2][cc] = acc[s][2][cc] + v[cc] * w2;
+                }
+                for (int f = 0; f < n_finish; ++f) {  // uniform: the lowest active output of this pass is complete
+                    float *dst = rowbuf + (size_t)slot * row_words;
+#pragma unroll
+                    for (int cc = 0; cc < CPT; ++cc) {
+                        if (owner && x0 + cc < w) dst[skew(x0 + cc)] = acc[s][0][cc];
+                        acc[s][0][cc] = acc[s][1][cc]; acc[s][1][cc] = acc[s][2][cc]; acc[s][2][cc] = 0.0f;
                     }
-                    if (n_active == 3) {
-#pragma unroll
-                        for (int c = 0; c < CPT; ++c) acc[s][2][c] = acc[s][2][c] + v[c] * w2;
-                    }
-                    for (int f = 0; f < n_finish; ++f) {  // uniform: the lowest active output of this pass is complete
-                        float *dst = rowbuf + (size_t)slot * w + x0;
-#pragma unroll
-                        for (int c = 0; c < CPT; ++c) {
-                            if (x0 + c < w) dst[c] = acc[s][0][c];
-                            acc[s][0][c] = acc[s][1][c]; acc[s][1][c] = acc[s][2][c]; acc[s][2][c] = 0.0f;
-                        }
-                        slot++;
-                    }
+                    slot++;
                 }
             }
         }
-        __syncthreads();
-        // horizontal passes over the rows finished in this band
-        const int f_lo = S.band_off[band], f_hi = S.band_off[band + 1];
-        int base = 0;
-        for (int fi = f_lo; fi < f_hi; ++fi) {
-            const FinDesc f = S.fin[fi];
-            const int items = fin_items(f.stream);
-            // threads [base, base + items) modulo nt take this row's outputs: rows of a band run side by side
-            for (int it = (tid - base % nt + nt) % nt; it < items; it += nt)
-                hpass_item(G, S, f, it, rowbuf + (size_t)(fi - f_lo) * w);
-            base += items;
+        __syncthreads();   // the stage is consumed, finished rows are visible
+        if (BULK && tid == 0 && c + NS < nchunks) issue(c + NS);
+        if (y_hi == h || y_hi % S.band_rows == 0) {
+            // horizontal passes over the rows finished in this band
+            const int f_lo = S.band_off[band], f_hi = S.band_off[band + 1];
+            int ibase = 0;
+            for (int fi = f_lo; fi < f_hi; ++fi) {
+                const FinDesc f = S.fin[fi];
+                const int items = fin_items(f.stream);
+                // threads [ibase, ibase + items) modulo nt take this row's outputs: rows of a band run side by side
+                for (int it = (tid - ibase % nt + nt) % nt; it < items; it += nt)
+                    hpass_item<true>(G, S, f, it, rowbuf + (size_t)(fi - f_lo) * row_words);
+                ibase += items;
+            }
+            band++;
+            slot = 0;
+            __syncthreads();
         }
-        __syncthreads();
     }
-    hash_regions(G, algo_mask, out + (size_t)I.out_index * 51);
+    hash_regions(G, H, algo_mask, out + (size_t)I.out_index * 51);
 }
 
 }  // namespace
@@ -541,8 +660,10 @@ int image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *descs, size_t n, uint
         std::vector<Item> &items = kv.second;
         std::vector<ImgDev> hostdesc(items.size());
         for (size_t j = 0; j < items.size(); ++j) {
-            bool al = ((uintptr_t)items[j].dev_pixels % 4 == 0) && (items[j].stride % 4 == 0);
-            hostdesc[j] = ImgDev{items[j].dev_pixels, items[j].stride, (uint32_t)items[j].idx, al ? 1u : 0u};
+            const uintptr_t base = (uintptr_t)items[j].dev_pixels;
+            uint32_t al = (base % 4 == 0 && items[j].stride % 4 == 0) ? 1u : 0u;
+            if (base % 16 == 0 && items[j].stride % 16 == 0 && (3 * (size_t)w) % 16 == 0) al = 2u;   // TMA bulk staging
+            hostdesc[j] = ImgDev{items[j].dev_pixels, items[j].stride, (uint32_t)items[j].idx, al};
         }
         // one descriptor buffer per group: the copy below must finish before the vector dies
         DevBuf descbuf;
@@ -551,16 +672,18 @@ int image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *descs, size_t n, uint
         uint64_t *out_words = reinterpret_cast<uint64_t *>(out_dev);
         double units = (3.0 * w * h + 408.0) * (double)items.size();
         if (T.streamable) {
-            size_t smem = ((sizeof(RegionGrids) + 15) & ~size_t(15)) + (size_t)T.dev.max_fin * w * 4;
+            size_t smem = T.stream_smem;
             ProfScope ps(ctx, UCFP_PROF_IMAGE_HASH, units);
             auto launch = [&](auto kern) -> int {
                 UCFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-                kern<<<(unsigned)items.size(), T.threads, smem, st>>>(T.dev, descbuf.as<ImgDev>(), algo_mask, out_words);
+                kern<<<(unsigned)items.size(), T.threads, smem, st>>>(T.dev, T.lay, descbuf.as<ImgDev>(), algo_mask, out_words);
                 return UCFP_OK;
             };
-            if (T.cpt == 1) UCFP_TRY(launch(image_stream_kernel<1, 512>));
-            else if (T.cpt == 4) UCFP_TRY(launch(image_stream_kernel<4, 256>));
-            else UCFP_TRY(launch(image_stream_kernel<8, 512>));
+            bool all_bulk = true;
+            for (const ImgDev &d : hostdesc) all_bulk = all_bulk && d.aligned4 == 2;
+            if (T.cpt == 1) UCFP_TRY(all_bulk ? launch(image_stream_kernel<1, 512, true>) : launch(image_stream_kernel<1, 512, false>));
+            else if (T.cpt == 4) UCFP_TRY(all_bulk ? launch(image_stream_kernel<4, 256, true>) : launch(image_stream_kernel<4, 256, false>));
+            else UCFP_TRY(all_bulk ? launch(image_stream_kernel<8, 512, true>) : launch(image_stream_kernel<8, 512, false>));
         } else {
             size_t per = (((size_t)w * h + 15) & ~size_t(15)) + (size_t)5 * kVOuts * w * 4 + 256;
             size_t grid = items.size();
@@ -568,9 +691,9 @@ int image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *descs, size_t n, uint
             if (grid * per > budget) grid = budget / per ? budget / per : 1;
             if (grid > (size_t)ctx->sm_count * 4) grid = (size_t)ctx->sm_count * 4;
             UCFP_TRY(ctx->img_tables_dev.reserve(grid * per));
-            UCFP_CUDA_TRY(cudaFuncSetAttribute(image_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionGrids)));
+            UCFP_CUDA_TRY(cudaFuncSetAttribute(image_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGridsBytes + sizeof(HashScratch))));
             ProfScope ps(ctx, UCFP_PROF_IMAGE_HASH, units);
-            image_generic_kernel<<<(unsigned)grid, 256, sizeof(RegionGrids), st>>>(T.dev, descbuf.as<ImgDev>(), (uint32_t)items.size(),
+            image_generic_kernel<<<(unsigned)grid, 256, kGridsBytes + sizeof(HashScratch), st>>>(T.dev, descbuf.as<ImgDev>(), (uint32_t)items.size(),
                                                                                   algo_mask, ctx->img_tables_dev.as<uint8_t>(), per, out_words);
         }
         count_launch(ctx);
