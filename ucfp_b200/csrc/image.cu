@@ -33,7 +33,10 @@ constexpr size_t kRowBufBudget = 32 * 1024;  // bytes of shared memory for buffe
 constexpr int kMaxBandRows = 64;
 
 struct Taps { int left, n, woff; };                         // one output sample of a 1-D Triangle pass
-struct __align__(16) VEntry { float w[3]; uint8_t n_active, n_finish; uint16_t pad; };
+struct __align__(16) VEntry { float w[3]; uint8_t n_active, n_finish; uint16_t pad; };   // host-side, per (pass, row)
+// Device-side per-row table of the four vertical passes: weights of the two lowest active outputs, the third
+// weight, and flags (byte s: bit 0 = three outputs active, bits 1..3 = outputs completed by this row).
+struct __align__(16) RowEntry { float w01[4][2]; float w2[4]; uint32_t flags; uint32_t pad[3]; };   // 64 bytes
 struct FinDesc { uint8_t stream, o, r, pad; };               // stream: 0 whole->32, 1 whole->8, 2 block->32, 3 block->8
 
 struct ShapeDev {
@@ -42,7 +45,7 @@ struct ShapeDev {
     const Taps *hout;      // [5][49]: column set 0 = whole width, 1 + c = block column c; absolute x
     const Taps *vout;      // [5][40]: row set 0 = whole height, 1 + r = block row r; absolute y
     const float *wts;
-    const VEntry *vtab;    // [4][h] (stream kernel)
+    const RowEntry *rowtab; // [h] (stream kernel)
     const FinDesc *fin;    // finished rows in emission order
     const int *band_off;   // [nbands + 1] into fin
     int band_rows, nbands, max_fin;
@@ -97,7 +100,7 @@ std::vector<HostTaps> make_taps(int src, int dst) {
     return t;
 }
 
-struct StreamSmem { uint32_t off_rowbuf, off_ring, off_bars, stage_bytes, stages, chunk_rows, row_pitch, row_words; };
+struct StreamSmem { uint32_t off_rowbuf, off_ring, off_bars, off_rowtab, stage_bytes, stages, chunk_rows, row_pitch, row_words; };
 
 struct ShapeTables {
     ShapeDev dev{};
@@ -229,9 +232,10 @@ int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
         L.off_rowbuf = (uint32_t)kGridsBytes;
         L.row_words = (uint32_t)(w + (w >> 5) + 1);       // skewed row: one pad word per 32
         L.off_ring = (uint32_t)(L.off_rowbuf + up((size_t)max_fin * L.row_words * 4, 128));
-        L.stages = (L.off_ring + 3 * (size_t)L.stage_bytes <= 108 * 1024) ? 3 : 2;
-        L.off_bars = L.off_ring + L.stages * L.stage_bytes;
-        size_t total = L.off_bars + 8 * L.stages;
+        L.stages = (L.off_ring + 3 * (size_t)L.stage_bytes + 2 * (size_t)band_rows * sizeof(RowEntry) <= 106 * 1024) ? 3 : 2;
+        L.off_bars = L.off_ring + L.stages * L.stage_bytes;          // full[stages], empty[stages]
+        L.off_rowtab = (uint32_t)up(L.off_bars + 16 * L.stages, 16);   // [2][band_rows] RowEntry, double-buffered
+        size_t total = L.off_rowtab + 2 * (size_t)band_rows * sizeof(RowEntry);
         size_t hash_end = L.off_rowbuf + sizeof(HashScratch);
         st.stream_smem = up(total > hash_end ? total : hash_end, 128);
         if (st.stream_smem > 200 * 1024) st.streamable = false;
@@ -240,7 +244,17 @@ int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
     // ---- upload one blob
     auto align16 = [](size_t x) { return (x + 15) & ~size_t(15); };
     size_t off_h = 0, off_v = align16(off_h + hout.size() * sizeof(Taps)), off_w = align16(off_v + vout.size() * sizeof(Taps));
-    size_t off_t = align16(off_w + wts.size() * 4), off_f = align16(off_t + (ok ? vtab.size() * sizeof(VEntry) : 0));
+    std::vector<RowEntry> rowtab(ok ? h : 0);
+    for (int y = 0; ok && y < h; ++y) {
+        RowEntry e{};
+        for (int st4 = 0; st4 < 4; ++st4) {
+            const VEntry &v = vtab[(size_t)st4 * h + y];
+            e.w01[st4][0] = v.w[0]; e.w01[st4][1] = v.w[1]; e.w2[st4] = v.w[2];
+            e.flags |= (uint32_t)((v.n_active == 3 ? 1u : 0u) | ((uint32_t)v.n_finish << 1)) << (8 * st4);
+        }
+        rowtab[y] = e;
+    }
+    size_t off_t = align16(off_w + wts.size() * 4), off_f = align16(off_t + rowtab.size() * sizeof(RowEntry));
     size_t off_b = align16(off_f + (ok ? fin_rows.size() * sizeof(FinDesc) : 0));
     size_t total = align16(off_b + (ok ? band_off.size() * 4 : 0)) + 16;
     std::vector<uint8_t> host(total, 0);
@@ -248,7 +262,7 @@ int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
     memcpy(&host[off_v], vout.data(), vout.size() * sizeof(Taps));
     memcpy(&host[off_w], wts.data(), wts.size() * 4);
     if (ok) {
-        memcpy(&host[off_t], vtab.data(), vtab.size() * sizeof(VEntry));
+        memcpy(&host[off_t], rowtab.data(), rowtab.size() * sizeof(RowEntry));
         memcpy(&host[off_f], fin_rows.data(), fin_rows.size() * sizeof(FinDesc));
         memcpy(&host[off_b], band_off.data(), band_off.size() * 4);
     }
@@ -259,7 +273,7 @@ int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
     d.hout = reinterpret_cast<const Taps *>(b + off_h);
     d.vout = reinterpret_cast<const Taps *>(b + off_v);
     d.wts = reinterpret_cast<const float *>(b + off_w);
-    d.vtab = ok ? reinterpret_cast<const VEntry *>(b + off_t) : nullptr;
+    d.rowtab = ok ? reinterpret_cast<const RowEntry *>(b + off_t) : nullptr;
     d.fin = ok ? reinterpret_cast<const FinDesc *>(b + off_f) : nullptr;
     d.band_off = ok ? reinterpret_cast<const int *>(b + off_b) : nullptr;
     d.band_rows = band_rows; d.nbands = ok ? (h + band_rows - 1) / band_rows : 0; d.max_fin = max_fin;
@@ -464,6 +478,10 @@ __device__ __forceinline__ void mul2(float v, uint64_t w01, float &p0, float &p1
     asm("mov.b64 {%0, %1}, %2;" : "=f"(p0), "=f"(p1) : "l"(r));
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
 template <int CPT, int MAXT, bool BULK>
 __global__ void __launch_bounds__(MAXT)
 image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, uint32_t algo_mask, uint64_t *out) {
@@ -471,16 +489,18 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
     RegionGrids &G = *reinterpret_cast<RegionGrids *>(smem_raw);
     float *rowbuf = reinterpret_cast<float *>(smem_raw + L.off_rowbuf);          // [max_fin][row_words], skewed rows
     unsigned char *ring = smem_raw + L.off_ring;                                 // [stages][chunk_rows * row_pitch]
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + L.off_bars);        // [stages]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + L.off_bars);        // [stages] TMA bytes landed
+    uint64_t *empty = full + L.stages;                                           // [stages] every warp is done reading
+    RowEntry *rtab = reinterpret_cast<RowEntry *>(smem_raw + L.off_rowtab);      // [2][band_rows]
     HashScratch &H = *reinterpret_cast<HashScratch *>(smem_raw + L.off_rowbuf);  // aliases the streaming buffers
-    const int w = S.w, h = S.h, tid = threadIdx.x, nt = blockDim.x;
+    const int w = S.w, h = S.h, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const ImgDev I = imgs[blockIdx.x];
     // threads past the last column group redo the last group's arithmetic and simply never store
     const int x0 = min(tid * CPT, ((w - 1) / CPT) * CPT);
     const bool owner = tid * CPT < w;
-    const int RS = (int)L.chunk_rows, nchunks = (h + RS - 1) / RS, NS = (int)L.stages;
+    const int RS = (int)L.chunk_rows, nchunks = (h + RS - 1) / RS, NS = (int)L.stages, BR = S.band_rows;
     const uint32_t row_bytes = 3u * (uint32_t)w;
-    const uint32_t src_pitch = BULK ? (I.stride == row_bytes ? row_bytes : L.row_pitch) : 0;
+    const size_t pitch = BULK ? (I.stride == row_bytes ? row_bytes : L.row_pitch) : I.stride;
     const int row_words = (int)L.row_words;
 
     auto issue = [&](int c) {            // thread 0: stage chunk c with TMA bulk copies
@@ -491,15 +511,21 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
         if (I.stride == row_bytes) bulk_g2s(dst, src, rows * row_bytes, &full[s]);
         else for (int r = 0; r < rows; ++r) bulk_g2s(dst + (size_t)r * L.row_pitch, src + (size_t)r * I.stride, row_bytes, &full[s]);
     };
-    if (BULK) {
-        if (tid == 0) {
-            for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
-        __syncthreads();
-        if (tid == 0) for (int c = 0; c < min(NS, nchunks); ++c) issue(c);
+    auto load_rowtab = [&](int band) {   // all threads: per-row pass tables of `band` into its shared-memory slot
+        const int y0 = band * BR, rows = min(BR, h - y0);
+        if (rows <= 0) return;
+        const uint4 *src = reinterpret_cast<const uint4 *>(S.rowtab + y0);
+        uint4 *dst = reinterpret_cast<uint4 *>(rtab + (size_t)(band & 1) * BR);
+        for (int i = tid; i < rows * 4; i += nt) dst[i] = __ldg(src + i);
+    };
+    if (BULK && tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nt / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    load_rowtab(0);
+    __syncthreads();
+    if (BULK && tid == 0) for (int c = 0; c < min(NS, nchunks); ++c) issue(c);
 
     float acc[4][3][CPT];
 #pragma unroll
@@ -509,61 +535,78 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
 #pragma unroll
             for (int c = 0; c < CPT; ++c) acc[s][j][c] = 0.0f;
 
-    int slot = 0, band = 0;
-    for (int c = 0; c < nchunks; ++c) {
-        const int y_lo = c * RS, y_hi = min(h, y_lo + RS);
-        if (BULK) mbar_wait(&full[c % NS], (c / NS) & 1);
-        const uint8_t *base = BULK ? ring + (size_t)(c % NS) * L.stage_bytes + 3 * (size_t)x0
-                                   : I.pixels + (size_t)y_lo * I.stride + 3 * (size_t)x0;
-        const size_t pitch = BULK ? src_pitch : I.stride;
-        for (int y = y_lo; y < y_hi; ++y) {
-            float v[CPT];
-            const uint8_t *px = base + (size_t)(y - y_lo) * pitch;
-            if (CPT % 4 == 0 && (BULK || I.aligned4) && w % CPT == 0) {
-                const uint32_t *p32 = reinterpret_cast<const uint32_t *>(px);
+    int c = 0;   // chunk counter over the whole image
+    for (int band = 0; band < S.nbands; ++band) {
+        const int band_lo = band * BR, band_hi = min(h, band_lo + BR);
+        const RowEntry *rt = rtab + (size_t)(band & 1) * BR;
+        int slot = 0;
+        for (int y_lo = band_lo; y_lo < band_hi; y_lo += RS, ++c) {
+            const int y_hi = min(band_hi, y_lo + RS);
+            const int s_idx = c % NS;
+            if (BULK) mbar_wait(&full[s_idx], (c / NS) & 1);
+            const uint8_t *base = BULK ? ring + (size_t)s_idx * L.stage_bytes + 3 * (size_t)x0
+                                       : I.pixels + (size_t)y_lo * I.stride + 3 * (size_t)x0;
+            for (int y = y_lo; y < y_hi; ++y) {
+                const RowEntry &e = rt[y - band_lo];
+                const ulonglong2 wa = *reinterpret_cast<const ulonglong2 *>(&e.w01[0][0]);   // passes 0, 1 (broadcast LDS.128)
+                const ulonglong2 wb = *reinterpret_cast<const ulonglong2 *>(&e.w01[2][0]);   // passes 2, 3
+                const uint32_t flags = e.flags;
+                const uint64_t w01[4] = {wa.x, wa.y, wb.x, wb.y};
+                float v[CPT];
+                const uint8_t *px = base + (size_t)(y - y_lo) * pitch;
+                if (CPT % 4 == 0 && (BULK || I.aligned4) && w % CPT == 0) {
+                    const uint32_t *p32 = reinterpret_cast<const uint32_t *>(px);
 #pragma unroll
-                for (int g = 0; g < CPT / 4; ++g)   // 4 pixels = 12 bytes = 3 words
-                    luma4(p32[3 * g], p32[3 * g + 1], p32[3 * g + 2], v[(4 * g) % CPT], v[(4 * g + 1) % CPT], v[(4 * g + 2) % CPT],
-                          v[(4 * g + 3) % CPT]);
-            } else {
-#pragma unroll
-                for (int cc = 0; cc < CPT; ++cc) {
-                    const int xc = min(cc, w - 1 - x0);   // CPT > 1 and a ragged last group: repeat the last column
-                    v[cc] = luma_to_f32(2126u * px[3 * xc] + 7152u * px[3 * xc + 1] + 722u * px[3 * xc + 2]);
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const ulonglong2 raw = __ldg(reinterpret_cast<const ulonglong2 *>(S.vtab + (size_t)s * h + y));  // uniform
-                const float w2 = __uint_as_float((uint32_t)raw.y);
-                const uint32_t meta = (uint32_t)(raw.y >> 32);
-                const int n_active = meta & 255, n_finish = (meta >> 8) & 255;
-#pragma unroll
-                for (int cc = 0; cc < CPT; ++cc) {
-                    float p0, p1;
-                    mul2(v[cc], raw.x, p0, p1);
-                    acc[s][0][cc] = acc[s][0][cc] + p0;
-                    acc[s][1][cc] = acc[s][1][cc] + p1;
-                }
-                if (n_active == 3) {
-#pragma unroll
-                    for (int cc = 0; cc < CPT; ++cc) acc[s][2][cc] = acc[s][2][cc] + v[cc] * w2;
-                }
-                for (int f = 0; f < n_finish; ++f) {  // uniform: the lowest active output of this pass is complete
-                    float *dst = rowbuf + (size_t)slot * row_words;
+                    for (int g = 0; g < CPT / 4; ++g)   // 4 pixels = 12 bytes = 3 words
+                        luma4(p32[3 * g], p32[3 * g + 1], p32[3 * g + 2], v[(4 * g) % CPT], v[(4 * g + 1) % CPT], v[(4 * g + 2) % CPT],
+                              v[(4 * g + 3) % CPT]);
+                } else {
 #pragma unroll
                     for (int cc = 0; cc < CPT; ++cc) {
-                        if (owner && x0 + cc < w) dst[skew(x0 + cc)] = acc[s][0][cc];
-                        acc[s][0][cc] = acc[s][1][cc]; acc[s][1][cc] = acc[s][2][cc]; acc[s][2][cc] = 0.0f;
+                        const int xc = min(cc, w - 1 - x0);   // a ragged last group repeats its last column
+                        v[cc] = luma_to_f32(2126u * px[3 * xc] + 7152u * px[3 * xc + 1] + 722u * px[3 * xc + 2]);
                     }
-                    slot++;
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+#pragma unroll
+                    for (int cc = 0; cc < CPT; ++cc) {
+                        float p0, p1;
+                        mul2(v[cc], w01[s], p0, p1);
+                        acc[s][0][cc] = acc[s][0][cc] + p0;
+                        acc[s][1][cc] = acc[s][1][cc] + p1;
+                    }
+                }
+                if (flags) {   // uniform and infrequent: a third active output, or outputs completed by this row
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const uint32_t fl = (flags >> (8 * s)) & 255u;
+                        if (fl & 1u) {
+                            const float w2 = e.w2[s];
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) acc[s][2][cc] = acc[s][2][cc] + v[cc] * w2;
+                        }
+                        for (uint32_t f = 0; f < (fl >> 1); ++f) {  // the lowest active output of this pass is complete
+                            float *dst = rowbuf + (size_t)slot * row_words;
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) {
+                                if (owner && x0 + cc < w) dst[skew(x0 + cc)] = acc[s][0][cc];
+                                acc[s][0][cc] = acc[s][1][cc]; acc[s][1][cc] = acc[s][2][cc]; acc[s][2][cc] = 0.0f;
+                            }
+                            slot++;
+                        }
+                    }
                 }
             }
+            if (BULK) {   // hand the stage back: every warp arrives, thread 0 refills once all have
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s_idx]);
+                if (tid == 0 && c + NS < nchunks) { mbar_wait(&empty[s_idx], (c / NS) & 1); issue(c + NS); }
+            }
         }
-        __syncthreads();   // the stage is consumed, finished rows are visible
-        if (BULK && tid == 0 && c + NS < nchunks) issue(c + NS);
-        if (y_hi == h || y_hi % S.band_rows == 0) {
-            // horizontal passes over the rows finished in this band
+        __syncthreads();   // finished rows of this band are visible to everyone
+        load_rowtab(band + 1);
+        {   // horizontal passes over the rows finished in this band
             const int f_lo = S.band_off[band], f_hi = S.band_off[band + 1];
             int ibase = 0;
             for (int fi = f_lo; fi < f_hi; ++fi) {
@@ -574,10 +617,8 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
                     hpass_item<true>(G, S, f, it, rowbuf + (size_t)(fi - f_lo) * row_words);
                 ibase += items;
             }
-            band++;
-            slot = 0;
-            __syncthreads();
         }
+        __syncthreads();
     }
     hash_regions(G, H, algo_mask, out + (size_t)I.out_index * 51);
 }
