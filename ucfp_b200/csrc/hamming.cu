@@ -79,14 +79,17 @@ __device__ __forceinline__ uint32_t xor_or(uint32_t a, uint32_t b, uint32_t c) {
     return r;
 }
 
-// Cold path of the scan: exact distances for the CPT codes of one thread against one query; rows with
-// (dist, id) < (thr, kth_id) are appended to the query's candidate list.  Kept out of line so that the
-// hot loop's register allocation is not shaped by it.
-__device__ __noinline__ void hamming_survivors(const uint32_t (&lo)[kCodesPerThread], const uint32_t (&hi)[kCodesPerThread],
-                                               uint4 s, uint32_t q, uint64_t tile_row, uint64_t row_end,
-                                               const uint64_t *__restrict__ ids, uint64_t id_base,
+// Cold path of the scan: exact distances for the 8 codes of one thread against one query; rows with
+// (dist, id) < (thr, kth_id) are appended to the query's candidate list.  Out of line so that the hot loop's
+// register allocation is not shaped by it, and with the codes passed BY VALUE (in registers): handing the arrays
+// over by reference spills them to local memory on every tile, and those stores halve the streaming bandwidth
+// (measured: 4.1 vs 7.2 TB/s at one query per pass, scripts/micro/stream_bw2.cu).
+__device__ __noinline__ void hamming_survivors(uint4 c01, uint4 c23, uint4 c45, uint4 c67, uint4 s, uint32_t q, uint64_t tile_row,
+                                               uint64_t row_end, const uint64_t *__restrict__ ids, uint64_t id_base,
                                                const uint64_t *__restrict__ kth_id, uint64_t *cand, uint32_t *count,
                                                uint32_t cap) {
+    const uint32_t lo[kCodesPerThread] = {c01.x, c01.z, c23.x, c23.z, c45.x, c45.z, c67.x, c67.z};
+    const uint32_t hi[kCodesPerThread] = {c01.y, c01.w, c23.y, c23.w, c45.y, c45.w, c67.y, c67.w};
     const uint64_t kid = kth_id[q];
 #pragma unroll
     for (int c = 0; c < kCodesPerThread; ++c) {
@@ -103,7 +106,7 @@ __device__ __noinline__ void hamming_survivors(const uint32_t (&lo)[kCodesPerThr
 }
 
 // Scans rows [row0, row0 + nrows) of the corpus against the nq staged queries.
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, 4)
 hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restrict__ ids, uint64_t id_base,
                     uint64_t row0, uint64_t nrows, const QSlot *__restrict__ slots, const uint64_t *__restrict__ kth_id,
                     uint32_t nq, uint64_t *cand, uint32_t *count, uint32_t cap) {
@@ -134,7 +137,9 @@ hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restri
                 m = min(m, (uint32_t)__popc(f));
             }
             if (m <= s.z)  // rare: at least one code of this thread may be within the threshold
-                hamming_survivors(lo, hi, s, q, tile_row, row_end, ids, id_base, kth_id, cand, count, cap);
+                hamming_survivors(make_uint4(lo[0], hi[0], lo[1], hi[1]), make_uint4(lo[2], hi[2], lo[3], hi[3]),
+                                  make_uint4(lo[4], hi[4], lo[5], hi[5]), make_uint4(lo[6], hi[6], lo[7], hi[7]), s, q, tile_row,
+                                  row_end, ids, id_base, kth_id, cand, count, cap);
         }
     }
 }
@@ -211,7 +216,9 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
         compact(seed == N);
 
         // small batches are HBM-bound: fewer, larger chunks; large batches tighten thr more often
-        const uint64_t growth = nqp <= 16 ? 32 : 8;
+        const bool streaming = nqp <= 16;   // HBM-bound regime: fewer and larger chunks
+        const uint64_t growth = streaming ? 64 : 8;
+        const uint64_t max_chunk = streaming ? (1ULL << 40) : kMaxChunkRows;
         uint64_t pos = seed, chunk = (uint64_t)seed * growth;
         while (pos < N) {
             uint64_t n = (N - pos < chunk) ? N - pos : chunk;
@@ -226,7 +233,7 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
             count_launch(ctx);
             pos += n;
             compact(pos == N);
-            chunk = chunk * growth < kMaxChunkRows ? chunk * growth : kMaxChunkRows;
+            chunk = chunk * growth < max_chunk ? chunk * growth : max_chunk;
         }
         UCFP_TRY(check_launch("hamming scan"));
         // exact recomputation of any query whose candidate list overflowed (device-side decision, no host sync)
