@@ -162,8 +162,11 @@ UCFP_API uint64_t ucfp_corpus_size(const ucfp_corpus *c);
  * docs/HASH_SPEC.md section 8 (row r, word j = splitmix64(seed, (start_row + r) * words_per_row + j)),
  * implicit ids.  HAMMING64 and MINHASH128 only. */
 UCFP_API int ucfp_corpus_append_synthetic(ucfp_corpus *c, uint64_t seed, uint64_t start_row, uint64_t n);
-/* Device pointer to the resident rows (read-only view for tests/bench planting), or NULL. */
+/* Device pointer to the resident rows (view for tests/bench planting), or NULL. */
 UCFP_API void *ucfp_corpus_device_rows(ucfp_corpus *c);
+/* Re-derives the side arrays (MinHash sketches; cosine norms and bf16 copies) of all resident rows.  Call it
+ * after rows were modified in place through ucfp_corpus_device_rows. */
+UCFP_API int ucfp_corpus_refresh(ucfp_corpus *c);
 
 /* ---- scans ------------------------------------------------------------------
  * All results are ordered best first with the total order stated; slots beyond

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "ucfp_corpus_size": (_u64, [_vp]),
     "ucfp_corpus_append_synthetic": (_int, [_vp, _u64, _u64, _u64]),
     "ucfp_corpus_device_rows": (_vp, [_vp]),
+    "ucfp_corpus_refresh": (_int, [_vp]),
     "ucfp_scan_hamming": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "ucfp_scan_jaccard": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "ucfp_scan_cosine": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),

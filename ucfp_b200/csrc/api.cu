@@ -243,6 +243,12 @@ static int after_append(ucfp_corpus *c, uint64_t first, uint64_t n) {
     return UCFP_OK;
 }
 
+int ucfp_corpus_refresh(ucfp_corpus *c) {
+    UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
+    UCFP_GUARD(c->ctx);
+    return after_append(c, 0, c->size);
+}
+
 int ucfp_corpus_append(ucfp_corpus *c, const uint64_t *ids, const void *rows, uint64_t n) {
     UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
     UCFP_GUARD(c->ctx);

@@ -157,6 +157,9 @@ class Corpus:
     def clear(self) -> None:
         check(self._L.ucfp_corpus_clear(self._h))
 
+    def refresh(self) -> None:
+        check(self._L.ucfp_corpus_refresh(self._h))
+
     def device_rows_ptr(self) -> int:
         return int(self._L.ucfp_corpus_device_rows(self._h) or 0)
 
