@@ -265,14 +265,16 @@ cosine_coarse_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
     uint64_t *tfull = empty + kStages;     // [2] accumulator stage ready for the epilogue
     uint64_t *tempty = tfull + 2;          // [2] accumulator stage drained
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
-    float *s_tau = reinterpret_cast<float *>(tmem_slot + 4);    // [nq] thr - eps
+    float *s_tau = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [nq padded to 32] thr - eps
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t tile_row = row0 + (uint64_t)blockIdx.x * kTileRows;
     const uint32_t q_tiles = (nq + n_tile - 1) / n_tile;
     const uint32_t b_bytes = n_tile * kBlockK * 2;
+    // persistent: this CTA takes corpus tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the three roles walk the same
+    // (tile, query tile, K chunk) sequence, so the TMA ring and the two TMEM stages stay full across tile boundaries
+    const uint32_t n_tiles = (uint32_t)((row_end - row0 + kTileRows - 1) / kTileRows);
 
-    for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) s_tau[i] = S.thr[i] - kCoarseEps;
+    for (uint32_t i = threadIdx.x; i < ((nq + 31) & ~31u); i += blockDim.x) s_tau[i] = i < nq ? S.thr[i] - kCoarseEps : INFINITY;
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_rows) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
@@ -293,66 +295,84 @@ cosine_coarse_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t it = 0;
-            for (uint32_t qt = 0; qt < q_tiles; ++qt)
-                for (uint32_t kc = 0; kc < k_chunks; ++kc, ++it) {
-                    const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], kABytes + b_bytes);
-                    tma_load_2d(sA + s * kABytes, &map_rows, &full[s], (int)(kc * kBlockK), (int)tile_row);
-                    tma_load_2d(sB + s * kBBytesMax, &map_q, &full[s], (int)(kc * kBlockK), (int)(qt * n_tile));
-                }
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const uint64_t tile_row = row0 + (uint64_t)tile * kTileRows;
+                for (uint32_t qt = 0; qt < q_tiles; ++qt)
+                    for (uint32_t kc = 0; kc < k_chunks; ++kc, ++it) {
+                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_expect_tx(&full[s], kABytes + b_bytes);
+                        tma_load_2d(sA + s * kABytes, &map_rows, &full[s], (int)(kc * kBlockK), (int)tile_row);
+                        tma_load_2d(sB + s * kBBytesMax, &map_q, &full[s], (int)(kc * kBlockK), (int)(qt * n_tile));
+                    }
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one elected lane) =====
         // instruction descriptor: D = f32, A = B = bf16, both K-major, N = n_tile, M = 128
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((n_tile >> 3) << 17) | ((kTileRows >> 4) << 24);
-        uint32_t it = 0;
-        for (uint32_t qt = 0; qt < q_tiles; ++qt) {
-            const uint32_t as = qt & 1, aph = (qt >> 1) & 1;
-            mbar_wait(&tempty[as], aph ^ 1);
-            tcgen05_fence_after();
-            const uint32_t d_tmem = tmem_base + as * kMaxNTile;
-            for (uint32_t kc = 0; kc < k_chunks; ++kc, ++it) {
-                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                mbar_wait(&full[s], ph);
+        uint32_t it = 0, acc_it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+            for (uint32_t qt = 0; qt < q_tiles; ++qt, ++acc_it) {
+                const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                mbar_wait(&tempty[as], aph ^ 1);
                 tcgen05_fence_after();
-                if (lane == 0) {
-                    const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * kABytes));
-                    const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * kBBytesMax));
+                const uint32_t d_tmem = tmem_base + as * kMaxNTile;
+                for (uint32_t kc = 0; kc < k_chunks; ++kc, ++it) {
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                    mbar_wait(&full[s], ph);
+                    tcgen05_fence_after();
+                    if (lane == 0) {
+                        const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * kABytes));
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * kBBytesMax));
 #pragma unroll
-                    for (int kk = 0; kk < kBlockK / 16; ++kk)   // UMMA_K = 16 bf16 = 32 bytes = +2 in the address field
-                        umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kc | kk) ? 1u : 0u);
-                    umma_commit(&empty[s]);                      // frees the smem stage when these MMAs retire
-                    if (kc == k_chunks - 1) umma_commit(&tfull[as]);
+                        for (int kk = 0; kk < kBlockK / 16; ++kk)   // UMMA_K = 16 bf16 = 32 bytes = +2 in the address field
+                            umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kc | kk) ? 1u : 0u);
+                        umma_commit(&empty[s]);                      // frees the smem stage when these MMAs retire
+                        if (kc == k_chunks - 1) umma_commit(&tfull[as]);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
-        }
     } else {
         // ===== epilogue: 4 warps, warp w reads TMEM lanes 32*(w%4).. (its hardware quadrant) =====
         const uint32_t quad = warp & 3;
-        const uint64_t my_row = tile_row + quad * 32 + lane;
-        const bool valid = my_row < row_end;
-        for (uint32_t qt = 0; qt < q_tiles; ++qt) {
-            const uint32_t as = qt & 1, aph = (qt >> 1) & 1;
-            mbar_wait(&tfull[as], aph);
-            tcgen05_fence_after();
-            const uint32_t cols = min(n_tile, nq - qt * n_tile);
-            for (uint32_t c0 = 0; c0 < cols; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((quad * 32u) << 16) + as * kMaxNTile + c0, v);
+        uint32_t acc_it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint64_t my_row = row0 + (uint64_t)tile * kTileRows + quad * 32 + lane;
+            const bool valid = my_row < row_end;
+            for (uint32_t qt = 0; qt < q_tiles; ++qt, ++acc_it) {
+                const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                mbar_wait(&tfull[as], aph);
+                tcgen05_fence_after();
+                const uint32_t cols = min(n_tile, nq - qt * n_tile);
+                for (uint32_t c0 = 0; c0 < cols; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((quad * 32u) << 16) + as * kMaxNTile + c0, v);
+                    // admission bounds of these 32 queries (padded with +inf): 8 broadcast LDS.128, then one pass
+                    // that only records whether ANY score clears its bound -- survivors are rare
+                    const float4 *tp = reinterpret_cast<const float4 *>(s_tau + qt * n_tile + c0);
+                    float tau[32];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const uint32_t qi = qt * n_tile + c0 + c;
-                    if (valid && c0 + c < cols && __uint_as_float(v[c]) >= s_tau[qi]) {
-                        uint32_t pos = atomicAdd(&S.count[qi], 1u);
-                        if (pos < kCap) S.cand[(size_t)qi * kCap + pos] = (uint32_t)my_row;
+                    for (int j = 0; j < 8; ++j) { float4 t = tp[j]; tau[4 * j] = t.x; tau[4 * j + 1] = t.y; tau[4 * j + 2] = t.z; tau[4 * j + 3] = t.w; }
+                    bool any = false;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) any |= __uint_as_float(v[c]) >= tau[c];
+                    if (any && valid) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            if (__uint_as_float(v[c]) >= tau[c]) {
+                                const uint32_t qi = qt * n_tile + c0 + c;
+                                uint32_t pos = atomicAdd(&S.count[qi], 1u);
+                                if (pos < kCap) S.cand[(size_t)qi * kCap + pos] = (uint32_t)my_row;
+                            }
+                        }
                     }
                 }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[as]);
             }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
         }
     }
     tcgen05_fence_before();
@@ -363,7 +383,7 @@ cosine_coarse_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
     }
 }
 
-constexpr size_t kGemmSmem = (size_t)kStages * (kABytes + kBBytesMax) + 16 * 8 + 16 + kMaxQueriesPerPass * 4 + 1024;
+constexpr size_t kGemmSmem = (size_t)kStages * (kABytes + kBBytesMax) + 16 * 8 + 16 + (kMaxQueriesPerPass + 32) * 4 + 1024;
 
 // ---- exact-selection key for flagged queries --------------------------------------------------------------
 struct CosineKey {
@@ -500,7 +520,8 @@ int cosine_scan(ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_
             uint32_t tiles = (uint32_t)((n + kTileRows - 1) / kTileRows);
             {
                 ProfScope ps(ctx, UCFP_PROF_COSINE_SCAN, 2.0 * (double)n * dim * nqp);
-                cosine_coarse_kernel<<<tiles, kGemmThreads, kGemmSmem, st>>>(map_rows, map_q, pos, pos + n, nqp, n_tile, dim_pad / kBlockK, S);
+                const uint32_t grid = tiles < (uint32_t)ctx->sm_count ? tiles : (uint32_t)ctx->sm_count;   // 1 CTA per SM (smem), persistent
+                cosine_coarse_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(map_rows, map_q, pos, pos + n, nqp, n_tile, dim_pad / kBlockK, S);
             }
             count_launch(ctx);
             pos += n;
