@@ -16,6 +16,8 @@
 //   image_generic_kernel     -- any shape (tiny, up-scaling, extreme aspect, very wide): output-major
 //       passes over a gray plane in global scratch.
 // Both end in hash_regions(): 17 x {8x32 . 32x32 . 32x8 partial DCT-II, median, mean, gradient, ballot}.
+#include <stdlib.h>
+
 #include <map>
 
 #include "common.cuh"
@@ -202,13 +204,16 @@ int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
                 }
             }
         if ((int)fin_rows.size() != 32 + 8 + 4 * 40) ok = false;
+        // shared-memory budgets (tunable for experiments through the environment; defaults chosen from measurements)
+        static const long env_rowbuf = getenv("UCFP_IMG_ROWBUF_KB") ? atol(getenv("UCFP_IMG_ROWBUF_KB")) : 0;
+        const size_t rowbuf_budget = env_rowbuf > 0 ? (size_t)env_rowbuf * 1024 : (w <= 512 ? 14 * 1024 : kRowBufBudget);
         for (int cand = kMaxBandRows; cand >= 1 && ok; cand >>= 1) {
             int nb = (h + cand - 1) / cand, mx = 0;
             std::vector<int> cnt(nb, 0);
             for (int y : fin_row_y) cnt[y / cand]++;
             for (int c : cnt) mx = c > mx ? c : mx;
-            if ((size_t)mx * (w + w / 32 + 1) * 4 <= kRowBufBudget || cand == 1) {
-                if ((size_t)mx * (w + w / 32 + 1) * 4 > kRowBufBudget) { ok = false; break; }
+            if ((size_t)mx * (w + w / 32 + 1) * 4 <= rowbuf_budget || cand == 1) {
+                if ((size_t)mx * (w + w / 32 + 1) * 4 > rowbuf_budget) { ok = false; break; }
                 band_rows = cand; max_fin = mx;
                 band_off.assign(nb + 1, 0);
                 for (int b = 0; b < nb; ++b) band_off[b + 1] = band_off[b] + cnt[b];
@@ -225,14 +230,17 @@ int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
         auto up = [](size_t x, size_t a) { return (x + a - 1) / a * a; };
         StreamSmem &L = st.lay;
         L.row_pitch = (uint32_t)up(3 * (size_t)w, 16);
+        static const long env_stage = getenv("UCFP_IMG_STAGE_KB") ? atol(getenv("UCFP_IMG_STAGE_KB")) : 0;
+        static const long env_stages = getenv("UCFP_IMG_STAGES") ? atol(getenv("UCFP_IMG_STAGES")) : 0;
+        const size_t stage_budget = env_stage > 0 ? (size_t)env_stage * 1024 : (w <= 512 ? 6 * 1024 : 24 * 1024);
         uint32_t rs = 1;
-        while (rs * 2 <= (uint32_t)band_rows && (size_t)rs * 2 * L.row_pitch <= 24 * 1024) rs *= 2;
+        while (rs * 2 <= (uint32_t)band_rows && (size_t)rs * 2 * L.row_pitch <= stage_budget) rs *= 2;
         L.chunk_rows = rs;
         L.stage_bytes = (uint32_t)up((size_t)rs * L.row_pitch, 128);
         L.off_rowbuf = (uint32_t)kGridsBytes;
         L.row_words = (uint32_t)(w + (w >> 5) + 1);       // skewed row: one pad word per 32
         L.off_ring = (uint32_t)(L.off_rowbuf + up((size_t)max_fin * L.row_words * 4, 128));
-        L.stages = (L.off_ring + 3 * (size_t)L.stage_bytes + 2 * (size_t)band_rows * sizeof(RowEntry) <= 106 * 1024) ? 3 : 2;
+        L.stages = env_stages > 0 ? (uint32_t)env_stages : (w <= 512 ? 2 : ((L.off_ring + 3 * (size_t)L.stage_bytes + 2 * (size_t)band_rows * sizeof(RowEntry) <= 106 * 1024) ? 3 : 2));
         L.off_bars = L.off_ring + L.stages * L.stage_bytes;          // full[stages], empty[stages]
         L.off_rowtab = (uint32_t)up(L.off_bars + 16 * L.stages, 16);   // [2][band_rows] RowEntry, double-buffered
         size_t total = L.off_rowtab + 2 * (size_t)band_rows * sizeof(RowEntry);

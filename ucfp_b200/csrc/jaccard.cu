@@ -110,17 +110,30 @@ jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint64_t *__restr
 
         for (uint32_t qi = 0; qi < nq; ++qi) {
             const uint4 *qv = reinterpret_cast<const uint4 *>(sq + (size_t)qi * kSketchWords);
-            uint32_t acc = 0;
-#pragma unroll
-            for (int j4 = 0; j4 < kSketchWords / 4; ++j4) {
-                uint4 v = qv[j4];  // broadcast LDS.128
-                acc += eq_bytes_flags(w[4 * j4], v.x) >> 7;
-                acc += eq_bytes_flags(w[4 * j4 + 1], v.y) >> 7;
-                acc += eq_bytes_flags(w[4 * j4 + 2], v.z) >> 7;
-                acc += eq_bytes_flags(w[4 * j4 + 3], v.w) >> 7;
-            }
-            const uint32_t bm = (acc * 0x01010101u) >> 24;  // byte matches: an upper bound on slot matches
             const uint32_t thr = sthr[qi];
+            const uint32_t need = 128u - thr;               // byte matches a row needs to stay in the race
+            uint32_t acc = 0;
+            bool alive = true;
+            // four groups of 8 words (32 slots).  After each of the first three, the warp stops as soon as no lane
+            // can still reach `need` even if every remaining byte matched -- exact branch-and-bound, and with a
+            // meaningful bound almost every (row, query) pair ends after the first group.
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+#pragma unroll
+                for (int j4 = 2 * g; j4 < 2 * g + 2; ++j4) {
+                    uint4 v = qv[j4];  // broadcast LDS.128
+                    acc += eq_bytes_flags(w[4 * j4], v.x) >> 7;
+                    acc += eq_bytes_flags(w[4 * j4 + 1], v.y) >> 7;
+                    acc += eq_bytes_flags(w[4 * j4 + 2], v.z) >> 7;
+                    acc += eq_bytes_flags(w[4 * j4 + 3], v.w) >> 7;
+                }
+                if (g < 3) {
+                    const uint32_t part = (acc * 0x01010101u) >> 24;
+                    if (!__any_sync(0xffffffffu, valid && part + (96u - 32u * g) >= need)) { alive = false; break; }
+                }
+            }
+            if (!alive) continue;
+            const uint32_t bm = (acc * 0x01010101u) >> 24;  // byte matches: an upper bound on slot matches
             const uint32_t lower = 128u - bm;               // lower bound on the key
             const uint64_t kid = skid[qi];
             // (key, id) can beat the current k-th only if (lower, id) < (thr, kth_id)
