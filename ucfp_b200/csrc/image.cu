@@ -61,7 +61,7 @@ struct RegionGrids {         // shared memory, per CTA, lives for the whole imag
 struct HashScratch {         // shared memory used only by hash_regions (may alias streaming buffers)
     float R[kRegions][32][8];
     float D[kRegions][64];
-    float C[8][32];
+    float C[8][33];              // 33: the 8 threads of an output row read C[v][x], v = 0..7, in distinct banks
     float med_lo[kRegions], med_hi[kRegions];
 };
 constexpr size_t kGridsBytes = (sizeof(RegionGrids) + 127) & ~size_t(127);
@@ -616,14 +616,15 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
         load_rowtab(band + 1);
         {   // horizontal passes over the rows finished in this band
             const int f_lo = S.band_off[band], f_hi = S.band_off[band + 1];
-            int ibase = 0;
+            int start = 0;   // first thread of the current row's items; rows of a band run side by side
             for (int fi = f_lo; fi < f_hi; ++fi) {
                 const FinDesc f = S.fin[fi];
-                const int items = fin_items(f.stream);
-                // threads [ibase, ibase + items) modulo nt take this row's outputs: rows of a band run side by side
-                for (int it = (tid - ibase % nt + nt) % nt; it < items; it += nt)
-                    hpass_item<true>(G, S, f, it, rowbuf + (size_t)(fi - f_lo) * row_words);
-                ibase += items;
+                const int items = fin_items(f.stream);   // <= 128 <= nt
+                int it = tid - start;
+                if (it < 0) it += nt;
+                if (it < items) hpass_item<true>(G, S, f, it, rowbuf + (size_t)(fi - f_lo) * row_words);
+                start += items;
+                if (start >= nt) start -= nt;
             }
         }
         __syncthreads();
