@@ -21,6 +21,7 @@
 // topk_select.cuh (histogram of distances + radix select on ids), so the result is
 // exact for every input.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -109,14 +110,22 @@ __device__ __noinline__ void hamming_survivors(uint4 c01, uint4 c23, uint4 c45, 
 __global__ void __launch_bounds__(kScanThreads, 4)
 hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restrict__ ids, uint64_t id_base,
                     uint64_t row0, uint64_t nrows, const QSlot *__restrict__ slots, const uint64_t *__restrict__ kth_id,
-                    uint32_t nq, uint64_t *cand, uint32_t *count, uint32_t cap) {
-    extern __shared__ uint4 sq[];  // nq query slots
-    for (uint32_t i = threadIdx.x; i < nq; i += kScanThreads) sq[i] = reinterpret_cast<const uint4 *>(slots)[i];
+                    uint32_t nq, uint32_t q_groups, uint64_t *cand, uint32_t *count, uint32_t cap) {
+    extern __shared__ uint4 sq[];  // query slots of this CTA's group
+    // Small chunks (the first few of a batch, where the admission bounds are still loose and the cold path runs
+    // often) have fewer tiles than the GPU has CTA slots: the queries are then split into q_groups groups and the
+    // grid is tiles x groups, one (tile, group) pair per CTA.  Large chunks use q_groups == 1 and a persistent grid.
+    const uint32_t grp = q_groups > 1 ? blockIdx.x % q_groups : 0;
+    const uint32_t q_lo = (uint32_t)((uint64_t)nq * grp / q_groups), q_hi = (uint32_t)((uint64_t)nq * (grp + 1) / q_groups);
+    const uint32_t nq_mine = q_hi - q_lo;
+    for (uint32_t i = threadIdx.x; i < nq_mine; i += kScanThreads) sq[i] = reinterpret_cast<const uint4 *>(slots)[q_lo + i];
     __syncthreads();
 
     const uint64_t row_end = row0 + nrows;
     const uint64_t ntiles = (nrows + kTileCodes - 1) / kTileCodes;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint64_t tile0 = q_groups > 1 ? blockIdx.x / q_groups : blockIdx.x;
+    const uint64_t tile_step = q_groups > 1 ? ntiles : gridDim.x;
+    for (uint64_t tile = tile0; tile < ntiles; tile += tile_step) {
         const uint64_t tile_row = row0 + tile * kTileCodes;  // even by construction
         uint32_t lo[kCodesPerThread], hi[kCodesPerThread];
 #pragma unroll
@@ -128,7 +137,7 @@ hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restri
             lo[2 * j] = v.x; hi[2 * j] = v.y; lo[2 * j + 1] = v.z; hi[2 * j + 1] = v.w;
         }
 #pragma unroll 2
-        for (uint32_t q = 0; q < nq; ++q) {
+        for (uint32_t q = 0; q < nq_mine; ++q) {
             const uint4 s = sq[q];  // broadcast LDS.128: {lo, hi, thr, -}
             uint32_t m = 64;
 #pragma unroll
@@ -138,8 +147,8 @@ hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restri
             }
             if (m <= s.z)  // rare: at least one code of this thread may be within the threshold
                 hamming_survivors(make_uint4(lo[0], hi[0], lo[1], hi[1]), make_uint4(lo[2], hi[2], lo[3], hi[3]),
-                                  make_uint4(lo[4], hi[4], lo[5], hi[5]), make_uint4(lo[6], hi[6], lo[7], hi[7]), s, q, tile_row,
-                                  row_end, ids, id_base, kth_id, cand, count, cap);
+                                  make_uint4(lo[4], hi[4], lo[5], hi[5]), make_uint4(lo[6], hi[6], lo[7], hi[7]), s, q_lo + q,
+                                  tile_row, row_end, ids, id_base, kth_id, cand, count, cap);
         }
     }
 }
@@ -217,18 +226,25 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
 
         // small batches are HBM-bound: fewer, larger chunks; large batches tighten thr more often
         const bool streaming = nqp <= 16;   // HBM-bound regime: fewer and larger chunks
-        const uint64_t growth = streaming ? 64 : 8;
+        static const long env_growth = getenv("UCFP_HAMMING_GROWTH") ? atol(getenv("UCFP_HAMMING_GROWTH")) : 0;
+        const uint64_t growth = streaming ? 64 : (env_growth > 1 ? (uint64_t)env_growth : 8);
         const uint64_t max_chunk = streaming ? (1ULL << 40) : kMaxChunkRows;
         uint64_t pos = seed, chunk = (uint64_t)seed * growth;
         while (pos < N) {
             uint64_t n = (N - pos < chunk) ? N - pos : chunk;
             uint64_t ntiles = (n + kTileCodes - 1) / kTileCodes;
-            uint64_t grid = (uint64_t)ctx->sm_count * scan_occ;
-            if (grid > ntiles) grid = ntiles;
+            const uint64_t slots_full = (uint64_t)ctx->sm_count * scan_occ;
+            uint64_t grid = slots_full, q_groups = 1;
+            if (ntiles < slots_full) {   // small chunk: split the queries so that every SM gets work
+                q_groups = (slots_full + ntiles - 1) / ntiles;
+                const uint64_t max_groups = (nqp + 7) / 8;   // at least 8 queries per group
+                if (q_groups > max_groups) q_groups = max_groups;
+                grid = ntiles * q_groups;
+            }
             {
                 ProfScope ps(ctx, UCFP_PROF_HAMMING_SCAN, 8.0 * (double)n * nqp);
                 hamming_scan_kernel<<<(unsigned)grid, kScanThreads, sizeof(QSlot) * nqp, st>>>(
-                    codes, ids, c->id_base, pos, n, slots, kth, nqp, cand, count, cap);
+                    codes, ids, c->id_base, pos, n, slots, kth, nqp, (uint32_t)q_groups, cand, count, cap);
             }
             count_launch(ctx);
             pos += n;
