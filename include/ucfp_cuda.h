@@ -155,6 +155,13 @@ UCFP_API void ucfp_corpus_destroy(ucfp_corpus *c);
  * value set by ucfp_corpus_set_id_base (default 0) -- the layout a range-sharded index uses; a corpus is
  * either all-explicit or all-implicit.  UCFP_ID_NONE is not a valid record id. */
 UCFP_API int ucfp_corpus_append(ucfp_corpus *c, const uint64_t *ids, const void *rows, uint64_t n);
+/* Bulk hydration from stored records: appends n rows, row i being the row-sized field at byte
+ * `field_offset` of the record at `records + i * record_stride` -- e.g. the u64 global_hash at offset 32 of
+ * 168-byte ImageFingerprints, the PHash global hash at offset 232 of 536-byte multi bundles, or the 1024-byte
+ * slot payload at offset 8 of 1032-byte MinHashSig<128> blobs laid out back to back as read from the
+ * fingerprints table.  `records` may be host or device memory; ids as in ucfp_corpus_append. */
+UCFP_API int ucfp_corpus_append_strided(ucfp_corpus *c, const uint64_t *ids, const void *records, uint64_t record_stride,
+                                        uint64_t field_offset, uint64_t n);
 UCFP_API int ucfp_corpus_set_id_base(ucfp_corpus *c, uint64_t id_base);
 UCFP_API int ucfp_corpus_clear(ucfp_corpus *c);
 UCFP_API uint64_t ucfp_corpus_size(const ucfp_corpus *c);

@@ -115,3 +115,32 @@ def test_hash_index_hamming_and_jaccard(ctx):
     db.upsert([mk(1, blob), mk(2, blob2)])
     hits = db.jaccard_knn(3, sig, 5)
     assert [h.record_id for h in hits] == [1, 2] and hits[0].score == 1.0 and hits[1].score == 100 / 128
+
+
+def test_bulk_hydration_from_stored_blobs(ctx):
+    """a run of stored 536-byte multi bundles / 1032-byte MinHash blobs is mirrored into HBM with one
+    strided copy (ucfp_corpus_append_strided) and queried like individually upserted records."""
+    from ucfp_b200 import Corpus, _ffi
+    rng = np.random.default_rng(0)
+    n = 5000
+    words = rng.integers(0, 2**63, (n, 51), dtype=np.int64).astype(np.uint64)
+    blobs = b"".join(image.pack_multihash(bytes(32), w) for w in words)
+    ids = (np.arange(n, dtype=np.uint64) * np.uint64(3) + np.uint64(11))
+    db = GpuIndexBackend(ctx)
+    db.hydrate_fingerprints(5, image.ALGORITHM_MULTIHASH, ids, blobs)
+    probe = int(words[1234, 17])                               # PHash global hash lives at offset 232
+    hits = db.hamming_knn(5, image.ALGORITHM_MULTIHASH, probe, 3)
+    assert hits[0].record_id == int(ids[1234]) and hits[0].score == 1.0
+    oi, od = oracle.hamming_topk(np.ascontiguousarray(words[:, 17]), np.array([probe], np.uint64), 3, ids=ids)
+    assert [h.record_id for h in hits] == oi[0].tolist()
+    # raw ABI: MinHash payload at offset 8 of 1032-byte records, device-resident source
+    import torch
+    sig = oracle.fill_u64(300 * 128, 9).reshape(300, 128)
+    recs = np.zeros((300, 1032), np.uint8)
+    recs[:, 0] = 1
+    recs[:, 8:] = sig.view(np.uint8).reshape(300, 1024)
+    c = Corpus(ctx, _ffi.KIND_MINHASH128, 300)
+    c.append_strided(torch.from_numpy(recs).cuda(), 1032, 8, 300)
+    gi, gm = c.scan_jaccard(sig[7:8].copy(), 1)
+    assert gi[0, 0] == 7 and gm[0, 0] == 128
+    c.close()

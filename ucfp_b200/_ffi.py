@@ -53,6 +53,7 @@ PROTOTYPES = {
     "ucfp_corpus_create": (_int, [_vp, _int, _u32, _u64, C.POINTER(_vp)]),
     "ucfp_corpus_destroy": (None, [_vp]),
     "ucfp_corpus_append": (_int, [_vp, _vp, _vp, _u64]),
+    "ucfp_corpus_append_strided": (_int, [_vp, _vp, _vp, _u64, _u64, _u64]),
     "ucfp_corpus_set_id_base": (_int, [_vp, _u64]),
     "ucfp_corpus_clear": (_int, [_vp]),
     "ucfp_corpus_size": (_u64, [_vp]),

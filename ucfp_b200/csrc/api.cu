@@ -275,6 +275,36 @@ int ucfp_corpus_append(ucfp_corpus *c, const uint64_t *ids, const void *rows, ui
     return UCFP_OK;
 }
 
+int ucfp_corpus_append_strided(ucfp_corpus *c, const uint64_t *ids, const void *records, uint64_t record_stride,
+                               uint64_t field_offset, uint64_t n) {
+    UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
+    UCFP_GUARD(c->ctx);
+    if (n == 0) return UCFP_OK;
+    UCFP_REQUIRE(records != nullptr, UCFP_E_INVALID, "records is NULL");
+    size_t rb = row_bytes(c);
+    UCFP_REQUIRE(record_stride >= field_offset + rb, UCFP_E_INVALID, "record stride %llu cannot hold a %zu-byte field at offset %llu",
+                 (unsigned long long)record_stride, rb, (unsigned long long)field_offset);
+    UCFP_REQUIRE(c->size + n <= c->capacity, UCFP_E_CAPACITY, "append of %llu rows exceeds capacity %llu (size %llu)",
+                 (unsigned long long)n, (unsigned long long)c->capacity, (unsigned long long)c->size);
+    int mode = ids ? 1 : 2;
+    UCFP_REQUIRE(c->id_mode == 0 || c->id_mode == mode, UCFP_E_STATE, "corpus mixes explicit and implicit record ids");
+    cudaStream_t st = c->ctx->stream;
+    if (mode == 1 && !c->ids) UCFP_CUDA_TRY(cudaMalloc((void **)&c->ids, 8 * (c->capacity + 16)));
+    const bool dev_src = classify(records) == Mem::Device;
+    // a pitched copy gathers the field of every record: source pitch = record stride, width = one row
+    UCFP_CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(c->rows) + rb * c->size, rb, static_cast<const char *>(records) + field_offset,
+                                    record_stride, rb, n, dev_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (mode == 1) {
+        cudaMemcpyKind ki = classify(ids) == Mem::Device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        UCFP_CUDA_TRY(cudaMemcpyAsync(c->ids + c->size, ids, 8 * n, ki, st));
+    }
+    UCFP_TRY(after_append(c, c->size, n));
+    if (!dev_src || mode == 1) UCFP_CUDA_TRY(cudaStreamSynchronize(st));
+    c->id_mode = mode;
+    c->size += n;
+    return UCFP_OK;
+}
+
 int ucfp_corpus_append_synthetic(ucfp_corpus *c, uint64_t seed, uint64_t start_row, uint64_t n) {
     UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
     UCFP_GUARD(c->ctx);

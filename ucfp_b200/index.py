@@ -85,6 +85,39 @@ class GpuIndexBackend:
             for i in ids:
                 self._mh[tenant_id].drop(i)
 
+    def hydrate_fingerprints(self, tenant_id: int, algorithm: str, record_ids, blobs: bytes) -> None:
+        """Bulk load: `blobs` = equally sized fingerprint blobs back to back, as a range scan of the
+        redb fingerprints table yields them (src/index/embedded/mod.rs:37-43).  One strided copy per call instead of
+        one upsert per record."""
+        ids = np.ascontiguousarray(record_ids, dtype=np.uint64)
+        n = len(ids)
+        if n == 0:
+            return
+        size = len(blobs) // n
+        buf = np.frombuffer(blobs, dtype=np.uint8)
+        if algorithm == "minhash-h128":
+            if size != 1032:
+                raise Error("Incompatible", f"MinHashSig<128> blobs must be 1032 bytes, got {size}")
+            shelf = self._mh.setdefault(tenant_id, _Shelf(self.ctx, _ffi.KIND_MINHASH128, 0, np.uint64, 128))
+            off, view = 8, buf.reshape(n, size)[:, 8:].copy().view(np.uint64)
+        else:
+            off = 232 if algorithm == ALGORITHM_MULTIHASH else 32
+            if size != (536 if algorithm == ALGORITHM_MULTIHASH else 168):
+                raise Error("Incompatible", f"{algorithm} blobs have the wrong size {size}")
+            shelf = self._ham.setdefault((tenant_id, algorithm), _Shelf(self.ctx, _ffi.KIND_HAMMING64, 0, np.uint64, 1))
+            view = buf.reshape(n, size)[:, off:off + 8].copy().view(np.uint64)
+        for rid, row in zip(ids, view):          # host copy stays the source of truth for deletes/rebuilds
+            shelf.rows[int(rid)] = np.ascontiguousarray(row).reshape(shelf.width)
+        # the HBM mirror itself is filled by one strided copy straight from the blob run
+        if shelf.corpus is not None:
+            shelf.corpus.close()
+        shelf.corpus = Corpus(self.ctx, shelf.kind, max(int(len(shelf.rows) * _GROW), 1024), dim=shelf.dim)
+        if len(shelf.rows) == n:
+            shelf.corpus.append_strided(buf, size, off, n, ids)
+            shelf.dirty = False
+        else:
+            shelf.dirty = True
+
     def flush(self) -> None:
         self.ctx.synchronize()
 

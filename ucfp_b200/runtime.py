@@ -148,6 +148,10 @@ class Corpus:
         n = rows.shape[0]
         check(self._L.ucfp_corpus_append(self._h, _ptr(ids), _ptr(rows), n))
 
+    def append_strided(self, records, record_stride: int, field_offset: int, n: int, ids=None) -> None:
+        """Bulk hydration: row i = the row-sized field at `field_offset` of record i (records `record_stride` apart)."""
+        check(self._L.ucfp_corpus_append_strided(self._h, _ptr(ids), _ptr(records), record_stride, field_offset, n))
+
     def append_synthetic(self, seed: int, start_row: int, n: int) -> None:
         check(self._L.ucfp_corpus_append_synthetic(self._h, seed, start_row, n))
 
