@@ -91,16 +91,20 @@ __device__ __noinline__ void hamming_survivors(uint4 c01, uint4 c23, uint4 c45, 
                                                uint32_t cap) {
     const uint32_t lo[kCodesPerThread] = {c01.x, c01.z, c23.x, c23.z, c45.x, c45.z, c67.x, c67.z};
     const uint32_t hi[kCodesPerThread] = {c01.y, c01.w, c23.y, c23.w, c45.y, c45.w, c67.y, c67.w};
+    // most calls end here: the one-POPC bound let the pair through but no true distance is within thr
+    uint32_t d[kCodesPerThread], dmin = 64;
+#pragma unroll
+    for (int c = 0; c < kCodesPerThread; ++c) { d[c] = __popc(lo[c] ^ s.x) + __popc(hi[c] ^ s.y); dmin = min(dmin, d[c]); }
+    if (dmin > s.z) return;
     const uint64_t kid = kth_id[q];
 #pragma unroll
     for (int c = 0; c < kCodesPerThread; ++c) {
-        uint32_t d = __popc(lo[c] ^ s.x) + __popc(hi[c] ^ s.y);
         uint64_t r = tile_row + 2ull * ((c >> 1) * kScanThreads + threadIdx.x) + (c & 1);
-        if (d <= s.z && r < row_end) {
+        if (d[c] <= s.z && r < row_end) {
             uint64_t id = ids ? ids[r] : id_base + r;
-            if (d < s.z || id < kid) {
+            if (d[c] < s.z || id < kid) {
                 uint32_t pos = atomicAdd(&count[q], 1u);
-                if (pos < cap) cand[(size_t)q * cap + pos] = ((uint64_t)d << 40) | r;
+                if (pos < cap) cand[(size_t)q * cap + pos] = ((uint64_t)d[c] << 40) | r;
             }
         }
     }
