@@ -13,7 +13,7 @@ ncu --set full --clock-control none --import-source on -k regex:hamming_scan_ker
 echo "hamming q1024 rc=$?"
 CMD="python scripts/dev_hamming_bench.py 1e9 1"
 $CMD > gpurun_out/plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:hamming_scan_kernel -s 9 -c 1 -o gpurun_out/hamming_scan_q1 $CMD > gpurun_out/ncu_full2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:hamming_scan_kernel -s 2 -c 1 -o gpurun_out/hamming_scan_q1 $CMD > gpurun_out/ncu_full2.log 2>&1
 echo "hamming q1 rc=$?"
 CMD="python scripts/prof_scan.py cosine 2e6 1024"
 $CMD > gpurun_out/plain4.log 2>&1 &&
@@ -21,7 +21,7 @@ ncu --set full --clock-control none --import-source on -k regex:cosine_coarse -s
 echo "cosine rc=$?"
 CMD="python scripts/prof_scan.py jaccard 4e6 256"
 $CMD > gpurun_out/plain5.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:jaccard_scan -s 14 -c 1 -o gpurun_out/jaccard_scan_q256 $CMD > gpurun_out/ncu_full4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:jaccard_scan -s 11 -c 1 -o gpurun_out/jaccard_scan_q256 $CMD > gpurun_out/ncu_full4.log 2>&1
 echo "jaccard rc=$?"
 CMD="python scripts/prof_image.py 1024 1024 1184"
 $CMD > gpurun_out/plain6.log 2>&1 &&
