@@ -27,6 +27,7 @@ constexpr int kScanThreads = 256;
 constexpr uint32_t kSeedRows = 1024;
 constexpr uint32_t kMaxQueriesPerPass = 256;     // 128 B of sketch + 4 B bound per query in shared memory
 constexpr uint64_t kMaxChunkRows = 1ULL << 26;
+constexpr uint32_t kLocalVerifyMax = 8;          // survivors with <= this many agreeing bytes verify lane-locally
 
 // Sketch layout: tiles of 32 rows; word j (slots 4j..4j+3) of row r lives at
 // (r / 32) * 1024 + j * 32 + (r % 32), so that a warp reads word j of 32 consecutive rows as one 128-byte line.
@@ -77,11 +78,24 @@ __global__ void jaccard_seed_kernel(const uint64_t *__restrict__ sigs, uint32_t 
     if (blockIdx.x == 0 && threadIdx.x == 0) count[qi] = rows;
 }
 
-// number of equal bytes in two packed words: SWAR zero-byte detection on a ^ b
-__device__ __forceinline__ uint32_t eq_bytes_flags(uint32_t a, uint32_t b) {
+// SWAR byte compare: 0x80 in every byte where a and b DIFFER (zero-byte detection on a ^ b, inverted)
+__device__ __forceinline__ uint32_t ne_bytes_flags(uint32_t a, uint32_t b) {
     uint32_t x = a ^ b;
     uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-    return ~(t | x | 0x7F7F7F7Fu);  // 0x80 in every byte where a and b agree
+    return (t | x) & 0x80808080u;
+}
+// Differing bytes of 8 word pairs with ONE popcount: word j's flags sit at bit 7 of each byte; g = (g >> 1) + flags
+// moves the older flags down to bits 6..0, so after 8 words every flag has its own bit.
+__device__ __forceinline__ uint32_t ne_bytes_8words(const uint32_t *w, uint4 q0, uint4 q1) {
+    uint32_t g = ne_bytes_flags(w[0], q0.x);
+    g = (g >> 1) + ne_bytes_flags(w[1], q0.y);
+    g = (g >> 1) + ne_bytes_flags(w[2], q0.z);
+    g = (g >> 1) + ne_bytes_flags(w[3], q0.w);
+    g = (g >> 1) + ne_bytes_flags(w[4], q1.x);
+    g = (g >> 1) + ne_bytes_flags(w[5], q1.y);
+    g = (g >> 1) + ne_bytes_flags(w[6], q1.z);
+    g = (g >> 1) + ne_bytes_flags(w[7], q1.w);
+    return (uint32_t)__popc(g);
 }
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -112,33 +126,46 @@ jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint64_t *__restr
             const uint4 *qv = reinterpret_cast<const uint4 *>(sq + (size_t)qi * kSketchWords);
             const uint32_t thr = sthr[qi];
             const uint32_t need = 128u - thr;               // byte matches a row needs to stay in the race
-            uint32_t acc = 0;
+            uint32_t bm = 0;                                // byte matches so far: an upper bound on slot matches
             bool alive = true;
             // four groups of 8 words (32 slots).  After each of the first three, the warp stops as soon as no lane
             // can still reach `need` even if every remaining byte matched -- exact branch-and-bound, and with a
             // meaningful bound almost every (row, query) pair ends after the first group.
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-#pragma unroll
-                for (int j4 = 2 * g; j4 < 2 * g + 2; ++j4) {
-                    uint4 v = qv[j4];  // broadcast LDS.128
-                    acc += eq_bytes_flags(w[4 * j4], v.x) >> 7;
-                    acc += eq_bytes_flags(w[4 * j4 + 1], v.y) >> 7;
-                    acc += eq_bytes_flags(w[4 * j4 + 2], v.z) >> 7;
-                    acc += eq_bytes_flags(w[4 * j4 + 3], v.w) >> 7;
-                }
-                if (g < 3) {
-                    const uint32_t part = (acc * 0x01010101u) >> 24;
-                    if (!__any_sync(0xffffffffu, valid && part + (96u - 32u * g) >= need)) { alive = false; break; }
-                }
+                bm += 32u - ne_bytes_8words(&w[8 * g], qv[2 * g], qv[2 * g + 1]);   // two broadcast LDS.128
+                if (g < 3 && !__any_sync(0xffffffffu, valid && bm + (96u - 32u * g) >= need)) { alive = false; break; }
             }
             if (!alive) continue;
-            const uint32_t bm = (acc * 0x01010101u) >> 24;  // byte matches: an upper bound on slot matches
             const uint32_t lower = 128u - bm;               // lower bound on the key
             const uint64_t kid = skid[qi];
             // (key, id) can beat the current k-th only if (lower, id) < (thr, kth_id)
-            unsigned hits = __ballot_sync(0xffffffffu, valid && (lower < thr || (lower == thr && id < kid)));
-            if (hits) {  // rare: verify against the full rows, one survivor at a time, whole warp per row
+            const bool hit = valid && (lower < thr || (lower == thr && id < kid));
+            if (__any_sync(0xffffffffu, hit)) {
+                // Survivors with only a few agreeing bytes (chance collisions: 1/256 per slot) are settled by their own
+                // lane: only the slots whose low bytes agree can match, so compare just those full 64-bit slots.
+                const bool local = hit && bm <= kLocalVerifyMax;
+                if (local) {
+                    const uint64_t *rp = sigs + row * kSlots;
+                    const uint64_t *qp = q + (size_t)qi * kSlots;
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int j = 0; j < kSketchWords; ++j) {   // fully unrolled: w[] must stay in registers
+                        uint32_t eq = ~ne_bytes_flags(w[j], sq[(size_t)qi * kSketchWords + j]) & 0x80808080u;
+                        while (eq) {
+                            const int slot = 4 * j + ((__ffs(eq) - 1) >> 3);
+                            eq &= eq - 1;
+                            m += (__ldg(rp + slot) == __ldg(qp + slot));
+                        }
+                    }
+                    const uint32_t key = 128u - m;
+                    if (key < thr || (key == thr && id < kid)) {
+                        uint32_t pos = atomicAdd(&S.count[qi], 1u);
+                        if (pos < S.cap) S.cand[(size_t)qi * S.cap + pos] = ((uint64_t)key << 40) | row;
+                    }
+                }
+                // rows with many agreeing bytes (real neighbours): the whole warp verifies one row at a time
+                unsigned hits = __ballot_sync(0xffffffffu, hit && !local);
                 while (hits) {
                     const int src = __ffs(hits) - 1;
                     hits &= hits - 1;
