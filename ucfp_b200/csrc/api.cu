@@ -113,6 +113,8 @@ void ucfp_destroy(ucfp_ctx *ctx) {
                       &ctx->misc, &ctx->img_desc_dev, &ctx->img_out_dev, &ctx->img_status_dev, &ctx->img_tables_dev, &ctx->img_stage_dev, &ctx->stats};
     for (DevBuf *b : bufs) b->release();
     ctx->pin_a.release(); ctx->pin_b.release();
+    image_cache_destroy(ctx);
+    for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

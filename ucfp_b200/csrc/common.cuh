@@ -59,6 +59,14 @@ struct DevBuf {
     template <typename T> T *as() const { return reinterpret_cast<T *>(ptr); }
 };
 
+// A DevBuf that frees itself: for per-call temporaries that must not leak on an early error return.
+struct ScopedDevBuf : DevBuf {
+    ScopedDevBuf() = default;
+    ScopedDevBuf(const ScopedDevBuf &) = delete;
+    ScopedDevBuf &operator=(const ScopedDevBuf &) = delete;
+    ~ScopedDevBuf() { release(); }
+};
+
 struct PinnedBuf {
     void *ptr = nullptr;
     size_t bytes = 0;
@@ -93,6 +101,7 @@ struct ucfp_ctx {
     ucfp::DevBuf img_desc_dev, img_out_dev, img_status_dev, img_tables_dev, img_stage_dev;
     ucfp::PinnedBuf pin_a, pin_b;
     ucfp::DevBuf stats;            // u64[4]: [0] queries recomputed by the exact fallback in the last scan
+    void *image_cache = nullptr;   // per-shape tap tables of image.cu (owned by it; freed by image_cache_destroy)
 };
 
 struct ucfp_corpus {
@@ -160,6 +169,7 @@ int synth_fill_u64(ucfp_ctx *ctx, uint64_t *dst_dev, uint64_t nwords, uint64_t s
 int image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *descs_host, size_t n, uint32_t algo_mask,
                      ucfp_image_hashes *out_dev, int32_t *status_host);
 
+void image_cache_destroy(ucfp_ctx *ctx);
 int stats_reset(ucfp_ctx *ctx);
 int stats_add_flags(ucfp_ctx *ctx, const uint32_t *flags_dev, uint32_t nq);
 

@@ -190,11 +190,8 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
     const uint64_t *codes = static_cast<const uint64_t *>(c->rows);
     const uint64_t *ids = c->id_mode == 1 ? c->ids : nullptr;
 
-    static bool attr_done = false;
-    if (!attr_done) {
-        UCFP_CUDA_TRY(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
-        attr_done = true;
-    }
+    // function attributes are per device: set them on every call (a host-side table write)
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
     int scan_occ = 0;
     UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_occ, hamming_scan_kernel, kScanThreads,
                                                                  sizeof(QSlot) * kMaxQueriesPerPass));

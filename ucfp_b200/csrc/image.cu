@@ -113,8 +113,7 @@ struct ShapeTables {
     size_t stream_smem = 0;
 };
 
-struct ShapeCache { std::map<uint64_t, ShapeTables> m; };
-std::map<ucfp_ctx *, ShapeCache> g_cache;  // guarded by ctx->mu (every caller holds it)
+struct ShapeCache { std::map<uint64_t, ShapeTables> m; };   // lives in ucfp_ctx::image_cache, guarded by ctx->mu
 
 int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
     std::vector<Taps> hout(5 * kHOuts), vout(5 * kVOuts);
@@ -697,7 +696,9 @@ int image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *descs, size_t n, uint
         groups[(uint64_t)d.width << 32 | d.height].push_back(it);
     }
 
-    ShapeCache &cache = g_cache[ctx];
+    if (!ctx->image_cache) ctx->image_cache = new (std::nothrow) ShapeCache();
+    UCFP_REQUIRE(ctx->image_cache != nullptr, UCFP_E_OOM, "out of host memory");
+    ShapeCache &cache = *static_cast<ShapeCache *>(ctx->image_cache);
     for (auto &kv : groups) {
         const int w = (int)(kv.first >> 32), h = (int)(kv.first & 0xffffffffu);
         auto found = cache.m.find(kv.first);
@@ -716,7 +717,7 @@ int image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *descs, size_t n, uint
             hostdesc[j] = ImgDev{items[j].dev_pixels, items[j].stride, (uint32_t)items[j].idx, al};
         }
         // one descriptor buffer per group: the copy below must finish before the vector dies
-        DevBuf descbuf;
+        ScopedDevBuf descbuf;
         UCFP_TRY(descbuf.reserve(sizeof(ImgDev) * items.size()));
         UCFP_CUDA_TRY(cudaMemcpyAsync(descbuf.ptr, hostdesc.data(), sizeof(ImgDev) * items.size(), cudaMemcpyHostToDevice, st));
         uint64_t *out_words = reinterpret_cast<uint64_t *>(out_dev);
@@ -748,10 +749,17 @@ int image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *descs, size_t n, uint
         }
         count_launch(ctx);
         UCFP_TRY(check_launch("image hash"));
-        UCFP_CUDA_TRY(cudaStreamSynchronize(st));  // descbuf and hostdesc are released here
-        descbuf.release();
+        UCFP_CUDA_TRY(cudaStreamSynchronize(st));  // descbuf and hostdesc die at the end of this iteration
     }
     return UCFP_OK;
+}
+
+void image_cache_destroy(ucfp_ctx *ctx) {
+    if (!ctx->image_cache) return;
+    ShapeCache *cache = static_cast<ShapeCache *>(ctx->image_cache);
+    for (auto &kv : cache->m) if (kv.second.blob) cudaFree(kv.second.blob);
+    delete cache;
+    ctx->image_cache = nullptr;
 }
 
 }  // namespace ucfp
