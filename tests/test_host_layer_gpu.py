@@ -144,3 +144,20 @@ def test_bulk_hydration_from_stored_blobs(ctx):
     gi, gm = c.scan_jaccard(sig[7:8].copy(), 1)
     assert gi[0, 0] == 7 and gm[0, 0] == 128
     c.close()
+
+
+def test_cpp_host_mirror_runs_on_the_gpu(tmp_path):
+    """include/ucfp/host.hpp end to end: the reference's index tests and one image bundle, from C++."""
+    import os
+    import subprocess
+    from ucfp_b200 import _ffi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_mirror_test")
+    libdir = os.path.dirname(_ffi.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "host_mirror_test.cpp"),
+                    "-o", exe, "-L", libdir, "-lucfp_cuda", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
+    bundle = bytes.fromhex([l for l in out.stdout.splitlines() if l.startswith("BUNDLE ")][0].split()[1])
+    _, arr = synthetic_png(64, 64)
+    assert bundle == image.pack_multihash(bytes([0xAB]) * 32, oracle.image_multihash(arr))
