@@ -38,7 +38,7 @@ struct Taps { int left, n, woff; };                         // one output sample
 struct __align__(16) VEntry { float w[3]; uint8_t n_active, n_finish; uint16_t pad; };   // host-side, per (pass, row)
 // Device-side per-row table of the four vertical passes: weights of the two lowest active outputs, the third
 // weight, and flags (byte s: bit 0 = three outputs active, bits 1..3 = outputs completed by this row).
-struct __align__(16) RowEntry { float w01[4][2]; float w2[4]; uint32_t flags; uint32_t pad[3]; };   // 64 bytes
+struct __align__(16) RowEntry { float w01[4][2]; float w2[4]; uint32_t flags; uint32_t run; uint32_t pad[2]; };   // 64 bytes; run = rows from here on with flags == 0
 struct FinDesc { uint8_t stream, o, r, pad; };               // stream: 0 whole->32, 1 whole->8, 2 block->32, 3 block->8
 
 struct ShapeDev {
@@ -261,6 +261,8 @@ int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
         }
         rowtab[y] = e;
     }
+    for (int y = h - 1; ok && y >= 0; --y)   // length of the run of flag-free rows starting at y
+        rowtab[y].run = rowtab[y].flags ? 0u : 1u + (y + 1 < h ? rowtab[y + 1].run : 0u);
     size_t off_t = align16(off_w + wts.size() * 4), off_f = align16(off_t + rowtab.size() * sizeof(RowEntry));
     size_t off_b = align16(off_f + (ok ? fin_rows.size() * sizeof(FinDesc) : 0));
     size_t total = align16(off_b + (ok ? band_off.size() * 4 : 0)) + 16;
@@ -553,15 +555,13 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
             if (BULK) mbar_wait(&full[s_idx], (c / NS) & 1);
             const uint8_t *base = BULK ? ring + (size_t)s_idx * L.stage_bytes + 3 * (size_t)x0
                                        : I.pixels + (size_t)y_lo * I.stride + 3 * (size_t)x0;
-            for (int y = y_lo; y < y_hi; ++y) {
-                const RowEntry &e = rt[y - band_lo];
+            // One row: luma of this thread's pixels, then the two lowest active outputs of each of the four passes.
+            auto row_body = [&](int y, const RowEntry &e, float (&v)[CPT]) {
                 const ulonglong2 wa = *reinterpret_cast<const ulonglong2 *>(&e.w01[0][0]);   // passes 0, 1 (broadcast LDS.128)
                 const ulonglong2 wb = *reinterpret_cast<const ulonglong2 *>(&e.w01[2][0]);   // passes 2, 3
-                const uint32_t flags = e.flags;
                 const uint64_t w01[4] = {wa.x, wa.y, wb.x, wb.y};
-                float v[CPT];
                 const uint8_t *px = base + (size_t)(y - y_lo) * pitch;
-                if (CPT % 4 == 0 && (BULK || I.aligned4) && w % CPT == 0) {
+                if (CPT % 4 == 0 && (BULK || (I.aligned4 && w % CPT == 0))) {   // bulk staging implies w % 16 == 0
                     const uint32_t *p32 = reinterpret_cast<const uint32_t *>(px);
 #pragma unroll
                     for (int g = 0; g < CPT / 4; ++g)   // 4 pixels = 12 bytes = 3 words
@@ -584,7 +584,21 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
                         acc[s][1][cc] = acc[s][1][cc] + p1;
                     }
                 }
-                if (flags) {   // uniform and infrequent: a third active output, or outputs completed by this row
+            };
+            int y = y_lo;
+            while (y < y_hi) {
+                // a run of rows on which no output completes and no third output is active: nothing but arithmetic
+                const int run = min((int)rt[y - band_lo].run, y_hi - y);
+                for (int i = 0; i < run; ++i, ++y) {
+                    float v[CPT];
+                    row_body(y, rt[y - band_lo], v);
+                }
+                if (y >= y_hi) break;
+                const RowEntry &e = rt[y - band_lo];
+                float v[CPT];
+                row_body(y, e, v);
+                const uint32_t flags = e.flags;   // uniform: a third active output, or outputs completed by this row
+                if (flags) {
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
                         const uint32_t fl = (flags >> (8 * s)) & 255u;
@@ -604,6 +618,7 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
                         }
                     }
                 }
+                ++y;
             }
             if (BULK) {   // hand the stage back: every warp arrives, thread 0 refills once all have
                 __syncwarp();
