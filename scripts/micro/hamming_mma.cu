@@ -1,0 +1,372 @@
+// Developer microbenchmark: batched Hamming filter on the int8 tensor pipe (tcgen05.mma kind::i8, sm_100a).
+// Codes and queries are expanded to +-1 int8 vectors, so that  D = sum a_i b_i = 64 - 2 * dist  lands in TMEM
+// as an exact s32; the epilogue keeps only "any D >= 64 - 2 thr_q" per 32 columns.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o hamming_mma hamming_mma.cu
+//   ./hamming_mma [rows_log2=26] [nq=1024] [mode=0]     mode 1: epilogue without TMEM loads, 2: loads only
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("%s: %s\n",#x,cudaGetErrorString(e)); return 1;}}while(0)
+
+constexpr int kQTile = 128, kCTile = 256, kRowBytes = 128, kStages = 2, kMaxQ = 1024;
+constexpr int kQBytes = kQTile * kRowBytes, kCBytes = kCTile * kRowBytes;
+#ifndef VARIANT
+#define VARIANT 0
+#endif
+#ifndef EPI_WARPS
+#define EPI_WARPS 8
+#endif
+constexpr int kExpWarps = 4, kEpiWarps = EPI_WARPS, kColsPerWarp = 256 / (kEpiWarps / 4), kThreads = 32 * (1 + kExpWarps + kEpiWarps);
+constexpr size_t kSmem = (size_t)(kMaxQ / kQTile) * kQBytes + kStages * kCBytes + kMaxQ * 4 + 256 + 1024;
+
+struct __align__(16) QSlot { uint32_t lo, hi, thr, pad; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void umma_i8(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) : "r"(taddr));
+}
+// 64 columns, low 16 bits of each, two columns per register (column 2i in the low half)
+__device__ __forceinline__ void tmem_ld64p_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) : "r"(taddr));
+}
+// waits for the outstanding tcgen05.ld; the registers are tied to the statement so that no use can move above it
+__device__ __forceinline__ void tmem_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]) :: "memory");
+}
+__device__ __forceinline__ int32_t max32(const uint32_t (&v)[32]) {
+    int32_t m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = (int32_t)v[j];
+#pragma unroll
+    for (int c = 4; c < 32; ++c) m[c & 3] = max(m[c & 3], (int32_t)v[c]);
+    return max(max(m[0], m[1]), max(m[2], m[3]));
+}
+
+// 4 bits -> 4 bytes, bit set -> +1 (0x01), clear -> -1 (0xFF)
+__device__ __forceinline__ uint32_t expand4(uint32_t nib) {
+    uint32_t t = (nib * 0x00204081u) & 0x01010101u;
+    return ~(t * 0xFEu);
+}
+// two 64-bit codes a, b -> 64 int8 elements  -a_k + 64 b_k  (a_k, b_k = +-1): 0xC1 ^ (abit * 0x7E) ^ (bbit * 0x80)
+__device__ __forceinline__ uint32_t expand4x2(uint32_t na, uint32_t nb) {
+    uint32_t ta = (na * 0x00204081u) & 0x01010101u, tb = (nb * 0x00204081u) & 0x01010101u;
+    return 0xC1C1C1C1u ^ (ta * 0x7Eu) ^ (tb << 7);
+}
+__device__ __forceinline__ void store_row2(unsigned char *tile, uint32_t r, uint64_t a, uint64_t b) {
+    unsigned char *row = tile + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t ha = (uint32_t)(a >> (16 * c)) & 0xFFFFu, hb = (uint32_t)(b >> (16 * c)) & 0xFFFFu;
+        uint4 w;
+        w.x = expand4x2(ha & 15, hb & 15); w.y = expand4x2((ha >> 4) & 15, (hb >> 4) & 15);
+        w.z = expand4x2((ha >> 8) & 15, (hb >> 8) & 15); w.w = expand4x2(ha >> 12, hb >> 12);
+        *reinterpret_cast<uint4 *>(row + ((c ^ (r & 7)) << 4)) = w;
+    }
+}
+// one 64-bit code -> 64 int8 in the first four 16-byte chunks of row r of a 128B-swizzled K-major tile
+__device__ __forceinline__ void store_row(unsigned char *tile, uint32_t r, uint32_t lo, uint32_t hi, bool valid) {
+    unsigned char *row = tile + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t h = (c < 2 ? lo : hi) >> ((c & 1) * 16);
+        uint4 w;
+        w.x = expand4(h & 15); w.y = expand4((h >> 4) & 15); w.z = expand4((h >> 8) & 15); w.w = expand4((h >> 12) & 15);
+        if (!valid) w = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(row + ((c ^ (r & 7)) << 4)) = w;
+    }
+}
+
+struct Tally { unsigned long long count, check; };
+// Cold path (the whole warp calls it: tcgen05.ld is warp-collective): re-reads the 32 accumulators of one chunk from TMEM (no other tcgen05.ld may be in flight), decodes which
+// columns can hold an admissible pair and settles those from the codes themselves.
+__device__ __noinline__ void hamming_cold(uint32_t taddr, uint64_t row0, uint64_t nrows, uint32_t thr, uint32_t q,
+                                          const uint64_t *__restrict__ codes, const QSlot *__restrict__ slots, Tally *tally) {
+    uint32_t v[32];
+    tmem_ld32(taddr, v);
+    uint32_t mask = 0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const int32_t D = (int32_t)v[c];
+        if ((((uint32_t)D ^ 64u) & 127u) <= 2 * thr || D >= 64 * (63 - 2 * (int32_t)thr)) mask |= 1u << c;
+    }
+    const QSlot s = slots[q];
+    const uint64_t qc = (uint64_t)s.hi << 32 | s.lo;
+    while (mask) {
+        const int c = __ffs(mask) - 1;
+        mask &= mask - 1;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint64_t r = row0 + 2 * c + h;
+            if (r < nrows) {
+                uint32_t d = __popcll(codes[r] ^ qc);
+                if (d <= thr) { tally->count++; tally->check += (r + 1) * (d + 1) * (q + 1); }
+            }
+        }
+    }
+}
+// hot test of one chunk: does any accumulator D = -x + 64 y (x, y = 64 - 2 dist of the two codes of a column) admit?
+//   x >= tau  <=>  low 7 bits of D, as a signed number, <= -tau   (tested on D << 25, a multiply: fma pipe)
+//   y >= tau  <=>  D >= 64 tau - 64
+__device__ __forceinline__ bool chunk_fires(const uint32_t (&v)[32], int32_t lo_bound, int32_t hi_bound) {
+    int32_t mx[4], mn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mx[j] = (int32_t)v[j]; mn[j] = (int32_t)(v[j] * 0x02000000u); }
+#pragma unroll
+    for (int c = 4; c < 32; ++c) { mx[c & 3] = max(mx[c & 3], (int32_t)v[c]); mn[c & 3] = min(mn[c & 3], (int32_t)(v[c] * 0x02000000u)); }
+    return min(min(mn[0], mn[1]), min(mn[2], mn[3])) <= lo_bound || max(max(mx[0], mx[1]), max(mx[2], mx[3])) >= hi_bound;
+}
+
+// running (min of D << 25, max of D) over 32 unpacked accumulators
+__device__ __forceinline__ void minmax_acc(const uint32_t (&v)[32], int32_t (&mn)[4], int32_t (&mx)[4]) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) { mx[c & 3] = max(mx[c & 3], (int32_t)v[c]); mn[c & 3] = min(mn[c & 3], (int32_t)(v[c] * 0x02000000u)); }
+}
+// the same over 32 registers holding 64 accumulators as s16 pairs: every field is moved to the top of a 32-bit word
+__device__ __forceinline__ void minmax_acc_packed(const uint32_t (&p)[32], int32_t (&mn)[4], int32_t (&mx)[4]) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        mx[c & 3] = max(max(mx[c & 3], (int32_t)p[c]), (int32_t)(p[c] * 0x10000u));
+        mn[c & 3] = min(min(mn[c & 3], (int32_t)(p[c] * 0x200u)), (int32_t)(p[c] * 0x02000000u));
+    }
+}
+// packed form of chunk_fires: 32 registers = 64 accumulators as s16 pairs; bounds are s16 values
+__device__ __forceinline__ bool chunk_fires_packed(const uint32_t (&p)[32], int32_t lo16, int32_t hi16) {
+    uint32_t mx[4], mn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mx[j] = p[j]; mn[j] = p[j] * 512u; }
+#pragma unroll
+    for (int c = 4; c < 32; c += 8) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            mx[j] = __vimax3_s16x2(mx[j], p[c + j], p[c + 4 + j]);
+            mn[j] = __vimin3_s16x2(mn[j], p[c + j] * 512u, p[c + 4 + j] * 512u);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mx[j] = __vmaxs2(mx[j], p[28 + j]); mn[j] = __vmins2(mn[j], p[28 + j] * 512u); }
+    const uint32_t m1 = __vimax3_s16x2(mx[0], mx[1], mx[2]), m2 = __vmaxs2(m1, mx[3]);
+    const uint32_t n1 = __vimin3_s16x2(mn[0], mn[1], mn[2]), n2 = __vmins2(n1, mn[3]);
+    const int32_t mxv = max((int32_t)(int16_t)(m2 & 0xFFFFu), (int32_t)m2 >> 16), mnv = min((int32_t)(int16_t)(n2 & 0xFFFFu), (int32_t)n2 >> 16);
+    return mnv <= lo16 || mxv >= hi16;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+hamming_mma_kernel(const uint64_t *__restrict__ codes, uint64_t nrows, const QSlot *__restrict__ slots, uint32_t nq,
+                   unsigned long long *count, unsigned long long *check, int mode, unsigned long long *clk) {
+    unsigned long long clk_c0 = clock64(), clk_t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(clk_t0));
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t q_tiles = (nq + kQTile - 1) / kQTile;
+    unsigned char *sQ = smem;
+    unsigned char *sC = smem + (size_t)(kMaxQ / kQTile) * kQBytes;
+    int32_t *s_tau = reinterpret_cast<int32_t *>(sC + kStages * kCBytes);
+    uint64_t *cfull = reinterpret_cast<uint64_t *>(s_tau + kMaxQ);
+    uint64_t *cempty = cfull + kStages, *tfull = cempty + kStages, *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_tiles = (uint32_t)((nrows + 2 * kCTile - 1) / (2 * kCTile));   // 2 codes per B row
+
+    // queries -> resident A tiles; admission bounds D >= 64 - 2 thr
+    for (uint32_t q = threadIdx.x; q < q_tiles * kQTile; q += blockDim.x) {
+        QSlot s = q < nq ? slots[q] : QSlot{0, 0, 0, 0};
+        store_row(sQ + (q / kQTile) * kQBytes, q % kQTile, s.lo, s.hi, q < nq);
+        s_tau[q] = q < nq ? 64 - 2 * (int)s.thr : 0x7FFFFFFF;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&cfull[s], kExpWarps * 32); mbar_init(&cempty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of sQ -> visible to the MMA
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kCTile >> 3) << 17) | ((uint32_t)(kQTile >> 4) << 24);
+        uint32_t it = 0, acc_it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            mbar_wait(&cfull[s], ph);
+            tc_fence_after();
+            const uint64_t bdesc = desc_sw128(smem_u32(sC + s * kCBytes));
+            for (uint32_t mt = 0; mt < q_tiles; ++mt, ++acc_it) {
+                const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                mbar_wait(&tempty[as], aph ^ 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t adesc = desc_sw128(smem_u32(sQ + mt * kQBytes));
+                    umma_i8(tmem_base + as * kCTile, adesc, bdesc, idesc, 0u);
+                    umma_i8(tmem_base + as * kCTile, adesc + 2, bdesc + 2, idesc, 1u);
+                    umma_commit(&tfull[as]);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) umma_commit(&cempty[s]);
+            __syncwarp();
+        }
+    } else if (warp <= kExpWarps) {
+        // ===== expanders: 2 codes per thread per stage =====
+        const uint32_t t = threadIdx.x - 32;
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            const uint64_t base = (uint64_t)tile * (2 * kCTile);
+            uint64_t c[4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {   // rows t and t + 128 of the stage: codes 2r, 2r + 1 (out of range -> 0, rejected by the cold path)
+                const uint64_t r0 = base + 2 * (t + 128 * j);
+                if (r0 + 1 < nrows) { ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(codes + r0); c[2 * j] = v.x; c[2 * j + 1] = v.y; }
+                else { c[2 * j] = r0 < nrows ? codes[r0] : 0; c[2 * j + 1] = 0; }
+            }
+            mbar_wait(&cempty[s], ph ^ 1);
+            store_row2(sC + s * kCBytes, t, c[0], c[1]);
+            store_row2(sC + s * kCBytes, t + 128, c[2], c[3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&cfull[s]);
+        }
+    } else {
+        // ===== epilogue: warp -> TMEM lane quadrant (warp % 4), half of the 256 columns =====
+        const uint32_t quad = warp & 3, part = (warp - 1 - kExpWarps) >> 2;
+        uint32_t acc_it = 0;
+        Tally tally{0, 0};
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint64_t base = (uint64_t)tile * (2 * kCTile) + 2 * part * kColsPerWarp;
+            for (uint32_t mt = 0; mt < q_tiles; ++mt, ++acc_it) {
+                const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                const uint32_t q = mt * kQTile + quad * 32 + lane;
+                const int32_t tau = s_tau[q];                 // 64 - 2 thr (INT_MAX for padding lanes)
+                const bool pad = tau == 0x7FFFFFFF;
+                const uint32_t thr = pad ? 0u : (uint32_t)(64 - tau) >> 1;
+                // x-test: min over (field << 25 | junk) <= lo_bound;  y-test: max over (D, or D16 << 16 | junk) >= hi_bound
+                const int32_t lo_bound = pad ? (int32_t)0x80000000 : (thr >= 64 ? 0x7FFFFFFF : (int32_t)(((uint32_t)(-tau) << 25) | 0x01FFFFFFu));
+                const int32_t hi_bound = pad ? 0x7FFFFFFF : (VARIANT == 2 ? (64 * (tau - 1)) * 65536 : 64 * (tau - 1));
+                mbar_wait(&tfull[as], aph);
+                tc_fence_after();
+                if (mode != 1) {
+                    const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * kCTile + part * kColsPerWarp;
+#pragma unroll
+                    for (uint32_t c0 = 0; c0 < kColsPerWarp; c0 += 64) {
+                        int32_t mn[4] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, mx[4] = {(int32_t)0x80000000, (int32_t)0x80000000, (int32_t)0x80000000, (int32_t)0x80000000};
+                        if (VARIANT == 2) {
+                            uint32_t va[32];
+                            tmem_ld64p_nowait(taddr + c0, va);
+                            tmem_wait(va);
+                            if (mode == 2) { if (max32(va) == 12345) tally.count++; continue; }
+                            minmax_acc_packed(va, mn, mx);
+                        } else {
+                            uint32_t va[32], vb[32];
+                            tmem_ld32_nowait(taddr + c0, va);
+                            tmem_ld32_nowait(taddr + c0 + 32, vb);
+                            tmem_wait(va); tmem_wait(vb);
+                            if (mode == 2) { if (max32(va) + max32(vb) == 12345) tally.count++; continue; }
+                            minmax_acc(va, mn, mx);
+                            minmax_acc(vb, mn, mx);
+                        }
+                        const bool fired = min(min(mn[0], mn[1]), min(mn[2], mn[3])) <= lo_bound || max(max(mx[0], mx[1]), max(mx[2], mx[3])) >= hi_bound;
+                        if (__any_sync(0xFFFFFFFFu, fired)) {
+                            hamming_cold(taddr + c0, base + 2 * c0, nrows, thr, q, codes, slots, &tally);
+                            hamming_cold(taddr + c0 + 32, base + 2 * c0 + 64, nrows, thr, q, codes, slots, &tally);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[as]);
+            }
+        }
+        if (tally.count) { atomicAdd(count, tally.count); atomicAdd(check, tally.check); }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && clk) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); clk[0] = clock64() - clk_c0; clk[1] = t1 - clk_t0; }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+__global__ void ref_kernel(const uint64_t *codes, uint64_t nrows, const QSlot *slots, uint32_t nq, unsigned long long *count, unsigned long long *check) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    uint64_t c = codes[r];
+    unsigned long long n = 0, s = 0;
+    for (uint32_t q = 0; q < nq; ++q) {
+        uint32_t d = __popcll(c ^ ((uint64_t)slots[q].hi << 32 | slots[q].lo));
+        if (d <= slots[q].thr) { n++; s += (r + 1) * (d + 1) * (q + 1); }
+    }
+    if (n) { atomicAdd(count, n); atomicAdd(check, s); }
+}
+__global__ void fill(uint64_t *p, uint64_t n, uint64_t seed) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, st = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += st) { uint64_t z = seed ^ ((i + 1) * 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; p[i] = z ^ (z >> 31); }
+}
+__global__ void make_slots(const uint64_t *q, uint32_t nq, QSlot *s, uint32_t thr_base) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) s[i] = QSlot{(uint32_t)q[i], (uint32_t)(q[i] >> 32), thr_base + i % 5, 0};
+}
+
+int main(int argc, char **argv) {
+    int lg = argc > 1 ? atoi(argv[1]) : 26; uint32_t nq = argc > 2 ? atoi(argv[2]) : 1024; int mode = argc > 3 ? atoi(argv[3]) : 0;
+    uint64_t N = (1ull << lg) - 77;   // ragged tail on purpose
+    int sms; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    uint64_t *codes, *q; QSlot *slots; unsigned long long *res;
+    CK(cudaMalloc(&codes, N * 8)); CK(cudaMalloc(&q, nq * 8)); CK(cudaMalloc(&slots, nq * 16)); CK(cudaMalloc(&res, 64));
+    fill<<<1024, 256>>>(codes, N, 0xC0DE); fill<<<4, 256>>>(q, nq, 0xBEEF);
+    CK(cudaFuncSetAttribute(hamming_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    for (uint32_t thr_base : {18u, 10u}) {
+        make_slots<<<(nq + 255) / 256, 256>>>(q, nq, slots, thr_base);
+        CK(cudaMemset(res, 0, 64));
+        uint64_t nref = N < (1ull << 22) ? N : (1ull << 22) - 5;
+        ref_kernel<<<(unsigned)((nref + 255) / 256), 256>>>(codes, nref, slots, nq, res, res + 1);
+        hamming_mma_kernel<<<sms, kThreads, kSmem>>>(codes, nref, slots, nq, res + 2, res + 3, 0, nullptr);
+        unsigned long long h[4]; CK(cudaMemcpy(h, res, 32, cudaMemcpyDeviceToHost));
+        printf("thr_base %u rows %llu: ref count %llu check %llx | mma count %llu check %llx  %s\n", thr_base, (unsigned long long)nref, h[0], h[1], h[2], h[3],
+               (h[0] == h[2] && h[1] == h[3]) ? "MATCH" : "MISMATCH");
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(a);
+            hamming_mma_kernel<<<sms, kThreads, kSmem>>>(codes, N, slots, nq, res + 2, res + 3, mode, res + 4);
+            cudaEventRecord(b); CK(cudaEventSynchronize(b));
+            float ms; cudaEventElapsedTime(&ms, a, b);
+            double pairs = (double)N * nq;
+            unsigned long long ck[2]; CK(cudaMemcpy(ck, res + 4, 16, cudaMemcpyDeviceToHost));
+            printf("  [SM clock %.0f MHz]", (double)ck[0] / (double)ck[1] * 1e3);
+            printf("  mode %d rows %llu nq %u: %.3f ms  %.2f Tpairs/s  (%.1f queries/s over 1B rows)\n", mode, (unsigned long long)N, nq, ms, pairs / ms * 1e-9, pairs / (ms * 1e-3) / 1e9);
+        }
+    }
+    CK(cudaDeviceSynchronize());
+    return 0;
+}

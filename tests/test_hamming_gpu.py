@@ -81,6 +81,60 @@ def test_duplicate_flood_takes_exact_fallback(ctx):
     assert ctx.last_scan_fallbacks() > 0       # this input must have gone through the exact selection
 
 
+# ---- batches of >= 16 queries run chunks of >= 2^19 rows on the int8 tensor pipe (hamming_mma_scan_kernel) ----------
+@pytest.mark.parametrize("n,nq,k", [(700_001, 16, 10), (1_500_000, 130, 10), (2_000_003, 1024, 10), (1_250_000, 1000, 3),
+                                    (900_000, 1025, 10), (1_100_000, 257, 100)])
+def test_tensor_path_matches_oracle(ctx, n, nq, k):
+    """Ragged query counts (partial 128-query tiles, > 1024 -> two passes) and ragged row counts (odd tails,
+    partial 512-code tiles) through the tensor-core filter: bit-exact ids and distances."""
+    codes = oracle.fill_u64(n, 0xC0DE + n)
+    queries = oracle.fill_u64(nq, 0xBEEF + nq)
+    queries[: min(nq, 8)] = codes[n - 1 - np.arange(min(nq, 8)) * 3]      # exact matches in the last (partial) tile
+    _check(ctx, codes, queries, k)
+    assert ctx.last_scan_fallbacks() == 0
+
+
+def test_tensor_path_extreme_codes_and_distances(ctx):
+    """All-zero / all-one codes and queries: x = +-64 is where the packed accumulator fields alias (dist 0 vs 64)."""
+    n = 1_200_000
+    codes = oracle.fill_u64(n, 5)
+    codes[600_000::1000] = U64(0)
+    codes[600_001::1000] = U64(2**64 - 1)
+    codes[600_002::1000] = U64(0x00000000FFFFFFFF)
+    queries = np.concatenate([np.array([0, 2**64 - 1, 0xFFFFFFFF00000000, 1, 2**63], dtype=U64), oracle.fill_u64(27, 6)])
+    ids = np.arange(n, dtype=U64)[::-1].copy()
+    _check(ctx, codes, queries, 10)
+    _check(ctx, codes, queries, 50, ids=ids)
+
+
+def test_tensor_path_heavy_ties_explicit_ids(ctx):
+    """Thousands of exact ties per query inside the tensor-scanned chunks: the (dist, id) admission rule with
+    permuted explicit ids, and an id_base, must hold at the boundary."""
+    n, nq, k = 1_600_000, 64, 10
+    rng = np.random.default_rng(11)
+    codes = rng.integers(0, 4096, n).astype(U64) << U64(13)
+    queries = rng.integers(0, 4096, nq).astype(U64) << U64(13)
+    for j in range(nq):
+        for d in range(12):
+            mask = U64(0)
+            for b in rng.choice(64, d, replace=False):
+                mask |= U64(1) << U64(int(b))
+            codes[rng.integers(n // 2, n)] = queries[j] ^ mask
+    ids = rng.permutation(n).astype(U64) * U64(7) + U64(1)
+    _check(ctx, codes, queries, k, ids=ids)
+    _check(ctx, codes, queries, k, id_base=2**40)
+
+
+def test_tensor_path_duplicate_flood_falls_back(ctx):
+    n, k = 1_300_000, 10
+    codes = oracle.fill_u64(n, 77)
+    codes[700_000:] = U64(0xFEEDFACECAFEBEEF)                       # 600 K identical rows, ids descending
+    ids = np.arange(n, 0, -1, dtype=U64)
+    queries = np.concatenate([np.array([0xFEEDFACECAFEBEEF, 0xFEEDFACECAFEBEEE], dtype=U64), oracle.fill_u64(30, 78)])
+    _check(ctx, codes, queries, k, ids=ids)
+    assert ctx.last_scan_fallbacks() > 0
+
+
 def test_fewer_rows_than_k_pads_with_sentinels(ctx):
     codes = oracle.fill_u64(5, 9)
     queries = oracle.fill_u64(3, 10)

@@ -16,11 +16,15 @@
 //             survivors compute the true distance and are appended to the query's list
 //             when (dist, id) < (thr, kth_id).
 //   compact   after every chunk (tightens thr); the last one writes the results.
+//   Batches of >= kMmaMinQueries queries run the large chunks on the int8 tensor pipe instead
+//   (hamming_mma_scan_kernel below): the POPC pipe (16 lanes/clk/SM) caps the loop above at ~14
+//   pairs/clk/SM, the tensor-core form filters ~57 pairs/clk/SM; same admission rule, same lists.
 // A list that overflows its capacity (adversarial duplicates with descending ids) is
 // flagged; flagged queries are recomputed by the exact multi-pass selection in
 // topk_select.cuh (histogram of distances + radix select on ids), so the result is
 // exact for every input.
 #include <cooperative_groups.h>
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -30,12 +34,13 @@ namespace ucfp {
 namespace {
 
 #include "topk_select.cuh"
+#include "sm100_ptx.cuh"
 
 constexpr int kScanThreads = 256;
 constexpr int kCodesPerThread = 8;                 // 4 x LDG.128 in flight per thread
 constexpr int kTileCodes = kScanThreads * kCodesPerThread;
 constexpr uint32_t kSeedRows = 2048;               // multiple of 2 (keeps 16-byte alignment of chunk starts)
-constexpr uint32_t kMaxQueriesPerPass = 2048;      // 16 B/query of shared memory
+constexpr uint32_t kMaxQueriesPerPass = 1024;      // POPC scan: 16 B/query of shared memory; tensor scan: 8 resident 128-query tiles
 constexpr uint64_t kMaxChunkRows = 1ULL << 28;
 
 struct __align__(16) QSlot { uint32_t lo, hi, thr, pad; };
@@ -157,6 +162,238 @@ hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restri
     }
 }
 
+// ---- batched scan on the int8 tensor pipe ---------------------------------------------------------
+// A Hamming distance matrix is a binary GEMM.  With bits mapped to +-1 (set -> +1, clear -> -1) the dot product of a
+// query and a code is  x = 64 - 2 * dist.  tcgen05.mma kind::i8 (s8 x s8 -> s32 in TMEM) computes 128 queries x 256
+// operand rows per instruction pair (K = 64 = 2 x 32).  Each operand row carries TWO codes a, b as  -a_k + 64 * b_k
+// (values +-63, +-65 fit s8), so one accumulator is  D = -x_a + 64 * x_b,  |D| <= 4160, and holds both distances:
+//     x_a >= tau   <=>   the low 7 bits of D, read as a signed number, are <= -tau     (x_a = 64 and x_a = -64 alias;
+//                                                                                       the latter is dist 64: a harmless false positive)
+//     x_b >= tau   <=>   D >= 64 * tau - 64                                             (x_a = -64 again the only false positive)
+// with tau = 64 - 2 * thr.  The epilogue never decodes distances: per thread (= one query) it reads 64 accumulators
+// as 32 registers of s16 pairs (tcgen05.ld ... pack::16b), moves each of the four fields of a register to the top of
+// a 32-bit word with a multiply (fma pipe) and keeps a running signed min / max (alu pipe); one vote per 128 codes.
+// Only when a bound is crossed does the warp take the cold path, which settles the candidates exactly from the
+// codes themselves under the same admission rule as hamming_survivors.  Queries stay resident in shared memory as
+// eight 128-row A tiles; codes are expanded to operand rows by four producer warps, two stages ahead of the MMAs.
+constexpr int kMmaQTile = 128;                       // UMMA M: queries per accumulator tile (TMEM lanes)
+constexpr int kMmaRows = 256;                        // UMMA N: operand rows per stage = 512 codes (TMEM columns)
+constexpr int kMmaTileCodes = 2 * kMmaRows;
+constexpr int kMmaRowBytes = 128;                    // one 128B-swizzle row; bytes 0..63 hold the K = 64 elements
+constexpr int kMmaQBytes = kMmaQTile * kMmaRowBytes; // 16 KiB per query tile
+constexpr int kMmaCBytes = kMmaRows * kMmaRowBytes;  // 32 KiB per code stage
+constexpr int kMmaStages = 2;
+constexpr int kMmaExpWarps = 4, kMmaEpiWarps = 16;
+constexpr int kMmaThreads = 32 * (1 + kMmaExpWarps + kMmaEpiWarps);
+constexpr int kMmaColsPerWarp = kMmaRows / (kMmaEpiWarps / 4);
+constexpr uint32_t kMmaMaxQueries = 1024;
+constexpr uint32_t kMmaMinQueries = 16;              // below this the POPC scan is HBM-bound anyway
+constexpr uint64_t kMmaMinChunkRows = 1ULL << 19;    // smaller chunks (loose bounds, many survivors) stay on the POPC scan
+constexpr size_t kMmaSmem = (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes + kMmaStages * kMmaCBytes + kMmaMaxQueries * 4 + 128 + 1024;
+static_assert(kMmaMaxQueries <= kMaxQueriesPerPass || kMaxQueriesPerPass <= kMmaMaxQueries, "");
+static_assert(kMmaColsPerWarp == 64, "one packed tcgen05.ld per warp and accumulator tile");
+
+// 4 bits -> 4 bytes 0/1
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
+// query row: 64 elements +-1 in the first four 16-byte chunks of row r of a 128B-swizzled K-major tile
+__device__ __forceinline__ void mma_store_query_row(unsigned char *tile, uint32_t r, uint32_t lo, uint32_t hi, bool valid) {
+    unsigned char *row = tile + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint32_t h = (c < 2 ? lo : hi) >> ((c & 1) * 16);
+        uint4 w;   // bit set -> 0x01, clear -> 0xFF
+        w.x = ~(spread4(h & 15) * 0xFEu); w.y = ~(spread4((h >> 4) & 15) * 0xFEu);
+        w.z = ~(spread4((h >> 8) & 15) * 0xFEu); w.w = ~(spread4((h >> 12) & 15) * 0xFEu);
+        if (!valid) w = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(row + ((c ^ (r & 7)) << 4)) = w;
+    }
+}
+// operand row of two codes: element k = -a_k + 64 b_k = 0xC1 ^ (abit * 0x7E) ^ (bbit * 0x80)
+__device__ __forceinline__ uint32_t mma_pack4(uint32_t na, uint32_t nb) { return 0xC1C1C1C1u ^ (spread4(na) * 0x7Eu) ^ (spread4(nb) << 7); }
+__device__ __forceinline__ void mma_store_code_row(unsigned char *tile, uint32_t r, uint64_t a, uint64_t b) {
+    unsigned char *row = tile + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint32_t ha = (uint32_t)(a >> (16 * c)) & 0xFFFFu, hb = (uint32_t)(b >> (16 * c)) & 0xFFFFu;
+        uint4 w;
+        w.x = mma_pack4(ha & 15, hb & 15); w.y = mma_pack4((ha >> 4) & 15, (hb >> 4) & 15);
+        w.z = mma_pack4((ha >> 8) & 15, (hb >> 8) & 15); w.w = mma_pack4(ha >> 12, hb >> 12);
+        *reinterpret_cast<uint4 *>(row + ((c ^ (r & 7)) << 4)) = w;
+    }
+}
+
+struct MmaScanArgs {
+    const uint64_t *codes; const uint64_t *ids; uint64_t id_base;
+    uint64_t row0, row_end;                  // rows [row0, row_end), row0 even
+    const QSlot *slots; const uint64_t *kth_id; uint32_t nq;
+    uint64_t *cand; uint32_t *count; uint32_t cap;
+};
+
+// Cold path, called by the WHOLE warp (tcgen05.ld is warp-collective) with no other tcgen05.ld in flight: re-reads
+// 32 accumulators unpacked, marks the columns that can hold an admissible pair and settles those from the codes.
+__device__ __noinline__ void hamming_mma_cold(uint32_t taddr, uint64_t first_row, uint32_t thr, uint32_t q, const MmaScanArgs &A) {
+    uint32_t v[32];
+    tmem_ld32(taddr, v);
+    const int32_t hi_bound = 64 * (63 - 2 * (int32_t)thr);
+    uint32_t mask = 0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const int32_t D = (int32_t)v[c];
+        if (((((uint32_t)D ^ 64u) & 127u) <= 2 * thr) | (D >= hi_bound)) mask |= 1u << c;
+    }
+    if (!mask) return;
+    const QSlot s = A.slots[q];
+    const uint64_t kid = A.kth_id[q];
+    while (mask) {
+        const int c = __ffs(mask) - 1;
+        mask &= mask - 1;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint64_t r = first_row + 2 * c + h;
+            if (r >= A.row_end) continue;
+            const uint64_t code = A.codes[r];
+            const uint32_t d = __popc((uint32_t)code ^ s.lo) + __popc((uint32_t)(code >> 32) ^ s.hi);
+            if (d > thr) continue;
+            const uint64_t id = A.ids ? A.ids[r] : A.id_base + r;
+            if (d < thr || id < kid) {
+                const uint32_t pos = atomicAdd(&A.count[q], 1u);
+                if (pos < A.cap) A.cand[(size_t)q * A.cap + pos] = ((uint64_t)d << 40) | r;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kMmaThreads, 1)
+hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *sQ = smem;                                                          // [8][16 KiB] query tiles
+    unsigned char *sC = smem + (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes;      // [kMmaStages][32 KiB] operand rows
+    uint32_t *s_thr = reinterpret_cast<uint32_t *>(sC + kMmaStages * kMmaCBytes);      // [1024] thr, 0xFFFFFFFF for padding lanes
+    uint64_t *cfull = reinterpret_cast<uint64_t *>(s_thr + kMmaMaxQueries);
+    uint64_t *cempty = cfull + kMmaStages, *tfull = cempty + kMmaStages, *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t q_tiles = (A.nq + kMmaQTile - 1) / kMmaQTile;
+    const uint32_t n_tiles = (uint32_t)((A.row_end - A.row0 + kMmaTileCodes - 1) / kMmaTileCodes);
+
+    for (uint32_t q = threadIdx.x; q < q_tiles * kMmaQTile; q += blockDim.x) {
+        const QSlot s = q < A.nq ? A.slots[q] : QSlot{0, 0, 0, 0};
+        mma_store_query_row(sQ + (q / kMmaQTile) * kMmaQBytes, q % kMmaQTile, s.lo, s.hi, q < A.nq);
+        s_thr[q] = q < A.nq ? s.thr : 0xFFFFFFFFu;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kMmaStages; ++s) { mbar_init(&cfull[s], kMmaExpWarps * 32); mbar_init(&cempty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kMmaEpiWarps); }
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc_512(tmem_slot);   // two accumulator stages of 256 columns
+    fence_proxy_async_smem();                   // the query tiles were written through the generic proxy
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== MMA issuer: D[128 queries x 256 rows] = Q_tile (K-major, 64 x s8) * rows^T, two K = 32 steps =====
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kMmaRows >> 3) << 17) | ((uint32_t)(kMmaQTile >> 4) << 24);
+        uint32_t it = 0, acc_it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t s = it % kMmaStages, ph = (it / kMmaStages) & 1;
+            mbar_wait(&cfull[s], ph);
+            tcgen05_fence_after();
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(sC + s * kMmaCBytes));
+            for (uint32_t mt = 0; mt < q_tiles; ++mt, ++acc_it) {
+                const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                mbar_wait(&tempty[as], aph ^ 1);
+                tcgen05_fence_after();
+                if (lane == 0) {
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(sQ + mt * kMmaQBytes));
+                    umma_i8(tmem_base + as * kMmaRows, adesc, bdesc, idesc, 0u);
+                    umma_i8(tmem_base + as * kMmaRows, adesc + 2, bdesc + 2, idesc, 1u);   // +32 bytes of K
+                    umma_commit(&tfull[as]);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) umma_commit(&cempty[s]);   // frees the operand stage when its MMAs retire
+            __syncwarp();
+        }
+    } else if (warp <= kMmaExpWarps) {
+        // ===== producers: thread t expands operand rows t and t + 128 of a stage (codes 2r, 2r + 1; 16-byte loads) =====
+        const uint32_t t = threadIdx.x - 32;
+        auto load_tile = [&](uint32_t tile, uint64_t (&c)[4]) {
+            const uint64_t base = A.row0 + (uint64_t)tile * kMmaTileCodes;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {   // rows past the end become code 0 and are rejected by the cold path's range check
+                const uint64_t r0 = base + 2 * (t + 128 * j);
+                if (r0 + 1 < A.row_end) {
+                    const uint4 v = ldg_stream_v4(reinterpret_cast<const uint4 *>(A.codes + r0));
+                    c[2 * j] = (uint64_t)v.y << 32 | v.x; c[2 * j + 1] = (uint64_t)v.w << 32 | v.z;
+                } else { c[2 * j] = r0 < A.row_end ? A.codes[r0] : 0; c[2 * j + 1] = 0; }
+            }
+        };
+        uint32_t it = 0;
+        uint64_t cur[4], nxt[4] = {0, 0, 0, 0};
+        if (blockIdx.x < n_tiles) load_tile(blockIdx.x, cur);
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t s = it % kMmaStages, ph = (it / kMmaStages) & 1;
+            if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, nxt);   // next tile's codes fly while this one is expanded
+            mbar_wait(&cempty[s], ph ^ 1);
+            mma_store_code_row(sC + s * kMmaCBytes, t, cur[0], cur[1]);
+            mma_store_code_row(sC + s * kMmaCBytes, t + 128, cur[2], cur[3]);
+            fence_proxy_async_smem();
+            mbar_arrive(&cfull[s]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+        }
+    } else {
+        // ===== epilogue: warp -> TMEM lane quadrant (warp % 4) and 64 of the 256 columns =====
+        const uint32_t quad = warp & 3, part = (warp - 1 - kMmaExpWarps) >> 2;
+        uint32_t acc_it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint64_t first_row = A.row0 + (uint64_t)tile * kMmaTileCodes + 2 * part * kMmaColsPerWarp;
+            for (uint32_t mt = 0; mt < q_tiles; ++mt, ++acc_it) {
+                const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                const uint32_t q = mt * kMmaQTile + quad * 32 + lane;
+                const uint32_t thr = s_thr[q];
+                const bool pad = thr == 0xFFFFFFFFu;
+                const int32_t tau = 64 - 2 * (int32_t)thr;
+                // fields at the top of a 32-bit word, junk below: min over the x fields <= lo_bound, max over the y fields >= hi_bound
+                const int32_t lo_bound = pad ? (int32_t)0x80000000 : (thr >= 64 ? 0x7FFFFFFF : (int32_t)(((uint32_t)(-tau) << 25) | 0x01FFFFFFu));
+                const int32_t hi_bound = pad ? 0x7FFFFFFF : (64 * (tau - 1)) * 65536;
+                mbar_wait(&tfull[as], aph);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * kMmaRows + part * kMmaColsPerWarp;
+                uint32_t p[32];
+                tmem_ld64_pack16_async(taddr, p);
+                tmem_ld_wait(p);
+                int32_t mn[4] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF};
+                int32_t mx[4] = {(int32_t)0x80000000, (int32_t)0x80000000, (int32_t)0x80000000, (int32_t)0x80000000};
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {   // register = (D of column 2c+1) << 16 | (D of column 2c) & 0xFFFF
+                    mx[c & 3] = max(max(mx[c & 3], (int32_t)p[c]), (int32_t)(p[c] * 0x10000u));
+                    mn[c & 3] = min(min(mn[c & 3], (int32_t)(p[c] * 0x200u)), (int32_t)(p[c] * 0x02000000u));
+                }
+                const bool fired = min(min(mn[0], mn[1]), min(mn[2], mn[3])) <= lo_bound || max(max(mx[0], mx[1]), max(mx[2], mx[3])) >= hi_bound;
+                if (__any_sync(0xFFFFFFFFu, fired)) {
+                    const uint32_t thr_c = pad ? 0u : thr;
+                    hamming_mma_cold(taddr, first_row, thr_c, pad ? 0u : q, A);         // padding lanes hold D = 0 everywhere: their
+                    hamming_mma_cold(taddr + 32, first_row + 64, thr_c, pad ? 0u : q, A);  // mask is empty and they return before any access
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[as]);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tcgen05_fence_after();
+        tmem_dealloc_512(tmem_base);
+    }
+}
+
 // exact-selection key for flagged queries: the true distance of one row
 struct HammingKey {
     static constexpr int kKeyBits = 8;
@@ -196,6 +433,8 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
     UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_occ, hamming_scan_kernel, kScanThreads,
                                                                  sizeof(QSlot) * kMaxQueriesPerPass));
     if (scan_occ < 1) scan_occ = 1;
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
+    static const bool env_no_mma = getenv("UCFP_HAMMING_NO_MMA") != nullptr;   // developer switch: POPC scan only
 
     for (size_t q0 = 0; q0 < nq; q0 += kMaxQueriesPerPass) {
         const uint32_t nqp = (uint32_t)((nq - q0 < kMaxQueriesPerPass) ? nq - q0 : kMaxQueriesPerPass);
@@ -227,6 +466,7 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
 
         // small batches are HBM-bound: fewer, larger chunks; large batches tighten thr more often
         const bool streaming = nqp <= 16;   // HBM-bound regime: fewer and larger chunks
+        const bool use_mma = nqp >= kMmaMinQueries && !env_no_mma;
         static const long env_growth = getenv("UCFP_HAMMING_GROWTH") ? atol(getenv("UCFP_HAMMING_GROWTH")) : 0;
         const uint64_t growth = streaming ? 64 : (env_growth > 1 ? (uint64_t)env_growth : 8);
         const uint64_t max_chunk = streaming ? (1ULL << 40) : kMaxChunkRows;
@@ -242,7 +482,13 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
                 if (q_groups > max_groups) q_groups = max_groups;
                 grid = ntiles * q_groups;
             }
-            {
+            if (use_mma && n >= kMmaMinChunkRows) {
+                const uint64_t tiles = (n + kMmaTileCodes - 1) / kMmaTileCodes;
+                const unsigned mma_grid = (unsigned)(tiles < (uint64_t)ctx->sm_count ? tiles : (uint64_t)ctx->sm_count);
+                ProfScope ps(ctx, UCFP_PROF_HAMMING_SCAN, 8.0 * (double)n * nqp);
+                hamming_mma_scan_kernel<<<mma_grid, kMmaThreads, kMmaSmem, st>>>(
+                    MmaScanArgs{codes, ids, c->id_base, pos, pos + n, slots, kth, nqp, cand, count, cap});
+            } else {
                 ProfScope ps(ctx, UCFP_PROF_HAMMING_SCAN, 8.0 * (double)n * nqp);
                 hamming_scan_kernel<<<(unsigned)grid, kScanThreads, sizeof(QSlot) * nqp, st>>>(
                     codes, ids, c->id_base, pos, n, slots, kth, nqp, (uint32_t)q_groups, cand, count, cap);
