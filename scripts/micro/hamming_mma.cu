@@ -7,12 +7,16 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("%s: %s\n",#x,cudaGetErrorString(e)); return 1;}}while(0)
 
 constexpr int kQTile = 128, kCTile = 256, kRowBytes = 128, kStages = 2, kMaxQ = 1024;
 constexpr int kQBytes = kQTile * kRowBytes, kCBytes = kCTile * kRowBytes;
 #ifndef VARIANT
 #define VARIANT 0
+#endif
+#ifndef SPLIT
+#define SPLIT 0
 #endif
 #ifndef EPI_WARPS
 #define EPI_WARPS 8
@@ -103,10 +107,22 @@ __device__ __forceinline__ void store_row(unsigned char *tile, uint32_t r, uint3
 }
 
 struct Tally { unsigned long long count, check; };
+__device__ unsigned long long g_cold_calls;
+// variant 3 cold path: one code per column, D = 64 - 2 dist
+__device__ __noinline__ void hamming_cold1(uint32_t taddr, uint64_t row0, uint64_t nrows, uint32_t thr, uint32_t q, Tally *tally) {
+    uint32_t v[32];
+    tmem_ld32(taddr, v);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const int32_t D = (int32_t)v[c];
+        if (D >= 64 - 2 * (int32_t)thr && row0 + c < nrows) { uint32_t d = (uint32_t)(64 - D) >> 1; tally->count++; tally->check += (row0 + c + 1) * (d + 1) * (q + 1); }
+    }
+}
 // Cold path (the whole warp calls it: tcgen05.ld is warp-collective): re-reads the 32 accumulators of one chunk from TMEM (no other tcgen05.ld may be in flight), decodes which
 // columns can hold an admissible pair and settles those from the codes themselves.
 __device__ __noinline__ void hamming_cold(uint32_t taddr, uint64_t row0, uint64_t nrows, uint32_t thr, uint32_t q,
                                           const uint64_t *__restrict__ codes, const QSlot *__restrict__ slots, Tally *tally) {
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_cold_calls, 1ull);
     uint32_t v[32];
     tmem_ld32(taddr, v);
     uint32_t mask = 0;
@@ -187,10 +203,11 @@ hamming_mma_kernel(const uint64_t *__restrict__ codes, uint64_t nrows, const QSl
     unsigned char *sC = smem + (size_t)(kMaxQ / kQTile) * kQBytes;
     int32_t *s_tau = reinterpret_cast<int32_t *>(sC + kStages * kCBytes);
     uint64_t *cfull = reinterpret_cast<uint64_t *>(s_tau + kMaxQ);
-    uint64_t *cempty = cfull + kStages, *tfull = cempty + kStages, *tempty = tfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint64_t *cempty = cfull + kStages, *tfull = cempty + kStages, *tempty = tfull + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t n_tiles = (uint32_t)((nrows + 2 * kCTile - 1) / (2 * kCTile));   // 2 codes per B row
+    constexpr uint32_t kCodesPerTile = VARIANT == 3 ? kCTile : 2 * kCTile;   // variant 3: one code per B row
+    const uint32_t n_tiles = (uint32_t)((nrows + kCodesPerTile - 1) / kCodesPerTile);
 
     // queries -> resident A tiles; admission bounds D >= 64 - 2 thr
     for (uint32_t q = threadIdx.x; q < q_tiles * kQTile; q += blockDim.x) {
@@ -200,7 +217,7 @@ hamming_mma_kernel(const uint64_t *__restrict__ codes, uint64_t nrows, const QSl
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&cfull[s], kExpWarps * 32); mbar_init(&cempty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpiWarps); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], SPLIT ? kEpiWarps / 2 : kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -222,6 +239,25 @@ hamming_mma_kernel(const uint64_t *__restrict__ codes, uint64_t nrows, const QSl
             mbar_wait(&cfull[s], ph);
             tc_fence_after();
             const uint64_t bdesc = desc_sw128(smem_u32(sC + s * kCBytes));
+#if SPLIT
+            const uint32_t idesc_h = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(kQTile >> 4) << 24);
+            for (uint32_t mt = 0; mt < q_tiles; ++mt)
+                for (uint32_t h = 0; h < 2; ++h, ++acc_it) {
+                    const uint32_t as = acc_it & 3, aph = (acc_it >> 2) & 1;
+                    mbar_wait(&tempty[as], aph ^ 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint64_t adesc = desc_sw128(smem_u32(sQ + mt * kQBytes)), bd = bdesc + h * (16384 >> 4);
+                        umma_i8(tmem_base + as * 128, adesc, bd, idesc_h, 0u);
+                        umma_i8(tmem_base + as * 128, adesc + 2, bd + 2, idesc_h, 1u);
+                        umma_commit(&tfull[as]);
+                    }
+                    __syncwarp();
+                }
+            if (lane == 0) umma_commit(&cempty[s]);
+            __syncwarp();
+            continue;
+#endif
             for (uint32_t mt = 0; mt < q_tiles; ++mt, ++acc_it) {
                 const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
                 mbar_wait(&tempty[as], aph ^ 1);
@@ -243,8 +279,17 @@ hamming_mma_kernel(const uint64_t *__restrict__ codes, uint64_t nrows, const QSl
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-            const uint64_t base = (uint64_t)tile * (2 * kCTile);
+            const uint64_t base = (uint64_t)tile * kCodesPerTile;
             uint64_t c[4];
+            if (VARIANT == 3) {
+                c[0] = base + t < nrows ? codes[base + t] : 0; c[1] = base + 128 + t < nrows ? codes[base + 128 + t] : 0;
+                mbar_wait(&cempty[s], ph ^ 1);
+                store_row(sC + s * kCBytes, t, (uint32_t)c[0], (uint32_t)(c[0] >> 32), base + t < nrows);
+                store_row(sC + s * kCBytes, t + 128, (uint32_t)c[1], (uint32_t)(c[1] >> 32), base + 128 + t < nrows);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&cfull[s]);
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {   // rows t and t + 128 of the stage: codes 2r, 2r + 1 (out of range -> 0, rejected by the cold path)
                 const uint64_t r0 = base + 2 * (t + 128 * j);
@@ -262,6 +307,54 @@ hamming_mma_kernel(const uint64_t *__restrict__ codes, uint64_t nrows, const QSl
         const uint32_t quad = warp & 3, part = (warp - 1 - kExpWarps) >> 2;
         uint32_t acc_it = 0;
         Tally tally{0, 0};
+#if SPLIT
+        {   // two groups of 8 warps take alternate accumulator tiles (128 columns = 256 codes each, 4 TMEM stages)
+            const uint32_t group = part >> 1, sub = part & 1;
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (uint32_t mt = 0; mt < q_tiles; ++mt)
+                    for (uint32_t h = 0; h < 2; ++h, ++acc_it) {
+                        if ((acc_it & 1) != group) continue;
+                        const uint32_t as = acc_it & 3, aph = (acc_it >> 2) & 1;
+                        const uint32_t q = mt * kQTile + quad * 32 + lane;
+                        const int32_t tau = s_tau[q];
+                        const bool pad = tau == 0x7FFFFFFF;
+                        const uint32_t thr = pad ? 0u : (uint32_t)(64 - tau) >> 1;
+                        const uint64_t base = (uint64_t)tile * 512 + h * 256 + sub * 128;
+                        mbar_wait(&tfull[as], aph);
+                        tc_fence_after();
+                        const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * 128 + sub * 64;
+                        uint32_t va[32];
+                        tmem_ld64p_nowait(taddr, va);
+                        tmem_wait(va);
+                        uint32_t hx[4], hn[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { hx[j] = va[j]; hn[j] = va[j] * 512u; }
+#pragma unroll
+                        for (int c = 4; c < 28; c += 8)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                hx[j] = __vimax3_s16x2(hx[j], va[c + j], va[c + 4 + j]);
+                                hn[j] = __vimin3_s16x2(hn[j], va[c + j] * 512u, va[c + 4 + j] * 512u);
+                            }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { hx[j] = __vmaxs2(hx[j], va[28 + j]); hn[j] = __vmins2(hn[j], va[28 + j] * 512u); }
+                        const uint32_t m2 = __vmaxs2(__vimax3_s16x2(hx[0], hx[1], hx[2]), hx[3]);
+                        const uint32_t n2 = __vmins2(__vimin3_s16x2(hn[0], hn[1], hn[2]), hn[3]);
+                        const int32_t hb = 64 * (tau - 1), lb16 = thr >= 64 ? 0x7FFF : (((2 * (int32_t)thr - 64) << 9) | 0x1FF);
+                        const bool f5 = pad ? false : ((int32_t)(int16_t)(m2 & 0xFFFFu) >= hb || ((int32_t)m2 >> 16) >= hb ||
+                                                       (int32_t)(int16_t)(n2 & 0xFFFFu) <= lb16 || ((int32_t)n2 >> 16) <= lb16);
+                        if (__any_sync(0xFFFFFFFFu, f5)) {
+                            hamming_cold(taddr, base, nrows, thr, q, codes, slots, &tally);
+                            hamming_cold(taddr + 32, base + 64, nrows, thr, q, codes, slots, &tally);
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[as]);
+                    }
+        }
+        if (tally.count) { atomicAdd(count, tally.count); atomicAdd(check, tally.check); }
+        goto done;
+#endif
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const uint64_t base = (uint64_t)tile * (2 * kCTile) + 2 * part * kColsPerWarp;
             for (uint32_t mt = 0; mt < q_tiles; ++mt, ++acc_it) {
@@ -280,7 +373,76 @@ hamming_mma_kernel(const uint64_t *__restrict__ codes, uint64_t nrows, const QSl
 #pragma unroll
                     for (uint32_t c0 = 0; c0 < kColsPerWarp; c0 += 64) {
                         int32_t mn[4] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, mx[4] = {(int32_t)0x80000000, (int32_t)0x80000000, (int32_t)0x80000000, (int32_t)0x80000000};
-                        if (VARIANT == 2) {
+                        if (VARIANT == 3) {
+                            uint32_t va[32];
+                            tmem_ld64p_nowait(taddr + c0, va);
+                            tmem_wait(va);
+                            if (mode == 2) { if (max32(va) == 12345) tally.count++; continue; }
+                            __half2 h[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) h[j] = *reinterpret_cast<__half2 *>(&va[j]);
+#pragma unroll
+                            for (int c = 4; c < 32; ++c) h[c & 3] = __hmax2(h[c & 3], *reinterpret_cast<__half2 *>(&va[c]));
+                            const __half2 hm = __hmax2(__hmax2(h[0], h[1]), __hmax2(h[2], h[3]));
+                            const uint32_t m = *reinterpret_cast<const uint32_t *>(&hm);
+                            const bool f3 = pad ? false : (tau <= 0 || (int32_t)(m & 0xFFFFu) >= tau || (int32_t)(m >> 16) >= tau);
+                            if (__any_sync(0xFFFFFFFFu, f3)) {
+                                hamming_cold1(taddr + c0, tile * (uint64_t)kCodesPerTile + part * kColsPerWarp + c0, nrows, pad ? 0 : thr, q, &tally);
+                                hamming_cold1(taddr + c0 + 32, tile * (uint64_t)kCodesPerTile + part * kColsPerWarp + c0 + 32, nrows, pad ? 0 : thr, q, &tally);
+                            }
+                            continue;
+                        } else if (VARIANT == 5) {   // packed pairs, both halves at once with s16x2 min / max
+                            uint32_t va[32];
+                            tmem_ld64p_nowait(taddr + c0, va);
+                            tmem_wait(va);
+                            uint32_t hx[4], hn[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { hx[j] = va[j]; hn[j] = va[j] * 512u; }
+#pragma unroll
+                            for (int c = 4; c < 28; c += 8)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    hx[j] = __vimax3_s16x2(hx[j], va[c + j], va[c + 4 + j]);
+                                    hn[j] = __vimin3_s16x2(hn[j], va[c + j] * 512u, va[c + 4 + j] * 512u);
+                                }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { hx[j] = __vimax3_s16x2(hx[j], va[28 + j], va[28 + j]); hn[j] = __vimin3_s16x2(hn[j], va[28 + j] * 512u, va[28 + j] * 512u); }
+                            const uint32_t m2 = __vimax3_s16x2(__vimax3_s16x2(hx[0], hx[1], hx[2]), hx[3], hx[3]);
+                            const uint32_t n2 = __vimin3_s16x2(__vimin3_s16x2(hn[0], hn[1], hn[2]), hn[3], hn[3]);
+                            const int32_t hb = 64 * (tau - 1), lb16 = thr >= 64 ? 0x7FFF : (((2 * (int32_t)thr - 64) << 9) | 0x1FF);
+                            const bool f5 = pad ? false : ((int32_t)(int16_t)(m2 & 0xFFFFu) >= hb || ((int32_t)m2 >> 16) >= hb ||
+                                                           (int32_t)(int16_t)(n2 & 0xFFFFu) <= lb16 || ((int32_t)n2 >> 16) <= lb16);
+#ifdef DEBUG_V5
+                            if (f5 && atomicAdd(&g_cold_calls, 0ull) < 3) printf("q %u thr %u tau %d hb %d lb16 %d m2 %08x n2 %08x va0 %08x va1 %08x hx %08x %08x %08x %08x hn %08x %08x %08x %08x\n", q, thr, tau, hb, lb16, m2, n2, va[0], va[1], hx[0], hx[1], hx[2], hx[3], hn[0], hn[1], hn[2], hn[3]);
+#endif
+                            if (__any_sync(0xFFFFFFFFu, f5)) {
+                                hamming_cold(taddr + c0, base + 2 * c0, nrows, thr, q, codes, slots, &tally);
+                                hamming_cold(taddr + c0 + 32, base + 2 * c0 + 64, nrows, thr, q, codes, slots, &tally);
+                            }
+                            continue;
+                        } else if (VARIANT == 4) {   // packed pairs: y fields by half2 max on the raw s16 patterns, x fields by shifted s32 min
+                            uint32_t va[32];
+                            tmem_ld64p_nowait(taddr + c0, va);
+                            tmem_wait(va);
+                            __half2 h[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { h[j] = *reinterpret_cast<__half2 *>(&va[j]); mn[j] = min((int32_t)(va[j] * 0x200u), (int32_t)(va[j] * 0x02000000u)); }
+#pragma unroll
+                            for (int c = 4; c < 32; ++c) {
+                                h[c & 3] = __hmax2(h[c & 3], *reinterpret_cast<__half2 *>(&va[c]));
+                                mn[c & 3] = min(min(mn[c & 3], (int32_t)(va[c] * 0x200u)), (int32_t)(va[c] * 0x02000000u));
+                            }
+                            const __half2 hm = __hmax2(__hmax2(h[0], h[1]), __hmax2(h[2], h[3]));
+                            const uint32_t m = *reinterpret_cast<const uint32_t *>(&hm);
+                            const int32_t hb = 64 * (tau - 1);   // > 0 when thr <= 30
+                            const bool f4 = pad ? false : (hb <= 0 || (int32_t)(int16_t)(m & 0xFFFFu) >= hb || ((int32_t)m >> 16) >= hb ||
+                                                           min(min(mn[0], mn[1]), min(mn[2], mn[3])) <= lo_bound);
+                            if (__any_sync(0xFFFFFFFFu, f4)) {
+                                hamming_cold(taddr + c0, base + 2 * c0, nrows, thr, q, codes, slots, &tally);
+                                hamming_cold(taddr + c0 + 32, base + 2 * c0 + 64, nrows, thr, q, codes, slots, &tally);
+                            }
+                            continue;
+                        } else if (VARIANT == 2) {
                             uint32_t va[32];
                             tmem_ld64p_nowait(taddr + c0, va);
                             tmem_wait(va);
@@ -309,6 +471,9 @@ hamming_mma_kernel(const uint64_t *__restrict__ codes, uint64_t nrows, const QSl
         }
         if (tally.count) { atomicAdd(count, tally.count); atomicAdd(check, tally.check); }
     }
+#if SPLIT
+done:
+#endif
     if (blockIdx.x == 0 && threadIdx.x == 0 && clk) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); clk[0] = clock64() - clk_c0; clk[1] = t1 - clk_t0; }
     tc_fence_before();
     __syncthreads();
@@ -363,7 +528,8 @@ int main(int argc, char **argv) {
             float ms; cudaEventElapsedTime(&ms, a, b);
             double pairs = (double)N * nq;
             unsigned long long ck[2]; CK(cudaMemcpy(ck, res + 4, 16, cudaMemcpyDeviceToHost));
-            printf("  [SM clock %.0f MHz]", (double)ck[0] / (double)ck[1] * 1e3);
+            unsigned long long cc; cudaMemcpyFromSymbol(&cc, g_cold_calls, 8); unsigned long long z = 0; cudaMemcpyToSymbol(g_cold_calls, &z, 8);
+            printf("  [SM clock %.0f MHz, cold calls %llu]", (double)ck[0] / (double)ck[1] * 1e3, cc);
             printf("  mode %d rows %llu nq %u: %.3f ms  %.2f Tpairs/s  (%.1f queries/s over 1B rows)\n", mode, (unsigned long long)N, nq, ms, pairs / ms * 1e-9, pairs / (ms * 1e-3) / 1e9);
         }
     }

@@ -171,8 +171,9 @@ hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restri
 //                                                                                       the latter is dist 64: a harmless false positive)
 //     x_b >= tau   <=>   D >= 64 * tau - 64                                             (x_a = -64 again the only false positive)
 // with tau = 64 - 2 * thr.  The epilogue never decodes distances: per thread (= one query) it reads 64 accumulators
-// as 32 registers of s16 pairs (tcgen05.ld ... pack::16b), moves each of the four fields of a register to the top of
-// a 32-bit word with a multiply (fma pipe) and keeps a running signed min / max (alu pipe); one vote per 128 codes.
+// as 32 registers of s16 pairs (tcgen05.ld ... pack::16b) and keeps a per-halfword signed max of D (the x_b test) and
+// min of D * 512 (x_a's 7 bits at the top of each halfword) with VIMNMX3.S16x2: 1 multiply + 1 min/max lane-op per
+// register = per four (query, code) pairs; one vote per 128 codes.
 // Only when a bound is crossed does the warp take the cold path, which settles the candidates exactly from the
 // codes themselves under the same admission rule as hamming_survivors.  Queries stay resident in shared memory as
 // eight 128-row A tiles; codes are expanded to operand rows by four producer warps, two stages ahead of the MMAs.
@@ -187,7 +188,7 @@ constexpr int kMmaExpWarps = 4, kMmaEpiWarps = 16;
 constexpr int kMmaThreads = 32 * (1 + kMmaExpWarps + kMmaEpiWarps);
 constexpr int kMmaColsPerWarp = kMmaRows / (kMmaEpiWarps / 4);
 constexpr uint32_t kMmaMaxQueries = 1024;
-constexpr uint32_t kMmaMinQueries = 16;              // below this the POPC scan is HBM-bound anyway
+constexpr uint32_t kMmaMinQueries = 64;              // measured crossover: the POPC scan costs 0.24 ms per query and 1 B rows, the tensor scan >= 15 ms per batch
 constexpr uint64_t kMmaMinChunkRows = 1ULL << 19;    // smaller chunks (loose bounds, many survivors) stay on the POPC scan
 constexpr size_t kMmaSmem = (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes + kMmaStages * kMmaCBytes + kMmaMaxQueries * 4 + 128 + 1024;
 static_assert(kMmaMaxQueries <= kMaxQueriesPerPass || kMaxQueriesPerPass <= kMmaMaxQueries, "");
@@ -300,12 +301,12 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
         uint32_t it = 0, acc_it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t s = it % kMmaStages, ph = (it / kMmaStages) & 1;
-            mbar_wait(&cfull[s], ph);
+            mbar_wait_sleep(&cfull[s], ph);
             tcgen05_fence_after();
             const uint64_t bdesc = umma_desc_sw128(smem_u32(sC + s * kMmaCBytes));
             for (uint32_t mt = 0; mt < q_tiles; ++mt, ++acc_it) {
                 const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-                mbar_wait(&tempty[as], aph ^ 1);
+                mbar_wait_sleep(&tempty[as], aph ^ 1);
                 tcgen05_fence_after();
                 if (lane == 0) {
                     const uint64_t adesc = umma_desc_sw128(smem_u32(sQ + mt * kMmaQBytes));
@@ -338,7 +339,7 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t s = it % kMmaStages, ph = (it / kMmaStages) & 1;
             if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, nxt);   // next tile's codes fly while this one is expanded
-            mbar_wait(&cempty[s], ph ^ 1);
+            mbar_wait_sleep(&cempty[s], ph ^ 1);
             mma_store_code_row(sC + s * kMmaCBytes, t, cur[0], cur[1]);
             mma_store_code_row(sC + s * kMmaCBytes, t + 128, cur[2], cur[3]);
             fence_proxy_async_smem();
@@ -358,23 +359,32 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
                 const uint32_t thr = s_thr[q];
                 const bool pad = thr == 0xFFFFFFFFu;
                 const int32_t tau = 64 - 2 * (int32_t)thr;
-                // fields at the top of a 32-bit word, junk below: min over the x fields <= lo_bound, max over the y fields >= hi_bound
-                const int32_t lo_bound = pad ? (int32_t)0x80000000 : (thr >= 64 ? 0x7FFFFFFF : (int32_t)(((uint32_t)(-tau) << 25) | 0x01FFFFFFu));
-                const int32_t hi_bound = pad ? 0x7FFFFFFF : (64 * (tau - 1)) * 65536;
-                mbar_wait(&tfull[as], aph);
+                // s16 bounds for the two fields of a 16-bit accumulator image: y = the value itself, x = its low 7 bits moved to the top
+                // of the halfword by * 512 (the upper halfword then carries < 512 of junk from the lower one, hence the | 0x1FF)
+                const int32_t hi16 = pad ? 0x7FFF : 64 * (tau - 1);
+                const int32_t lo16 = pad ? -0x8000 : (thr >= 64 ? 0x7FFF : ((-tau * 512) | 0x1FF));
+                mbar_wait_sleep(&tfull[as], aph);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * kMmaRows + part * kMmaColsPerWarp;
-                uint32_t p[32];
+                uint32_t p[32];   // register c = (D of column 2c+1) << 16 | (D of column 2c) & 0xFFFF
                 tmem_ld64_pack16_async(taddr, p);
                 tmem_ld_wait(p);
-                int32_t mn[4] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF};
-                int32_t mx[4] = {(int32_t)0x80000000, (int32_t)0x80000000, (int32_t)0x80000000, (int32_t)0x80000000};
+                uint32_t mx[4], mn[4];   // per-halfword signed max of D, min of D << 9 (VIMNMX3.S16x2: two columns per lane-op)
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {   // register = (D of column 2c+1) << 16 | (D of column 2c) & 0xFFFF
-                    mx[c & 3] = max(max(mx[c & 3], (int32_t)p[c]), (int32_t)(p[c] * 0x10000u));
-                    mn[c & 3] = min(min(mn[c & 3], (int32_t)(p[c] * 0x200u)), (int32_t)(p[c] * 0x02000000u));
-                }
-                const bool fired = min(min(mn[0], mn[1]), min(mn[2], mn[3])) <= lo_bound || max(max(mx[0], mx[1]), max(mx[2], mx[3])) >= hi_bound;
+                for (int j = 0; j < 4; ++j) { mx[j] = p[j]; mn[j] = p[j] * 512u; }
+#pragma unroll
+                for (int c = 4; c < 28; c += 8)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        mx[j] = __vimax3_s16x2(mx[j], p[c + j], p[c + 4 + j]);
+                        mn[j] = __vimin3_s16x2(mn[j], p[c + j] * 512u, p[c + 4 + j] * 512u);
+                    }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { mx[j] = __vmaxs2(mx[j], p[28 + j]); mn[j] = __vmins2(mn[j], p[28 + j] * 512u); }
+                const uint32_t m2 = __vmaxs2(__vimax3_s16x2(mx[0], mx[1], mx[2]), mx[3]);
+                const uint32_t n2 = __vmins2(__vimin3_s16x2(mn[0], mn[1], mn[2]), mn[3]);
+                const bool fired = (int32_t)(int16_t)(m2 & 0xFFFFu) >= hi16 || ((int32_t)m2 >> 16) >= hi16 ||
+                                   (int32_t)(int16_t)(n2 & 0xFFFFu) <= lo16 || ((int32_t)n2 >> 16) <= lo16;
                 if (__any_sync(0xFFFFFFFFu, fired)) {
                     const uint32_t thr_c = pad ? 0u : thr;
                     hamming_mma_cold(taddr, first_row, thr_c, pad ? 0u : q, A);         // padding lanes hold D = 0 everywhere: their
