@@ -174,8 +174,8 @@ hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restri
 // as 32 registers of s16 pairs (tcgen05.ld ... pack::16b) and keeps a per-halfword signed max of D (the x_b test) and
 // min of D * 512 (x_a's 7 bits at the top of each halfword) with VIMNMX3.S16x2: 1 multiply + 1 min/max lane-op per
 // register = per four (query, code) pairs; one vote per 128 codes.
-// Only when a bound is crossed does the warp take the cold path, which settles the candidates exactly from the
-// codes themselves under the same admission rule as hamming_survivors.  Queries stay resident in shared memory as
+// Only when a bound is crossed does that lane take the cold path, which decodes the distances from its registers and
+// applies the same admission rule as hamming_survivors.  Queries stay resident in shared memory as
 // eight 128-row A tiles; codes are expanded to operand rows by four producer warps, two stages ahead of the MMAs.
 constexpr int kMmaQTile = 128;                       // UMMA M: queries per accumulator tile (TMEM lanes)
 constexpr int kMmaRows = 256;                        // UMMA N: operand rows per stage = 512 codes (TMEM columns)
@@ -190,7 +190,7 @@ constexpr int kMmaColsPerWarp = kMmaRows / (kMmaEpiWarps / 4);
 constexpr uint32_t kMmaMaxQueries = 1024;
 constexpr uint32_t kMmaMinQueries = 64;              // measured crossover: the POPC scan costs 0.24 ms per query and 1 B rows, the tensor scan >= 15 ms per batch
 constexpr uint64_t kMmaMinChunkRows = 1ULL << 19;    // smaller chunks (loose bounds, many survivors) stay on the POPC scan
-constexpr size_t kMmaSmem = (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes + kMmaStages * kMmaCBytes + kMmaMaxQueries * 4 + 128 + 1024;
+constexpr size_t kMmaSmem = (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes + kMmaStages * kMmaCBytes + kMmaMaxQueries * (16 + 8 + 4) + 128 + 1024;
 static_assert(kMmaMaxQueries <= kMaxQueriesPerPass || kMaxQueriesPerPass <= kMmaMaxQueries, "");
 static_assert(kMmaColsPerWarp == 64, "one packed tcgen05.ld per warp and accumulator tile");
 
@@ -230,35 +230,54 @@ struct MmaScanArgs {
     uint64_t *cand; uint32_t *count; uint32_t cap;
 };
 
-// Cold path, called by the WHOLE warp (tcgen05.ld is warp-collective) with no other tcgen05.ld in flight: re-reads
-// 32 accumulators unpacked, marks the columns that can hold an admissible pair and settles those from the codes.
-__device__ __noinline__ void hamming_mma_cold(uint32_t taddr, uint64_t first_row, uint32_t thr, uint32_t q, const MmaScanArgs &A) {
-    uint32_t v[32];
-    tmem_ld32(taddr, v);
-    const int32_t hi_bound = 64 * (63 - 2 * (int32_t)thr);
-    uint32_t mask = 0;
+// Cold path of one lane (= one query) whose bounds were crossed somewhere in its 64 accumulators.  It runs AFTER the warp
+// has handed the TMEM stage back, from the packed register image alone (|D| <= 4160 fits the 16 bits that were loaded),
+// so a fire delays one warp, not the CTA's MMA pipeline.  Nothing waits on global memory except the list append: query
+// slots and k-th ids sit in shared memory and both distances are decoded from D = -x_a + 64 x_b  (u = 64 - x_a is D's
+// low 7 bits ^ 64; x_b = (D + x_a) / 64).  Only u == 0, where x_a = 64 and -64 alias, reads the two codes.
+__device__ __forceinline__ void hamming_mma_settle(const uint32_t (&p)[32], uint64_t first_row, uint32_t thr_hot, uint32_t q,
+                                                   const MmaScanArgs &A, const uint4 *s_q, const uint64_t *s_kid) {
+    const int32_t hi_bound = 64 * (63 - 2 * (int32_t)thr_hot);
+    uint32_t m_even = 0, m_odd = 0;   // bit c: column 2c / 2c + 1 can hold an admissible pair
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
-        const int32_t D = (int32_t)v[c];
-        if (((((uint32_t)D ^ 64u) & 127u) <= 2 * thr) | (D >= hi_bound)) mask |= 1u << c;
+        const int32_t de = (int32_t)(int16_t)(p[c] & 0xFFFFu), dq = (int32_t)p[c] >> 16;
+        if (((((uint32_t)de ^ 64u) & 127u) <= 2 * thr_hot) | (de >= hi_bound)) m_even |= 1u << c;
+        if (((((uint32_t)dq ^ 64u) & 127u) <= 2 * thr_hot) | (dq >= hi_bound)) m_odd |= 1u << c;
     }
-    if (!mask) return;
-    const QSlot s = A.slots[q];
-    const uint64_t kid = A.kth_id[q];
-    while (mask) {
-        const int c = __ffs(mask) - 1;
-        mask &= mask - 1;
+    const uint4 s = s_q[q];          // {lo, hi, thr, -}
+    const uint32_t thr = s.z;
+    const uint64_t kid = s_kid[q];
+    while (m_even | m_odd) {
+        const bool odd = m_even == 0;
+        uint32_t &m = odd ? m_odd : m_even;
+        const int c = __ffs(m) - 1;
+        m &= m - 1;
+        uint32_t reg = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) reg = (c == j) ? p[j] : reg;   // register select: no local-memory copy of p[]
+        const int32_t D = odd ? (int32_t)reg >> 16 : (int32_t)(int16_t)(reg & 0xFFFFu);
+        const uint64_t r0 = first_row + 2 * (2 * c + (odd ? 1 : 0));
+        const uint32_t u = ((uint32_t)D ^ 64u) & 127u;
+        uint32_t d[2];
+        if (u != 0) {
+            const int32_t xa = 64 - (int32_t)u, xb = (D + xa) >> 6;
+            d[0] = u >> 1; d[1] = (uint32_t)(64 - xb) >> 1;
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint64_t code = r0 + h < A.row_end ? A.codes[r0 + h] : 0;
+                d[h] = __popc((uint32_t)code ^ s.x) + __popc((uint32_t)(code >> 32) ^ s.y);
+            }
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const uint64_t r = first_row + 2 * c + h;
-            if (r >= A.row_end) continue;
-            const uint64_t code = A.codes[r];
-            const uint32_t d = __popc((uint32_t)code ^ s.lo) + __popc((uint32_t)(code >> 32) ^ s.hi);
-            if (d > thr) continue;
-            const uint64_t id = A.ids ? A.ids[r] : A.id_base + r;
-            if (d < thr || id < kid) {
+            const uint64_t r = r0 + h;
+            if (r >= A.row_end || d[h] > thr) continue;
+            const uint64_t id = A.ids ? (d[h] == thr ? A.ids[r] : 0) : A.id_base + r;
+            if (d[h] < thr || id < kid) {
                 const uint32_t pos = atomicAdd(&A.count[q], 1u);
-                if (pos < A.cap) A.cand[(size_t)q * A.cap + pos] = ((uint64_t)d << 40) | r;
+                if (pos < A.cap) A.cand[(size_t)q * A.cap + pos] = ((uint64_t)d[h] << 40) | r;
             }
         }
     }
@@ -270,7 +289,9 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *sQ = smem;                                                          // [8][16 KiB] query tiles
     unsigned char *sC = smem + (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes;      // [kMmaStages][32 KiB] operand rows
-    uint32_t *s_thr = reinterpret_cast<uint32_t *>(sC + kMmaStages * kMmaCBytes);      // [1024] thr, 0xFFFFFFFF for padding lanes
+    uint4 *s_q = reinterpret_cast<uint4 *>(sC + kMmaStages * kMmaCBytes);              // [1024] query slots {lo, hi, thr, -}
+    uint64_t *s_kid = reinterpret_cast<uint64_t *>(s_q + kMmaMaxQueries);              // [1024] id of the current k-th result
+    uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_kid + kMmaMaxQueries);            // [1024] bound of the hot test, 0xFFFFFFFF = never
     uint64_t *cfull = reinterpret_cast<uint64_t *>(s_thr + kMmaMaxQueries);
     uint64_t *cempty = cfull + kMmaStages, *tfull = cempty + kMmaStages, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
@@ -281,7 +302,14 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
     for (uint32_t q = threadIdx.x; q < q_tiles * kMmaQTile; q += blockDim.x) {
         const QSlot s = q < A.nq ? A.slots[q] : QSlot{0, 0, 0, 0};
         mma_store_query_row(sQ + (q / kMmaQTile) * kMmaQBytes, q % kMmaQTile, s.lo, s.hi, q < A.nq);
-        s_thr[q] = q < A.nq ? s.thr : 0xFFFFFFFFu;
+        const uint64_t kid = q < A.nq ? A.kth_id[q] : 0;
+        s_q[q] = make_uint4(s.lo, s.hi, s.thr, 0);
+        s_kid[q] = kid;
+        // Implicit ids grow with the row index and the k-th result is an earlier row, so a tie at distance thr can never be
+        // admitted: the hot test may use thr - 1 (about 4x fewer trips through the cold path).
+        uint32_t hot = s.thr;
+        if (A.ids == nullptr && kid != UINT64_MAX) hot = s.thr == 0 ? 0xFFFFFFFFu : s.thr - 1;
+        s_thr[q] = q < A.nq ? hot : 0xFFFFFFFFu;
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMmaStages; ++s) { mbar_init(&cfull[s], kMmaExpWarps * 32); mbar_init(&cempty[s], 1); }
@@ -385,14 +413,10 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
                 const uint32_t n2 = __vmins2(__vimin3_s16x2(mn[0], mn[1], mn[2]), mn[3]);
                 const bool fired = (int32_t)(int16_t)(m2 & 0xFFFFu) >= hi16 || ((int32_t)m2 >> 16) >= hi16 ||
                                    (int32_t)(int16_t)(n2 & 0xFFFFu) <= lo16 || ((int32_t)n2 >> 16) <= lo16;
-                if (__any_sync(0xFFFFFFFFu, fired)) {
-                    const uint32_t thr_c = pad ? 0u : thr;
-                    hamming_mma_cold(taddr, first_row, thr_c, pad ? 0u : q, A);         // padding lanes hold D = 0 everywhere: their
-                    hamming_mma_cold(taddr + 32, first_row + 64, thr_c, pad ? 0u : q, A);  // mask is empty and they return before any access
-                }
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[as]);
+                if (lane == 0) mbar_arrive(&tempty[as]);   // the accumulators now live in registers: release the stage first
+                if (fired) hamming_mma_settle(p, first_row, pad ? 0u : thr, q, A, s_q, s_kid);
             }
         }
     }
