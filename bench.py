@@ -12,8 +12,10 @@ slice, NCCL all-gathers the per-rank top-k candidates and every rank runs the sa
 
 One JSON line on stdout (rank 0).  `value` = queries/s with queries and results resident in HBM;
 `e2e` = the same through the C ABI with pinned HOST query/result buffers (H2D + D2H inside the timed
-region); `roofline` = the dominant kernel (hamming_scan_kernel) timed live with CUDA events inside the
-library; `cpu_baseline` = the CPU oracle on this box's host cores on a bounded sample.
+region); `roofline` = the dominant kernel (hamming_mma_scan_kernel, the int8 tensor-core form of the scan
+that batches of >= 64 queries use) timed live with CUDA events inside the library, with the HBM-bound
+one-query-per-pass regime of hamming_scan_kernel beside it (`streaming`); `cpu_baseline` = the CPU oracle
+on this box's host cores on a bounded sample.
 """
 from __future__ import annotations
 
@@ -254,6 +256,7 @@ def main() -> int:
     with ClockSampler(local_rank) as clocks:
         ctx.profile_begin()
         total_ms = timed(step_device, args.steps)
+        t_ms, t_ops, t_n = ctx.profile_read(_ffi.PROF_HAMMING_TENSOR)
         k_ms, k_bytes, k_n = ctx.profile_end(_ffi.PROF_HAMMING_SCAN)
     launches = ctx.kernel_launches - launches0
     lt = torch.tensor([launches], dtype=torch.int64, device=dev)
@@ -287,9 +290,12 @@ def main() -> int:
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        mp = json.load(open(peaks_path))
+        peak, peak_src = mp["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        bf16_peak, bf16_src = mp.get("bf16_tflops_sustained", mp["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        bf16_peak, bf16_src = 1400.0, "fallback (B200_PROFILING.md, sustained)"
     for v in streaming.values():
         v["frac_of_hbm_peak"] = v["call_GBps"] / peak
 
@@ -343,8 +349,33 @@ def main() -> int:
     achieved = k_bytes / (k_ms / 1e3) / 1e9 if k_ms else None
     traffic_path = os.path.join(ROOT, "profiles", "hamming_scan_traffic.json")
     # ncu-measured DRAM bytes per scanned row (profiles/), scaled to this run's rows per launch
-    traffic = (json.load(open(traffic_path))["dram_bytes_per_row"] * shard * args.steps / k_n
-               if os.path.exists(traffic_path) and k_n else None)
+    n_launch = t_n if t_n else k_n
+    traffic = (json.load(open(traffic_path))["dram_bytes_per_row"] * shard * args.steps / n_launch
+               if os.path.exists(traffic_path) and n_launch else None)
+
+    # Dominant kernel of the step.  A >= 64-query batch runs on the int8 tensor pipe: achieved = int8 operations the
+    # tensor pipe executes (64 per (query, code) pair -- one 64-element +-1 dot product per TWO pairs) / kernel time.
+    # MEASURED_PEAKS.json has no int8 figure; int8 issues at twice the bf16 rate, so peak = 2 x the measured bf16 peak.
+    pairs = nq * float(shard) * args.steps
+    if t_n:
+        tops = t_ops / (t_ms / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "hamming_mma_scan_kernel", "achieved": tops, "peak": 2 * bf16_peak,
+                    "unit": "TFLOP/s", "frac": tops / (2 * bf16_peak), "traffic": traffic,
+                    "peak_source": "2 x " + bf16_src + ": int8 tcgen05.mma issues at twice the bf16 rate; no int8 figure is measured",
+                    "launches": t_n, "kernel_ms_per_step": t_ms / args.steps,
+                    "pairs_per_s": (t_ops / 64.0) / (t_ms / 1e3),
+                    "all_scan_launches": {"launches": k_n, "kernel_ms_per_step": k_ms / args.steps,
+                                          "pairs_per_s": pairs / (k_ms / 1e3) if k_ms else None},
+                    "note": "achieved counts int8 operations (TOP/s) EXECUTED by the tensor pipe; the textbook binary-GEMM count "
+                            "is 128 per pair, twice this.  The bound in force is the epilogue (tcgen05.ld + s16x2 min/max on the "
+                            "ALU pipe), see DESIGN.md 4.1; HBM traffic is 8 B per row per 1024-query batch (`traffic`).  "
+                            "`streaming` is hamming_scan_kernel with 1-2 queries per corpus pass, where HBM is the bound",
+                    "streaming": streaming}
+    else:
+        roofline = {"bound": "hbm", "kernel": "hamming_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src, "launches": k_n,
+                    "kernel_ms_per_step": k_ms / args.steps, "pairs_per_s": pairs / (k_ms / 1e3) if k_ms else None,
+                    "note": "algorithmic bytes = 8 B x rows x queries per launch", "streaming": streaming}
 
     if rank == 0:
         cb = None
@@ -360,15 +391,7 @@ def main() -> int:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nq * 8, "d2h_bytes_per_step": nq * K * 12,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(lt.item()),
-            "roofline": {"bound": "hbm", "kernel": "hamming_scan_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic,
-                         "peak_source": peak_src, "launches": k_n, "kernel_ms_per_step": k_ms / args.steps,
-                         "note": "algorithmic bytes = 8 B x rows x queries per launch; one DRAM pass serves the whole "
-                                 "query batch, so the batched figure exceeds the DRAM peak by design (the POPC pipe is "
-                                 "the bound in force); `streaming` is the same kernel with 1-2 queries per pass, where "
-                                 "HBM is the bound",
-                         "pairs_per_s": nq * float(shard) * args.steps / (k_ms / 1e3) if k_ms else None,
-                         "streaming": streaming},
+            "roofline": roofline,
             "clocks": clocks.summary(),
             "secondary": secondary,
             "config2": config2,

@@ -86,11 +86,17 @@ UCFP_API uint64_t ucfp_ctx_kernel_launches(const ucfp_ctx *ctx);
  * its dominant kernels with CUDA events on the context's stream.  _end synchronises and returns, for
  * one kernel class, the summed device time, the summed ALGORITHMIC bytes (Hamming: 8 B x rows x queries
  * of each launch; Jaccard: 1024 B x rows x queries; image: 3*w*h + 408 B per image) or flops (cosine:
- * 2 x rows x dim x queries) and the number of launches. */
-enum { UCFP_PROF_HAMMING_SCAN = 1, UCFP_PROF_JACCARD_SCAN = 2, UCFP_PROF_COSINE_SCAN = 3, UCFP_PROF_IMAGE_HASH = 4 };
+ * 2 x rows x dim x queries) and the number of launches.  UCFP_PROF_HAMMING_SCAN covers every scan launch of a
+ * Hamming call; UCFP_PROF_HAMMING_TENSOR only the launches of the tensor-core scan (batches >= 64 queries), with
+ * units = int8 operations the tensor pipe executes: 64 per (query, code) pair (one 64-element +-1 dot product per
+ * TWO pairs, two codes being packed into one operand row).  _read returns the sums without ending the region. */
+enum { UCFP_PROF_HAMMING_SCAN = 1, UCFP_PROF_JACCARD_SCAN = 2, UCFP_PROF_COSINE_SCAN = 3, UCFP_PROF_IMAGE_HASH = 4,
+       UCFP_PROF_HAMMING_TENSOR = 5 };
 UCFP_API int ucfp_ctx_profile_begin(ucfp_ctx *ctx);
 UCFP_API int ucfp_ctx_profile_end(ucfp_ctx *ctx, int kernel_class, double *kernel_ms, double *alg_units,
                                   uint64_t *launches);
+UCFP_API int ucfp_ctx_profile_read(ucfp_ctx *ctx, int kernel_class, double *kernel_ms, double *alg_units,
+                                   uint64_t *launches);
 
 /* ---- image hashing seam ---------------------------------------------------
  * Replaces the calls into imgfprint at src/modality/image.rs:68-70 and

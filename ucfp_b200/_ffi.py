@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libucfp_cuda.so")
 OK, E_INVALID, E_CUDA, E_OOM, E_UNSUPPORTED, E_STATE, E_CAPACITY = 0, -1, -2, -3, -4, -5, -6
 KIND_HAMMING64, KIND_MINHASH128, KIND_COSINE = 1, 2, 3
 ALGO_AHASH, ALGO_PHASH, ALGO_DHASH, ALGO_MULTI = 1, 2, 4, 7
-PROF_HAMMING_SCAN, PROF_JACCARD_SCAN, PROF_COSINE_SCAN, PROF_IMAGE_HASH = 1, 2, 3, 4
+PROF_HAMMING_SCAN, PROF_JACCARD_SCAN, PROF_COSINE_SCAN, PROF_IMAGE_HASH, PROF_HAMMING_TENSOR = 1, 2, 3, 4, 5
 ID_NONE = 2**64 - 1
 
 _CODE_NAMES = {E_INVALID: "UCFP_E_INVALID", E_CUDA: "UCFP_E_CUDA", E_OOM: "UCFP_E_OOM",
@@ -48,6 +48,7 @@ PROTOTYPES = {
     "ucfp_ctx_kernel_launches": (_u64, [_vp]),
     "ucfp_ctx_profile_begin": (_int, [_vp]),
     "ucfp_ctx_profile_end": (_int, [_vp, _int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_u64)]),
+    "ucfp_ctx_profile_read": (_int, [_vp, _int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_u64)]),
     "ucfp_image_hash_batch": (_int, [_vp, C.POINTER(ImageDesc), _sz, _u32, _vp, _vp]),
     "ucfp_image_hash_uniform": (_int, [_vp, _vp, _sz, _u32, _u32, _u64, _u64, _u32, _vp]),
     "ucfp_corpus_create": (_int, [_vp, _int, _u32, _u64, C.POINTER(_vp)]),

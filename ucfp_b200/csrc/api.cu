@@ -151,6 +151,22 @@ int ucfp_ctx_profile_begin(ucfp_ctx *ctx) {
     return UCFP_OK;
 }
 
+int ucfp_ctx_profile_read(ucfp_ctx *ctx, int kernel_class, double *kernel_ms, double *alg_units, uint64_t *launches) {
+    UCFP_GUARD(ctx);
+    UCFP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    double ms = 0, units = 0; uint64_t n = 0;
+    for (auto &r : ctx->prof) {
+        if (r.kind != kernel_class) continue;
+        float t = 0;
+        UCFP_CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
+        ms += t; units += r.units; n++;
+    }
+    if (kernel_ms) *kernel_ms = ms;
+    if (alg_units) *alg_units = units;
+    if (launches) *launches = n;
+    return UCFP_OK;
+}
+
 int ucfp_ctx_profile_end(ucfp_ctx *ctx, int kernel_class, double *kernel_ms, double *alg_units, uint64_t *launches) {
     UCFP_GUARD(ctx);
     UCFP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -520,6 +520,7 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
                 const uint64_t tiles = (n + kMmaTileCodes - 1) / kMmaTileCodes;
                 const unsigned mma_grid = (unsigned)(tiles < (uint64_t)ctx->sm_count ? tiles : (uint64_t)ctx->sm_count);
                 ProfScope ps(ctx, UCFP_PROF_HAMMING_SCAN, 8.0 * (double)n * nqp);
+                ProfScope pt(ctx, UCFP_PROF_HAMMING_TENSOR, 64.0 * (double)n * nqp);
                 hamming_mma_scan_kernel<<<mma_grid, kMmaThreads, kMmaSmem, st>>>(
                     MmaScanArgs{codes, ids, c->id_base, pos, pos + n, slots, kth, nqp, cand, count, cap});
             } else {

@@ -79,6 +79,12 @@ class Context:
         check(self._L.ucfp_ctx_profile_end(self._h, kernel_class, C.byref(ms), C.byref(units), C.byref(n)))
         return ms.value, units.value, int(n.value)
 
+    def profile_read(self, kernel_class: int):
+        """Like profile_end, without ending the region (several kernel classes of one timed region)."""
+        ms, units, n = C.c_double(0), C.c_double(0), C.c_uint64(0)
+        check(self._L.ucfp_ctx_profile_read(self._h, kernel_class, C.byref(ms), C.byref(units), C.byref(n)))
+        return ms.value, units.value, int(n.value)
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._L.ucfp_destroy(self._h)
