@@ -32,7 +32,8 @@ def _check(ctx, codes, queries, k, ids=None, id_base=0):
 
 
 @pytest.mark.parametrize("n,nq,k", [(1, 1, 1), (7, 3, 10), (2047, 5, 10), (2048, 5, 10), (2049, 5, 10), (4097, 2, 1),
-                                    (100_003, 64, 10), (262_144, 33, 100), (1_000_001, 17, 10)])
+                                    (100_003, 64, 10), (262_144, 33, 100), (1_000_001, 17, 10),
+                                    (5_000, 3, 1500), (200_000, 70, 1100), (1_030, 2, 2048)])
 def test_random_corpus_matches_oracle(ctx, n, nq, k):
     codes = oracle.fill_u64(n, 0xC0DE)
     queries = oracle.fill_u64(nq, 0xBEEF)

@@ -39,7 +39,7 @@ namespace {
 constexpr int kScanThreads = 256;
 constexpr int kCodesPerThread = 8;                 // 4 x LDG.128 in flight per thread
 constexpr int kTileCodes = kScanThreads * kCodesPerThread;
-constexpr uint32_t kSeedRows = 2048;               // multiple of 2 (keeps 16-byte alignment of chunk starts)
+constexpr uint32_t kSeedRows = 1024;               // multiple of 2 (keeps 16-byte alignment of chunk starts); raised to k when k is larger
 constexpr uint32_t kMaxQueriesPerPass = 1024;      // POPC scan: 16 B/query of shared memory; tensor scan: 8 resident 128-query tiles
 constexpr uint64_t kMaxChunkRows = 1ULL << 28;
 
@@ -189,7 +189,7 @@ constexpr int kMmaThreads = 32 * (1 + kMmaExpWarps + kMmaEpiWarps);
 constexpr int kMmaColsPerWarp = kMmaRows / (kMmaEpiWarps / 4);
 constexpr uint32_t kMmaMaxQueries = 1024;
 constexpr uint32_t kMmaMinQueries = 64;              // measured crossover: the POPC scan costs 0.24 ms per query and 1 B rows, the tensor scan >= 15 ms per batch
-constexpr uint64_t kMmaMinChunkRows = 1ULL << 19;    // smaller chunks (loose bounds, many survivors) stay on the POPC scan
+constexpr uint64_t kMmaMinChunkRows = 1ULL << 16;    // smaller chunks (fewer tiles than SMs, very loose bounds) stay on the POPC scan
 constexpr size_t kMmaSmem = (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes + kMmaStages * kMmaCBytes + kMmaMaxQueries * (16 + 8 + 4) + 128 + 1024;
 static_assert(kMmaMaxQueries <= kMaxQueriesPerPass || kMaxQueriesPerPass <= kMmaMaxQueries, "");
 static_assert(kMmaColsPerWarp == 64, "one packed tcgen05.ld per warp and accumulator tile");
@@ -485,7 +485,12 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
         uint32_t *dist_out = dist_out_dev + q0 * k;
 
         hamming_init_kernel<<<(nqp + 255) / 256, 256, 0, st>>>(q_dev + q0, nqp, slots, kth, count, flags);
-        const uint32_t seed = (uint32_t)(N < kSeedRows ? N : kSeedRows);
+        static const long env_seed = getenv("UCFP_HAMMING_SEED") ? atol(getenv("UCFP_HAMMING_SEED")) : 0;   // developer knobs
+        static const long env_mma_rows = getenv("UCFP_HAMMING_MMA_MIN_ROWS") ? atol(getenv("UCFP_HAMMING_MMA_MIN_ROWS")) : 0;
+        uint32_t seed_rows = env_seed > 0 ? (uint32_t)env_seed : kSeedRows;
+        if (seed_rows < 2 * k) seed_rows = (uint32_t)(2 * k);   // the seed must fill a k-list with room to spare, or its bound admits everything
+        const uint32_t seed = (uint32_t)(N < seed_rows ? N : seed_rows);
+        const uint64_t mma_min_rows = env_mma_rows > 0 ? (uint64_t)env_mma_rows : kMmaMinChunkRows;
         hamming_seed_kernel<<<dim3((seed + 255) / 256, nqp), 256, 0, st>>>(codes, seed, slots, cand, count, cap);
         count_launch(ctx, 2);
 
@@ -502,7 +507,10 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
         const bool streaming = nqp <= 16;   // HBM-bound regime: fewer and larger chunks
         const bool use_mma = nqp >= kMmaMinQueries && !env_no_mma;
         static const long env_growth = getenv("UCFP_HAMMING_GROWTH") ? atol(getenv("UCFP_HAMMING_GROWTH")) : 0;
-        const uint64_t growth = streaming ? 64 : (env_growth > 1 ? (uint64_t)env_growth : 8);
+        // a chunk of g x (rows seen) admits about g x k rows per query; the lists hold cap entries including the k kept ones
+        const uint64_t growth_cap = (cap - k) / (2 * k) > 2 ? (cap - k) / (2 * k) : 2;
+        const uint64_t growth_want = streaming ? 64 : (env_growth > 1 ? (uint64_t)env_growth : 8);
+        const uint64_t growth = growth_want < growth_cap ? growth_want : growth_cap;
         const uint64_t max_chunk = streaming ? (1ULL << 40) : kMaxChunkRows;
         uint64_t pos = seed, chunk = (uint64_t)seed * growth;
         while (pos < N) {
@@ -516,7 +524,7 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
                 if (q_groups > max_groups) q_groups = max_groups;
                 grid = ntiles * q_groups;
             }
-            if (use_mma && n >= kMmaMinChunkRows) {
+            if (use_mma && n >= mma_min_rows) {
                 const uint64_t tiles = (n + kMmaTileCodes - 1) / kMmaTileCodes;
                 const unsigned mma_grid = (unsigned)(tiles < (uint64_t)ctx->sm_count ? tiles : (uint64_t)ctx->sm_count);
                 ProfScope ps(ctx, UCFP_PROF_HAMMING_SCAN, 8.0 * (double)n * nqp);
