@@ -204,6 +204,7 @@ def main() -> int:
     if mine.any():
         view[torch.from_numpy((rows[mine] - np.uint64(lo)).astype(np.int64)).to(dev)] = \
             torch.from_numpy(codes[mine].view(np.int64)).to(dev)
+        corpus.refresh()   # rows were written in place: rebuild the tensor scan's operand rows
 
     queries = make_queries(nq)
     q_host = torch.from_numpy(queries.view(np.int64)).pin_memory()
@@ -327,6 +328,7 @@ def main() -> int:
 
         v2 = torch.as_tensor(_Rows2(), device=dev)
         v2[torch.from_numpy(r2.astype(np.int64)).to(dev)] = torch.from_numpy(k2.view(np.int64)).to(dev)
+        c2.refresh()
         for _ in range(3):
             c2.scan_hamming(q_dev, K, ids_out, dist_out)
         ms2 = timed(lambda: c2.scan_hamming(q_dev, K, ids_out, dist_out), 5) / 5

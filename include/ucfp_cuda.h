@@ -177,7 +177,8 @@ UCFP_API uint64_t ucfp_corpus_size(const ucfp_corpus *c);
 UCFP_API int ucfp_corpus_append_synthetic(ucfp_corpus *c, uint64_t seed, uint64_t start_row, uint64_t n);
 /* Device pointer to the resident rows (view for tests/bench planting), or NULL. */
 UCFP_API void *ucfp_corpus_device_rows(ucfp_corpus *c);
-/* Re-derives the side arrays (MinHash sketches; cosine norms and bf16 copies) of all resident rows.  Call it
+/* Re-derives the side arrays (Hamming tensor-scan operand rows; MinHash sketches; cosine norms and bf16 copies) of
+ * all resident rows.  Call it
  * after rows were modified in place through ucfp_corpus_device_rows. */
 UCFP_API int ucfp_corpus_refresh(ucfp_corpus *c);
 

@@ -15,6 +15,9 @@ constexpr int kQBytes = kQTile * kRowBytes, kCBytes = kCTile * kRowBytes;
 #ifndef VARIANT
 #define VARIANT 0
 #endif
+#ifndef SW64
+#define SW64 0
+#endif
 #ifndef SPLIT
 #define SPLIT 0
 #endif
@@ -40,6 +43,9 @@ __device__ __forceinline__ void umma_i8(uint32_t d, uint64_t a, uint64_t b, uint
 }
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
     return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_sw64(uint32_t addr) {   // K-major, 64-byte rows, 8-row groups 512 bytes apart
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -83,14 +89,20 @@ __device__ __forceinline__ uint32_t expand4x2(uint32_t na, uint32_t nb) {
     return 0xC1C1C1C1u ^ (ta * 0x7Eu) ^ (tb << 7);
 }
 __device__ __forceinline__ void store_row2(unsigned char *tile, uint32_t r, uint64_t a, uint64_t b) {
+#if SW64
+    unsigned char *row = tile + r * 64;
+    const uint32_t sw = (r >> 1) & 3;
+#else
     unsigned char *row = tile + (r >> 3) * 1024 + (r & 7) * 128;
+    const uint32_t sw = r & 7;
+#endif
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         uint32_t ha = (uint32_t)(a >> (16 * c)) & 0xFFFFu, hb = (uint32_t)(b >> (16 * c)) & 0xFFFFu;
         uint4 w;
         w.x = expand4x2(ha & 15, hb & 15); w.y = expand4x2((ha >> 4) & 15, (hb >> 4) & 15);
         w.z = expand4x2((ha >> 8) & 15, (hb >> 8) & 15); w.w = expand4x2(ha >> 12, hb >> 12);
-        *reinterpret_cast<uint4 *>(row + ((c ^ (r & 7)) << 4)) = w;
+        *reinterpret_cast<uint4 *>(row + ((c ^ sw) << 4)) = w;
     }
 }
 // one 64-bit code -> 64 int8 in the first four 16-byte chunks of row r of a 128B-swizzled K-major tile
@@ -238,7 +250,7 @@ hamming_mma_kernel(const uint64_t *__restrict__ codes, uint64_t nrows, const QSl
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
             mbar_wait(&cfull[s], ph);
             tc_fence_after();
-            const uint64_t bdesc = desc_sw128(smem_u32(sC + s * kCBytes));
+            const uint64_t bdesc = SW64 ? desc_sw64(smem_u32(sC + s * kCBytes)) : desc_sw128(smem_u32(sC + s * kCBytes));
 #if SPLIT
             const uint32_t idesc_h = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(kQTile >> 4) << 24);
             for (uint32_t mt = 0; mt < q_tiles; ++mt)

@@ -136,6 +136,59 @@ def test_tensor_path_duplicate_flood_falls_back(ctx):
     assert ctx.last_scan_fallbacks() > 0
 
 
+def test_tensor_path_incremental_appends_rebuild_pair_rows(ctx):
+    """Operand rows pair codes (2r, 2r+1): appends that start at an odd row must rebuild the shared row; in-place edits
+    followed by refresh() must be seen by the tensor scan."""
+    import torch
+    n1, n2, n3, n4 = 333_333, 1, 250_001, 415_665
+    codes = oracle.fill_u64(n1 + n2 + n3 + n4, 31)
+    queries = oracle.fill_u64(96, 32)
+    corpus = Corpus(ctx, _ffi.KIND_HAMMING64, len(codes))
+    pos = 0
+    for m in (n1, n2, n3, n4):
+        corpus.append(codes[pos:pos + m].copy())
+        pos += m
+    gi, gd = corpus.scan_hamming(queries, 10)
+    oi, od = oracle.hamming_topk(codes, queries, 10, threads=oracle.host_threads())
+    np.testing.assert_array_equal(gd, od)
+    np.testing.assert_array_equal(gi, oi)
+    # overwrite two rows in place with exact copies of queries, one at an odd and one at an even row
+    class _A:
+        __cuda_array_interface__ = {"shape": (len(codes),), "typestr": "<i8", "data": (corpus.device_rows_ptr(), False), "version": 2}
+    view = torch.as_tensor(_A(), device="cuda")
+    codes[777_777] = queries[5]; codes[900_000] = queries[6]
+    view[777_777] = int(queries[5].view(np.int64)); view[900_000] = int(queries[6].view(np.int64))
+    torch.cuda.synchronize()
+    corpus.refresh()
+    gi, gd = corpus.scan_hamming(queries, 10)
+    oi, od = oracle.hamming_topk(codes, queries, 10, threads=oracle.host_threads())
+    np.testing.assert_array_equal(gd, od)
+    np.testing.assert_array_equal(gi, oi)
+    assert gd[5, 0] == 0 and gi[5, 0] == 777_777 and gd[6, 0] == 0 and gi[6, 0] == 900_000
+    corpus.close()
+
+
+def test_tensor_path_without_operand_rows_in_a_fresh_process():
+    """The scan also runs without the pre-built operand rows (their allocation is optional): the producer warps then expand
+    the codes in the kernel.  The switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prog = ("import numpy as np, oracle\n"
+            "from ucfp_b200 import Context, Corpus, _ffi\n"
+            "ctx = Context(0)\n"
+            "codes = oracle.fill_u64(1_234_567, 41); q = oracle.fill_u64(200, 42); q[:4] = codes[[5, 700_001, 1_234_566, 99_999]]\n"
+            "c = Corpus(ctx, _ffi.KIND_HAMMING64, len(codes)); c.append(codes)\n"
+            "gi, gd = c.scan_hamming(q, 10)\n"
+            "oi, od = oracle.hamming_topk(codes, q, 10, threads=oracle.host_threads())\n"
+            "assert (gi == oi).all() and (gd == od).all() and ctx.last_scan_fallbacks() == 0\n"
+            "print('ok')\n")
+    env = dict(os.environ, UCFP_HAMMING_NO_OPS="1", PYTHONPATH=root)
+    out = subprocess.run([sys.executable, "-c", prog], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
 def test_fewer_rows_than_k_pads_with_sentinels(ctx):
     codes = oracle.fill_u64(5, 9)
     queries = oracle.fill_u64(3, 10)
@@ -210,6 +263,7 @@ def test_config2_scale_100m_codes_1024_queries(ctx):
     uniq_rows, first = np.unique(rows.numpy(), return_index=True)   # colliding rows keep the first write
     view[torch.from_numpy(uniq_rows).cuda()] = torch.from_numpy(planted[first].view(np.int64)).cuda()
     torch.cuda.synchronize()
+    corpus.refresh()                                      # rows were written in place: rebuild the operand rows
     q_dev = torch.from_numpy(queries.view(np.int64)).cuda()
     ids_dev, dist_dev = corpus.scan_hamming(q_dev, k)
     torch.cuda.synchronize()

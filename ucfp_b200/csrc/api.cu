@@ -207,6 +207,13 @@ int ucfp_corpus_create(ucfp_ctx *ctx, int kind, uint32_t dim, uint64_t capacity,
         e = cudaMalloc(&c->cos_bf16, 2 * (size_t)c->dim_pad * (capacity + 256));
         if (e == cudaSuccess) e = cudaMalloc((void **)&c->cos_inv_norm, 4 * (capacity + 256));
     }
+    if (e == cudaSuccess && kind == UCFP_KIND_HAMMING64) {
+        // Operand rows of the tensor-core scan, 32 B per code on top of the 8 B code.  Optional: without them (allocation
+        // refused) the scan expands the codes on the fly in its producer warps, slower for 64-512-query batches.
+        const size_t ops_bytes = 64 * ((capacity + 1) / 2 + 512);   // whole 256-row stages stay readable
+        if (cudaMalloc((void **)&c->ham_ops, ops_bytes) != cudaSuccess) { cudaGetLastError(); c->ham_ops = nullptr; }
+        else if (cudaMemsetAsync(c->ham_ops, 0, ops_bytes, ctx->stream) != cudaSuccess) { cudaGetLastError(); cudaFree(c->ham_ops); c->ham_ops = nullptr; }
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         set_error("corpus allocation of %llu rows failed: %s", (unsigned long long)capacity, cudaGetErrorString(e));
@@ -229,6 +236,7 @@ void ucfp_corpus_destroy(ucfp_corpus *c) {
         cudaStreamSynchronize(c->ctx->stream);
         if (c->rows) cudaFree(c->rows);
         if (c->ids) cudaFree(c->ids);
+        if (c->ham_ops) cudaFree(c->ham_ops);
         if (c->mh_sketch) cudaFree(c->mh_sketch);
         if (c->cos_bf16) cudaFree(c->cos_bf16);
         if (c->cos_inv_norm) cudaFree(c->cos_inv_norm);
@@ -256,6 +264,7 @@ int ucfp_corpus_clear(ucfp_corpus *c) {
 }
 
 static int after_append(ucfp_corpus *c, uint64_t first, uint64_t n) {
+    if (c->kind == UCFP_KIND_HAMMING64) return hamming_on_append(c, first, n);
     if (c->kind == UCFP_KIND_MINHASH128) return jaccard_on_append(c, first, n);
     if (c->kind == UCFP_KIND_COSINE) return cosine_on_append(c, first, n);
     return UCFP_OK;

@@ -115,6 +115,7 @@ struct ucfp_corpus {
     void *rows = nullptr;          // HAMMING64: u64[cap]; MINHASH128: u64[cap][128]; COSINE: f32[cap][dim]
     uint64_t *ids = nullptr;       // u64[cap] when id_mode == 1
     // kind-specific side arrays
+    uint8_t *ham_ops = nullptr;    // HAMMING64: s8[cap / 2][64], tensor-scan operand rows (codes 2r, 2r+1 as -a_k + 64 b_k); may be null
     uint8_t *mh_sketch = nullptr;  // MINHASH128: u8[cap][128], low byte of every slot (prefilter)
     void *cos_bf16 = nullptr;      // COSINE: bf16[cap][dim_pad] rows scaled to unit norm, for the tensor-core pass
     float *cos_inv_norm = nullptr; // COSINE: 1/|v| in f32 (0 for zero rows)
@@ -158,6 +159,7 @@ inline int check_launch(const char *what) {
 // ---- kernels-side entry points implemented in the per-path .cu files -------
 int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, uint32_t *dist_out_dev);
 int jaccard_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, uint32_t *m_out_dev);
+int hamming_on_append(ucfp_corpus *c, uint64_t first_row, uint64_t n);
 int jaccard_on_append(ucfp_corpus *c, uint64_t first_row, uint64_t n);
 int cosine_scan(ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, float *score_out_dev);
 int cosine_on_append(ucfp_corpus *c, uint64_t first_row, uint64_t n);

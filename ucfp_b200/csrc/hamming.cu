@@ -183,14 +183,16 @@ constexpr int kMmaTileCodes = 2 * kMmaRows;
 constexpr int kMmaRowBytes = 128;                    // one 128B-swizzle row; bytes 0..63 hold the K = 64 elements
 constexpr int kMmaQBytes = kMmaQTile * kMmaRowBytes; // 16 KiB per query tile
 constexpr int kMmaCBytes = kMmaRows * kMmaRowBytes;  // 32 KiB per code stage
-constexpr int kMmaStages = 2;
+constexpr int kMmaStages = 2;                        // in-kernel expansion: 2 x 32 KiB (128-byte rows, SWIZZLE_128B)
+constexpr int kMmaImgBytes = kMmaRows * 64;          // pre-built stage image: 16 KiB (64-byte rows, SWIZZLE_64B)
+constexpr int kMmaMaxImgStages = 8;
 constexpr int kMmaExpWarps = 4, kMmaEpiWarps = 16;
 constexpr int kMmaThreads = 32 * (1 + kMmaExpWarps + kMmaEpiWarps);
 constexpr int kMmaColsPerWarp = kMmaRows / (kMmaEpiWarps / 4);
 constexpr uint32_t kMmaMaxQueries = 1024;
 constexpr uint32_t kMmaMinQueries = 64;              // measured crossover: the POPC scan costs 0.24 ms per query and 1 B rows, the tensor scan >= 15 ms per batch
 constexpr uint64_t kMmaMinChunkRows = 1ULL << 16;    // smaller chunks (fewer tiles than SMs, very loose bounds) stay on the POPC scan
-constexpr size_t kMmaSmem = (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes + kMmaStages * kMmaCBytes + kMmaMaxQueries * (16 + 8 + 4) + 128 + 1024;
+constexpr size_t kMmaSmem = (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes + kMmaStages * kMmaCBytes + kMmaMaxQueries * (16 + 8 + 4) + 256 + 1024;
 static_assert(kMmaMaxQueries <= kMaxQueriesPerPass || kMaxQueriesPerPass <= kMmaMaxQueries, "");
 static_assert(kMmaColsPerWarp == 64, "one packed tcgen05.ld per warp and accumulator tile");
 
@@ -223,8 +225,25 @@ __device__ __forceinline__ void mma_store_code_row(unsigned char *tile, uint32_t
     }
 }
 
+// Operand rows built once at append time (corpus->ham_ops): row g = codes 2g and 2g + 1, 64 bytes.  They are stored as the
+// shared-memory IMAGE of the scan's stage tiles -- 256 rows = 16 KiB per tile, 64B-swizzled (chunk c of row r at chunk
+// c ^ ((r >> 1) & 3)) -- so that the scan's producer is one TMA bulk copy per stage.
+__global__ void hamming_ops_kernel(const uint64_t *__restrict__ codes, uint64_t row_lo, uint64_t row_hi, uint64_t size, uint4 *__restrict__ ops) {
+    const uint64_t g = row_lo / 2 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * g >= row_hi) return;
+    const uint64_t a = codes[2 * g], b = 2 * g + 1 < size ? codes[2 * g + 1] : 0;
+    const uint32_t r = (uint32_t)(g % kMmaRows);
+    uint4 *row = ops + 4 * g;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint32_t ha = (uint32_t)(a >> (16 * c)) & 0xFFFFu, hb = (uint32_t)(b >> (16 * c)) & 0xFFFFu;
+        row[c ^ ((r >> 1) & 3)] = make_uint4(mma_pack4(ha & 15, hb & 15), mma_pack4((ha >> 4) & 15, (hb >> 4) & 15),
+                                             mma_pack4((ha >> 8) & 15, (hb >> 8) & 15), mma_pack4(ha >> 12, hb >> 12));
+    }
+}
+
 struct MmaScanArgs {
-    const uint64_t *codes; const uint64_t *ids; uint64_t id_base;
+    const uint64_t *codes; const uint4 *ops; const uint64_t *ids; uint64_t id_base;   // ops: pre-built stage images or null
     uint64_t row0, row_end;                  // rows [row0, row_end), row0 even
     const QSlot *slots; const uint64_t *kth_id; uint32_t nq;
     uint64_t *cand; uint32_t *count; uint32_t cap;
@@ -283,20 +302,25 @@ __device__ __forceinline__ void hamming_mma_settle(const uint32_t (&p)[32], uint
     }
 }
 
+template <bool kPreExpanded>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char *sQ = smem;                                                          // [8][16 KiB] query tiles
-    unsigned char *sC = smem + (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes;      // [kMmaStages][32 KiB] operand rows
-    uint4 *s_q = reinterpret_cast<uint4 *>(sC + kMmaStages * kMmaCBytes);              // [1024] query slots {lo, hi, thr, -}
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t q_tiles = (A.nq + kMmaQTile - 1) / kMmaQTile;
+    unsigned char *sQ = smem;                                                          // [q_tiles][16 KiB] query tiles
+    // operand-row stages: expansion path 2 x 32 KiB after all eight query-tile slots; image path 16 KiB each, starting right
+    // after the query tiles in use (4 stages at 1024 queries, 8 at <= 512)
+    unsigned char *sC = kPreExpanded ? smem + (size_t)q_tiles * kMmaQBytes : smem + (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes;
+    const uint32_t n_stages = kPreExpanded ? min((uint32_t)kMmaMaxImgStages, 12u - q_tiles) : (uint32_t)kMmaStages;
+    const uint32_t stage_bytes = kPreExpanded ? kMmaImgBytes : kMmaCBytes;
+    uint4 *s_q = reinterpret_cast<uint4 *>(smem + (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes + kMmaStages * kMmaCBytes);   // [1024] query slots {lo, hi, thr, -}
     uint64_t *s_kid = reinterpret_cast<uint64_t *>(s_q + kMmaMaxQueries);              // [1024] id of the current k-th result
     uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_kid + kMmaMaxQueries);            // [1024] bound of the hot test, 0xFFFFFFFF = never
     uint64_t *cfull = reinterpret_cast<uint64_t *>(s_thr + kMmaMaxQueries);
-    uint64_t *cempty = cfull + kMmaStages, *tfull = cempty + kMmaStages, *tempty = tfull + 2;
+    uint64_t *cempty = cfull + kMmaMaxImgStages, *tfull = cempty + kMmaMaxImgStages, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t q_tiles = (A.nq + kMmaQTile - 1) / kMmaQTile;
     const uint32_t n_tiles = (uint32_t)((A.row_end - A.row0 + kMmaTileCodes - 1) / kMmaTileCodes);
 
     for (uint32_t q = threadIdx.x; q < q_tiles * kMmaQTile; q += blockDim.x) {
@@ -312,7 +336,7 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
         s_thr[q] = q < A.nq ? hot : 0xFFFFFFFFu;
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kMmaStages; ++s) { mbar_init(&cfull[s], kMmaExpWarps * 32); mbar_init(&cempty[s], 1); }
+        for (uint32_t s = 0; s < n_stages; ++s) { mbar_init(&cfull[s], kPreExpanded ? 1 : kMmaExpWarps * 32); mbar_init(&cempty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kMmaEpiWarps); }
         mbar_fence_init();
     }
@@ -328,10 +352,10 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
         const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kMmaRows >> 3) << 17) | ((uint32_t)(kMmaQTile >> 4) << 24);
         uint32_t it = 0, acc_it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const uint32_t s = it % kMmaStages, ph = (it / kMmaStages) & 1;
+            const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
             mbar_wait_sleep(&cfull[s], ph);
             tcgen05_fence_after();
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(sC + s * kMmaCBytes));
+            const uint64_t bdesc = kPreExpanded ? umma_desc_sw64(smem_u32(sC + s * stage_bytes)) : umma_desc_sw128(smem_u32(sC + s * stage_bytes));
             for (uint32_t mt = 0; mt < q_tiles; ++mt, ++acc_it) {
                 const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
                 mbar_wait_sleep(&tempty[as], aph ^ 1);
@@ -348,32 +372,47 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
             __syncwarp();
         }
     } else if (warp <= kMmaExpWarps) {
-        // ===== producers: thread t expands operand rows t and t + 128 of a stage (codes 2r, 2r + 1; 16-byte loads) =====
+        // ===== producers: thread t fills operand rows t and t + 128 of a stage =====
         const uint32_t t = threadIdx.x - 32;
-        auto load_tile = [&](uint32_t tile, uint64_t (&c)[4]) {
-            const uint64_t base = A.row0 + (uint64_t)tile * kMmaTileCodes;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {   // rows past the end become code 0 and are rejected by the cold path's range check
-                const uint64_t r0 = base + 2 * (t + 128 * j);
-                if (r0 + 1 < A.row_end) {
-                    const uint4 v = ldg_stream_v4(reinterpret_cast<const uint4 *>(A.codes + r0));
-                    c[2 * j] = (uint64_t)v.y << 32 | v.x; c[2 * j + 1] = (uint64_t)v.w << 32 | v.z;
-                } else { c[2 * j] = r0 < A.row_end ? A.codes[r0] : 0; c[2 * j + 1] = 0; }
-            }
-        };
         uint32_t it = 0;
-        uint64_t cur[4], nxt[4] = {0, 0, 0, 0};
-        if (blockIdx.x < n_tiles) load_tile(blockIdx.x, cur);
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const uint32_t s = it % kMmaStages, ph = (it / kMmaStages) & 1;
-            if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, nxt);   // next tile's codes fly while this one is expanded
-            mbar_wait_sleep(&cempty[s], ph ^ 1);
-            mma_store_code_row(sC + s * kMmaCBytes, t, cur[0], cur[1]);
-            mma_store_code_row(sC + s * kMmaCBytes, t + 128, cur[2], cur[3]);
-            fence_proxy_async_smem();
-            mbar_arrive(&cfull[s]);
+        if (kPreExpanded) {
+            // stage images come ready-made from HBM (corpus->ham_ops): one elected thread, one 16 KiB TMA bulk copy per stage,
+            // as many in flight as there are stages
+            if (threadIdx.x == 32) {
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(A.ops) + (A.row0 / kMmaTileCodes) * (uint64_t)kMmaImgBytes;
+                for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                    const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
+                    mbar_wait_sleep(&cempty[s], ph ^ 1);
+                    mbar_expect_tx(&cfull[s], kMmaImgBytes);
+                    tma_bulk_g2s(sC + s * kMmaImgBytes, src + (uint64_t)tile * kMmaImgBytes, kMmaImgBytes, &cfull[s]);
+                }
+            }
+        } else {
+            // thread t expands codes 2r, 2r + 1 (16-byte loads) for r = t and t + 128
+            auto load_tile = [&](uint32_t tile, uint64_t (&c)[4]) {
+                const uint64_t base = A.row0 + (uint64_t)tile * kMmaTileCodes;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+                for (int j = 0; j < 2; ++j) {   // rows past the end become code 0 and are rejected by the cold path's range check
+                    const uint64_t r0 = base + 2 * (t + 128 * j);
+                    if (r0 + 1 < A.row_end) {
+                        const uint4 v = ldg_stream_v4(reinterpret_cast<const uint4 *>(A.codes + r0));
+                        c[2 * j] = (uint64_t)v.y << 32 | v.x; c[2 * j + 1] = (uint64_t)v.w << 32 | v.z;
+                    } else { c[2 * j] = r0 < A.row_end ? A.codes[r0] : 0; c[2 * j + 1] = 0; }
+                }
+            };
+            uint64_t cur[4], nxt[4] = {0, 0, 0, 0};
+            if (blockIdx.x < n_tiles) load_tile(blockIdx.x, cur);
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t s = it % kMmaStages, ph = (it / kMmaStages) & 1;
+                if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, nxt);   // next tile's codes fly while this one is expanded
+                mbar_wait_sleep(&cempty[s], ph ^ 1);
+                mma_store_code_row(sC + s * kMmaCBytes, t, cur[0], cur[1]);
+                mma_store_code_row(sC + s * kMmaCBytes, t + 128, cur[2], cur[3]);
+                fence_proxy_async_smem();
+                mbar_arrive(&cfull[s]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+            }
         }
     } else {
         // ===== epilogue: warp -> TMEM lane quadrant (warp % 4) and 64 of the 256 columns =====
@@ -443,6 +482,17 @@ struct HammingKey {
 
 }  // namespace
 
+// Called before c->size grows: rows [first_row, first_row + n) were just written.  The pair row of an odd first_row is rebuilt.
+int hamming_on_append(ucfp_corpus *c, uint64_t first_row, uint64_t n) {
+    if (!c->ham_ops || n == 0) return UCFP_OK;
+    const uint64_t lo = first_row & ~1ULL, hi = first_row + n;
+    const uint64_t pairs = (hi - lo + 1) / 2;
+    hamming_ops_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, c->ctx->stream>>>(static_cast<const uint64_t *>(c->rows), lo, hi, hi,
+                                                                                  reinterpret_cast<uint4 *>(c->ham_ops));
+    count_launch(c->ctx);
+    return check_launch("hamming_ops");
+}
+
 int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev,
                  uint32_t *dist_out_dev) {
     ucfp_ctx *ctx = c->ctx;
@@ -467,8 +517,10 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
     UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_occ, hamming_scan_kernel, kScanThreads,
                                                                  sizeof(QSlot) * kMaxQueriesPerPass));
     if (scan_occ < 1) scan_occ = 1;
-    UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
-    static const bool env_no_mma = getenv("UCFP_HAMMING_NO_MMA") != nullptr;   // developer switch: POPC scan only
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
+    static const bool env_no_mma = getenv("UCFP_HAMMING_NO_MMA") != nullptr;   // developer switches: POPC scan only /
+    static const bool env_no_ops = getenv("UCFP_HAMMING_NO_OPS") != nullptr;   // expand codes in the kernel although operand rows exist
 
     for (size_t q0 = 0; q0 < nq; q0 += kMaxQueriesPerPass) {
         const uint32_t nqp = (uint32_t)((nq - q0 < kMaxQueriesPerPass) ? nq - q0 : kMaxQueriesPerPass);
@@ -489,6 +541,7 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
         static const long env_mma_rows = getenv("UCFP_HAMMING_MMA_MIN_ROWS") ? atol(getenv("UCFP_HAMMING_MMA_MIN_ROWS")) : 0;
         uint32_t seed_rows = env_seed > 0 ? (uint32_t)env_seed : kSeedRows;
         if (seed_rows < 2 * k) seed_rows = (uint32_t)(2 * k);   // the seed must fill a k-list with room to spare, or its bound admits everything
+        seed_rows = (seed_rows + kMmaTileCodes - 1) / kMmaTileCodes * kMmaTileCodes;   // chunk starts = seed x growth^i stay aligned to the 512-code stage images
         const uint32_t seed = (uint32_t)(N < seed_rows ? N : seed_rows);
         const uint64_t mma_min_rows = env_mma_rows > 0 ? (uint64_t)env_mma_rows : kMmaMinChunkRows;
         hamming_seed_kernel<<<dim3((seed + 255) / 256, nqp), 256, 0, st>>>(codes, seed, slots, cand, count, cap);
@@ -529,8 +582,11 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
                 const unsigned mma_grid = (unsigned)(tiles < (uint64_t)ctx->sm_count ? tiles : (uint64_t)ctx->sm_count);
                 ProfScope ps(ctx, UCFP_PROF_HAMMING_SCAN, 8.0 * (double)n * nqp);
                 ProfScope pt(ctx, UCFP_PROF_HAMMING_TENSOR, 64.0 * (double)n * nqp);
-                hamming_mma_scan_kernel<<<mma_grid, kMmaThreads, kMmaSmem, st>>>(
-                    MmaScanArgs{codes, ids, c->id_base, pos, pos + n, slots, kth, nqp, cand, count, cap});
+                const MmaScanArgs margs{codes, reinterpret_cast<const uint4 *>(c->ham_ops), ids, c->id_base, pos, pos + n, slots, kth, nqp, cand, count, cap};
+                // With all eight query tiles in use a 512-code stage lasts ~3 300 clk and the in-kernel expansion hides completely
+                // behind it (measured 41.8 vs 43.0 ms per 1 B rows); below that the ready-made images win (7.6 vs 13.5 ms at 64-128 queries).
+                if (c->ham_ops && !env_no_ops && pos % kMmaTileCodes == 0 && nqp <= 7 * kMmaQTile) hamming_mma_scan_kernel<true><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
+                else hamming_mma_scan_kernel<false><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
             } else {
                 ProfScope ps(ctx, UCFP_PROF_HAMMING_SCAN, 8.0 * (double)n * nqp);
                 hamming_scan_kernel<<<(unsigned)grid, kScanThreads, sizeof(QSlot) * nqp, st>>>(

@@ -41,6 +41,12 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (UBLKCP in SASS)
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 // all 512 TMEM columns of the SM; one warp calls alloc, the same warp deallocs
@@ -76,6 +82,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset: next 8-row group
     d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+    return d;
+}
+
+// K-major operand tile with 64-byte rows in 64B-swizzled shared memory (8-row groups 512 bytes apart; 16-byte chunk c of
+// row r sits at chunk c ^ ((r >> 1) & 3)).
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                               // SWIZZLE_64B
     return d;
 }
 
