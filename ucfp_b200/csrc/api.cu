@@ -201,7 +201,7 @@ int ucfp_corpus_create(ucfp_ctx *ctx, int kind, uint32_t dim, uint64_t capacity,
     size_t rb = row_bytes(c);
     // +16 rows of slack so that vector loads of the last partial tile never leave the allocation
     cudaError_t e = cudaMalloc(&c->rows, rb * (capacity + 16));
-    if (e == cudaSuccess && kind == UCFP_KIND_MINHASH128) e = cudaMalloc((void **)&c->mh_sketch, 128 * ((capacity + 31) / 32 * 32 + 512));  // whole 256-row tiles stay readable
+    if (e == cudaSuccess && kind == UCFP_KIND_MINHASH128) e = cudaMalloc((void **)&c->mh_sketch, 2 * 128 * ((capacity + 31) / 32 * 32 + 512));  // two planes (byte 0, byte 1 of every slot); whole 256-row tiles stay readable
     if (e == cudaSuccess && kind == UCFP_KIND_COSINE) {
         c->dim_pad = (dim + 63) / 64 * 64;
         e = cudaMalloc(&c->cos_bf16, 2 * (size_t)c->dim_pad * (capacity + 256));

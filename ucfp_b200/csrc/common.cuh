@@ -116,7 +116,7 @@ struct ucfp_corpus {
     uint64_t *ids = nullptr;       // u64[cap] when id_mode == 1
     // kind-specific side arrays
     uint8_t *ham_ops = nullptr;    // HAMMING64: s8[cap / 2][64], tensor-scan operand rows (codes 2r, 2r+1 as -a_k + 64 b_k); may be null
-    uint8_t *mh_sketch = nullptr;  // MINHASH128: u8[cap][128], low byte of every slot (prefilter)
+    uint8_t *mh_sketch = nullptr;  // MINHASH128: 2 planes of u8[cap][128]: byte 0 of every slot (scan prefilter), byte 1 (second check of survivors)
     void *cos_bf16 = nullptr;      // COSINE: bf16[cap][dim_pad] rows scaled to unit norm, for the tensor-core pass
     float *cos_inv_norm = nullptr; // COSINE: 1/|v| in f32 (0 for zero rows)
     uint32_t dim_pad = 0;

@@ -13,6 +13,7 @@
 // Selection (thresholds that tighten chunk by chunk, compaction, overflow fallback) is shared with the
 // Hamming scan: topk_select.cuh, key = 128 - matches.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -25,15 +26,19 @@ constexpr int kSlots = 128;
 constexpr int kSketchWords = 32;                 // 128 slots x 1 byte
 constexpr int kScanThreads = 256;
 constexpr uint32_t kSeedRows = 1024;
-constexpr uint32_t kMaxQueriesPerPass = 256;     // 128 B of sketch + 4 B bound per query in shared memory
+constexpr uint32_t kMaxQueriesPerPass = 256;     // 2 x 128 B of sketch planes + 12 B of bound per query in shared memory
 constexpr uint64_t kMaxChunkRows = 1ULL << 26;
 constexpr uint32_t kLocalVerifyMax = 8;          // survivors with <= this many agreeing bytes verify lane-locally
 
 // Sketch layout: tiles of 32 rows; word j (slots 4j..4j+3) of row r lives at
 // (r / 32) * 1024 + j * 32 + (r % 32), so that a warp reads word j of 32 consecutive rows as one 128-byte line.
 __device__ __forceinline__ size_t sketch_index(uint64_t row, int j) { return (row >> 5) * 1024 + (size_t)j * 32 + (row & 31); }
+// 32-bit words of one sketch plane as allocated by ucfp_corpus_create (whole 256-row tiles stay readable)
+inline size_t sketch_plane_words(uint64_t capacity) { return 32 * ((capacity + 31) / 32 * 32 + 512); }
 
-__global__ void sketch_build_kernel(const uint64_t *__restrict__ sigs, uint32_t *sketch, uint64_t first, uint64_t n) {
+// plane 0 = byte 0 of every slot (streamed by the scan), plane 1 = byte 1 (consulted only for rows that survive plane 0
+// while the bounds are still loose: it turns 255 of 256 chance collisions away without touching the 1 KiB row)
+__global__ void sketch_build_kernel(const uint64_t *__restrict__ sigs, uint32_t *sketch, uint32_t *sketch1, uint64_t first, uint64_t n) {
     uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * kSketchWords) return;
     uint64_t row = first + idx / kSketchWords;
@@ -42,6 +47,8 @@ __global__ void sketch_build_kernel(const uint64_t *__restrict__ sigs, uint32_t 
     ulonglong2 a = p[0], b = p[1];
     uint32_t w = (uint32_t)(a.x & 255) | (uint32_t)(a.y & 255) << 8 | (uint32_t)(b.x & 255) << 16 | (uint32_t)(b.y & 255) << 24;
     sketch[sketch_index(row, j)] = w;
+    uint32_t w1 = (uint32_t)((a.x >> 8) & 255) | (uint32_t)((a.y >> 8) & 255) << 8 | (uint32_t)((b.x >> 8) & 255) << 16 | (uint32_t)((b.y >> 8) & 255) << 24;
+    sketch1[sketch_index(row, j)] = w1;
 }
 
 // query sketches, row-major [q][32], plus per-query selection state
@@ -52,6 +59,8 @@ __global__ void jaccard_init_kernel(const uint64_t *__restrict__ q, uint32_t nq,
     uint32_t qi = idx / kSketchWords, j = idx % kSketchWords;
     const uint64_t *p = q + (size_t)qi * kSlots + 4 * j;
     qsketch[idx] = (uint32_t)(p[0] & 255) | (uint32_t)(p[1] & 255) << 8 | (uint32_t)(p[2] & 255) << 16 | (uint32_t)(p[3] & 255) << 24;
+    qsketch[(size_t)nq * kSketchWords + idx] = (uint32_t)((p[0] >> 8) & 255) | (uint32_t)((p[1] >> 8) & 255) << 8 |
+                                               (uint32_t)((p[2] >> 8) & 255) << 16 | (uint32_t)((p[3] >> 8) & 255) << 24;   // plane 1
     if (j == 0) { thr[qi] = 128; kth_id[qi] = UINT64_MAX; count[qi] = 0; flags[qi] = 0; }
 }
 
@@ -84,8 +93,8 @@ __device__ __forceinline__ uint32_t ne_bytes_flags(uint32_t a, uint32_t b) {
     uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
     return (t | x) & 0x80808080u;
 }
-// Differing bytes of 8 word pairs with ONE popcount: word j's flags sit at bit 7 of each byte; g = (g >> 1) + flags
-// moves the older flags down to bits 6..0, so after 8 words every flag has its own bit.
+// Differing bytes of 8 word pairs as ONE bitmap (one popcount counts them): word j's flags sit at bit 7 of each byte;
+// g = (g >> 1) + flags moves the older flags down to bits 6..0, so after 8 words every flag has its own bit.
 __device__ __forceinline__ uint32_t ne_bytes_8words(const uint32_t *w, uint4 q0, uint4 q1) {
     uint32_t g = ne_bytes_flags(w[0], q0.x);
     g = (g >> 1) + ne_bytes_flags(w[1], q0.y);
@@ -95,25 +104,37 @@ __device__ __forceinline__ uint32_t ne_bytes_8words(const uint32_t *w, uint4 q0,
     g = (g >> 1) + ne_bytes_flags(w[5], q1.y);
     g = (g >> 1) + ne_bytes_flags(w[6], q1.z);
     g = (g >> 1) + ne_bytes_flags(w[7], q1.w);
-    return (uint32_t)__popc(g);
+    return g;   // bit 8 b + j set <=> byte b of word j differs
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint64_t *__restrict__ sigs, const uint64_t *__restrict__ ids,
-                    uint64_t id_base, uint64_t row0, uint64_t nrows, const uint64_t *__restrict__ q,
-                    const uint32_t *__restrict__ qsketch, uint32_t nq, SelectState S) {
+jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint32_t *__restrict__ sketch1, const uint64_t *__restrict__ sigs,
+                    const uint64_t *__restrict__ ids, uint64_t id_base, uint64_t row0, uint64_t nrows, const uint64_t *__restrict__ q_all,
+                    const uint32_t *__restrict__ qsketch, uint32_t nq_all, uint32_t q_groups, SelectState S) {
     extern __shared__ uint32_t smem[];
-    uint32_t *sq = smem;                        // [nq][32] query sketches
-    uint32_t *sthr = smem + (size_t)nq * kSketchWords;  // [nq] admission bound (key = 128 - matches)
+    // Small chunks (the first of a batch) have fewer row tiles than the GPU has CTA slots: the queries are then split into
+    // q_groups groups and the grid is tiles x groups.  Large chunks use q_groups == 1 and a persistent grid.
+    const uint32_t grp = q_groups > 1 ? blockIdx.x % q_groups : 0;
+    const uint32_t q_lo = (uint32_t)((uint64_t)nq_all * grp / q_groups), q_hi = (uint32_t)((uint64_t)nq_all * (grp + 1) / q_groups);
+    const uint32_t nq = q_hi - q_lo;
+    const uint64_t *q = q_all + (size_t)q_lo * kSlots;
+    uint32_t *sq = smem;                        // [nq][32] query sketches, plane 0 (byte 0 of every slot)
+    uint32_t *sq1 = smem + (size_t)nq * kSketchWords;   // [nq][32] plane 1 (byte 1)
+    uint32_t *sthr = sq1 + (size_t)nq * kSketchWords;   // [nq] admission bound (key = 128 - matches)
     uint64_t *skid = reinterpret_cast<uint64_t *>(sthr + ((nq + 1) & ~1u));  // [nq] id of the current k-th result
-    for (uint32_t i = threadIdx.x; i < nq * kSketchWords; i += kScanThreads) sq[i] = qsketch[i];
-    for (uint32_t i = threadIdx.x; i < nq; i += kScanThreads) { sthr[i] = S.thr[(size_t)i * S.thr_stride]; skid[i] = S.kth_id[i]; }
+    for (uint32_t i = threadIdx.x; i < nq * kSketchWords; i += kScanThreads) {
+        sq[i] = qsketch[(size_t)q_lo * kSketchWords + i];
+        sq1[i] = qsketch[(size_t)(nq_all + q_lo) * kSketchWords + i];
+    }
+    for (uint32_t i = threadIdx.x; i < nq; i += kScanThreads) { sthr[i] = S.thr[(size_t)(q_lo + i) * S.thr_stride]; skid[i] = S.kth_id[q_lo + i]; }
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const uint64_t row_end = row0 + nrows;
     const uint64_t ntiles = (nrows + kScanThreads - 1) / kScanThreads;   // row0 is a multiple of 32
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint64_t tile0 = q_groups > 1 ? blockIdx.x / q_groups : blockIdx.x;
+    const uint64_t tile_step = q_groups > 1 ? ntiles : gridDim.x;
+    for (uint64_t tile = tile0; tile < ntiles; tile += tile_step) {
         const uint64_t row = row0 + tile * kScanThreads + threadIdx.x;
         const bool valid = row < row_end;
         uint32_t w[kSketchWords];
@@ -127,13 +148,15 @@ jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint64_t *__restr
             const uint32_t thr = sthr[qi];
             const uint32_t need = 128u - thr;               // byte matches a row needs to stay in the race
             uint32_t bm = 0;                                // byte matches so far: an upper bound on slot matches
+            uint32_t ne[4];                                 // per group: bitmap of differing bytes (bit 8 b + j = byte b of word j)
             bool alive = true;
             // four groups of 8 words (32 slots).  After each of the first three, the warp stops as soon as no lane
             // can still reach `need` even if every remaining byte matched -- exact branch-and-bound, and with a
             // meaningful bound almost every (row, query) pair ends after the first group.
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                bm += 32u - ne_bytes_8words(&w[8 * g], qv[2 * g], qv[2 * g + 1]);   // two broadcast LDS.128
+                ne[g] = ne_bytes_8words(&w[8 * g], qv[2 * g], qv[2 * g + 1]);      // two broadcast LDS.128
+                bm += 32u - (uint32_t)__popc(ne[g]);
                 if (g < 3 && !__any_sync(0xffffffffu, valid && bm + (96u - 32u * g) >= need)) { alive = false; break; }
             }
             if (!alive) continue;
@@ -146,22 +169,27 @@ jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint64_t *__restr
                 // lane: only the slots whose low bytes agree can match, so compare just those full 64-bit slots.
                 const bool local = hit && bm <= kLocalVerifyMax;
                 if (local) {
+                    // only the slots whose low bytes agree can match: their positions are the zero bits of ne[].  Byte 1 of the
+                    // slot (sketch plane 1, the tile's 4 KiB stay in L1 across the query loop) settles 255 of 256 chance
+                    // collisions; the 1 KiB row is read only when both bytes agree.
                     const uint64_t *rp = sigs + row * kSlots;
                     const uint64_t *qp = q + (size_t)qi * kSlots;
                     uint32_t m = 0;
 #pragma unroll
-                    for (int j = 0; j < kSketchWords; ++j) {   // fully unrolled: w[] must stay in registers
-                        uint32_t eq = ~ne_bytes_flags(w[j], sq[(size_t)qi * kSketchWords + j]) & 0x80808080u;
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t eq = ~ne[g];
                         while (eq) {
-                            const int slot = 4 * j + ((__ffs(eq) - 1) >> 3);
+                            const int p = __ffs(eq) - 1;
                             eq &= eq - 1;
-                            m += (__ldg(rp + slot) == __ldg(qp + slot));
+                            const int j = 8 * g + (p & 7), b = p >> 3, slot = 4 * j + b;
+                            const uint32_t w1 = __ldg(sketch1 + sketch_index(row, j)), q1 = sq1[(size_t)qi * kSketchWords + j];
+                            if ((((w1 ^ q1) >> (8 * b)) & 255u) == 0) m += (__ldg(rp + slot) == __ldg(qp + slot));
                         }
                     }
                     const uint32_t key = 128u - m;
                     if (key < thr || (key == thr && id < kid)) {
-                        uint32_t pos = atomicAdd(&S.count[qi], 1u);
-                        if (pos < S.cap) S.cand[(size_t)qi * S.cap + pos] = ((uint64_t)key << 40) | row;
+                        uint32_t pos = atomicAdd(&S.count[q_lo + qi], 1u);
+                        if (pos < S.cap) S.cand[(size_t)(q_lo + qi) * S.cap + pos] = ((uint64_t)key << 40) | row;
                     }
                 }
                 // rows with many agreeing bytes (real neighbours): the whole warp verifies one row at a time
@@ -174,8 +202,8 @@ jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint64_t *__restr
                     const uint32_t m = warp_matches(sigs + srow * kSlots, q + (size_t)qi * kSlots, lane);
                     const uint32_t key = 128u - m;
                     if (lane == 0 && (key < thr || (key == thr && sid < kid))) {
-                        uint32_t pos = atomicAdd(&S.count[qi], 1u);
-                        if (pos < S.cap) S.cand[(size_t)qi * S.cap + pos] = ((uint64_t)key << 40) | srow;
+                        uint32_t pos = atomicAdd(&S.count[q_lo + qi], 1u);
+                        if (pos < S.cap) S.cand[(size_t)(q_lo + qi) * S.cap + pos] = ((uint64_t)key << 40) | srow;
                     }
                 }
             }
@@ -205,7 +233,8 @@ int jaccard_on_append(ucfp_corpus *c, uint64_t first_row, uint64_t n) {
     if (n == 0) return UCFP_OK;
     uint64_t items = n * kSketchWords;
     sketch_build_kernel<<<(unsigned)((items + 255) / 256), 256, 0, c->ctx->stream>>>(
-        static_cast<const uint64_t *>(c->rows), reinterpret_cast<uint32_t *>(c->mh_sketch), first_row, n);
+        static_cast<const uint64_t *>(c->rows), reinterpret_cast<uint32_t *>(c->mh_sketch),
+        reinterpret_cast<uint32_t *>(c->mh_sketch) + sketch_plane_words(c->capacity), first_row, n);
     count_launch(c->ctx);
     return check_launch("sketch_build");
 }
@@ -226,22 +255,24 @@ int jaccard_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
     while (cap < 4 * k) cap <<= 1;
     const uint64_t *sigs = static_cast<const uint64_t *>(c->rows);
     const uint32_t *sketch = reinterpret_cast<const uint32_t *>(c->mh_sketch);
+    const uint32_t *sketch1 = sketch + sketch_plane_words(c->capacity);
     const uint64_t *ids = c->id_mode == 1 ? c->ids : nullptr;
     UCFP_CUDA_TRY(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
-    const size_t scan_smem_max = (size_t)kMaxQueriesPerPass * (kSketchWords + 1 + 2) * 4 + 8;
+    const size_t scan_smem_max = (size_t)kMaxQueriesPerPass * (2 * kSketchWords + 1 + 2) * 4 + 8;
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(jaccard_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_max));
     int occ = 0;
     UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jaccard_scan_kernel, kScanThreads, scan_smem_max));
     if (occ < 1) occ = 1;
 
     for (size_t q0 = 0; q0 < nq; q0 += kMaxQueriesPerPass) {
         const uint32_t nqp = (uint32_t)((nq - q0 < kMaxQueriesPerPass) ? nq - q0 : kMaxQueriesPerPass);
-        UCFP_TRY(ctx->qstate.reserve((size_t)nqp * (kSketchWords * 4 + 4 + 8) + 64));
+        UCFP_TRY(ctx->qstate.reserve((size_t)nqp * (2 * kSketchWords * 4 + 4 + 8) + 64));
         UCFP_TRY(ctx->cand.reserve(sizeof(uint64_t) * (size_t)cap * nqp));
         UCFP_TRY(ctx->cand_count.reserve(sizeof(uint32_t) * nqp));
         UCFP_TRY(ctx->flags.reserve(sizeof(uint32_t) * (nqp + 1)));
         uint64_t *kth = ctx->qstate.as<uint64_t>();
         uint32_t *qsk = reinterpret_cast<uint32_t *>(kth + nqp);
-        uint32_t *thr = qsk + (size_t)nqp * kSketchWords;
+        uint32_t *thr = qsk + 2 * (size_t)nqp * kSketchWords;   // two query sketch planes precede the bounds
         uint64_t *cand = ctx->cand.as<uint64_t>();
         uint32_t *count = ctx->cand_count.as<uint32_t>();
         uint32_t *flags = ctx->flags.as<uint32_t>();
@@ -259,17 +290,27 @@ int jaccard_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
             count_launch(ctx);
         };
         compact(seed == N);
-        const uint64_t growth = nqp <= 8 ? 32 : 8;
+        // Chunks scanned under a loose bound cost ~8x more per row (no early exit, every chance collision is verified), and the
+        // bound only tightens between chunks: x4 steps reach a useful bound after ~340 K rows of config 3 instead of ~590 K.
+        static const long env_growth = getenv("UCFP_JACCARD_GROWTH") ? atol(getenv("UCFP_JACCARD_GROWTH")) : 0;   // developer knob
+        const uint64_t growth = env_growth > 1 ? (uint64_t)env_growth : (nqp <= 8 ? 32 : 4);
         uint64_t pos = seed, chunk = (uint64_t)seed * growth;
-        const size_t smem = (size_t)nqp * (kSketchWords + 1 + 2) * 4 + 8;
+        const size_t smem = (size_t)nqp * (2 * kSketchWords + 1 + 2) * 4 + 8;
         while (pos < N) {
             uint64_t n = (N - pos < chunk) ? N - pos : chunk;
             uint64_t ntiles = (n + kScanThreads - 1) / kScanThreads;
-            uint64_t grid = (uint64_t)ctx->sm_count * occ;
-            if (grid > ntiles) grid = ntiles;
+            const uint64_t slots_full = (uint64_t)ctx->sm_count * occ;
+            uint64_t grid = slots_full, q_groups = 1;
+            if (ntiles < slots_full) {   // small chunk: split the queries so that every SM gets work
+                q_groups = (slots_full + ntiles - 1) / ntiles;
+                const uint64_t max_groups = (nqp + 7) / 8;   // at least 8 queries per group
+                if (q_groups > max_groups) q_groups = max_groups;
+                grid = ntiles * q_groups;
+            }
             {
                 ProfScope ps(ctx, UCFP_PROF_JACCARD_SCAN, 1024.0 * (double)n * nqp);
-                jaccard_scan_kernel<<<(unsigned)grid, kScanThreads, smem, st>>>(sketch, sigs, ids, c->id_base, pos, n, qp, qsk, nqp, sel);
+                jaccard_scan_kernel<<<(unsigned)grid, kScanThreads, smem, st>>>(sketch, sketch1, sigs, ids, c->id_base, pos, n, qp, qsk, nqp,
+                                                                               (uint32_t)q_groups, sel);
             }
             count_launch(ctx);
             pos += n;
