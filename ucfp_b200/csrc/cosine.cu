@@ -29,7 +29,7 @@ namespace {
 #include "sm100_ptx.cuh"
 
 constexpr float kCoarseEps = 0.0078125f;   // 2^-7, see header
-constexpr uint32_t kSeedRows = 1024;
+constexpr uint32_t kSeedRows = 512;        // kSmallList (topk_select.cuh): list entries the small rescoring launch sorts
 constexpr uint32_t kMaxQueriesPerPass = 1024;
 constexpr uint64_t kMaxChunkRows = 1ULL << 24;
 constexpr uint32_t kCap = 4096;            // candidate rows per query between two rescoring steps
@@ -97,6 +97,7 @@ struct CosState {
     uint32_t *kept_n;     // [nq]
     float *thr;           // [nq] exact score of the current k-th result (-inf while fewer than k)
     uint32_t *flags;      // [nq]
+    uint32_t *big;        // [nq] list too long for the small rescoring launch
 };
 
 __global__ void cosine_init_kernel(CosState S, uint32_t nq) {
@@ -119,13 +120,21 @@ __device__ __forceinline__ bool hit_before(float sa, uint64_t ia, float sb, uint
 __global__ void __launch_bounds__(512)
 cosine_rescore_kernel(CosState S, uint32_t k, const float *__restrict__ rows, const float *__restrict__ row_norm, uint32_t dim,
                       const float *__restrict__ queries, const float *__restrict__ q_norm, const uint64_t *__restrict__ ids,
-                      uint64_t id_base, int final_pass, uint64_t *ids_out, float *score_out) {
+                      uint64_t id_base, int final_pass, uint64_t *ids_out, float *score_out, uint32_t smem_entries, int second_launch) {
     extern __shared__ unsigned char sm_raw[];
     const uint32_t q = blockIdx.x;
     const uint32_t n_raw = S.count[q];
     const uint32_t n_new = min(n_raw, kCap);
     const uint32_t n_old = S.kept_n[q];
     const uint32_t n = n_new + n_old;
+    // Two launches per step: the first with shared memory for kSmallList entries (16 KiB: many CTAs per SM, one wave) handles
+    // the usual short lists and leaves longer ones, marked in S.big, to the second launch (128 KiB, one CTA per SM), whose
+    // other CTAs return at once.
+    if (!second_launch) {
+        const bool big = n > smem_entries;
+        if (threadIdx.x == 0) S.big[q] = big ? 1u : 0u;
+        if (big) return;
+    } else if (!S.big[q]) return;
     uint32_t P = 1;
     while (P < n) P <<= 1;
     uint64_t *s_id = reinterpret_cast<uint64_t *>(sm_raw);
@@ -427,7 +436,7 @@ int cosine_scan(ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_
         __nv_bfloat16 *q_unit = ctx->qstate.as<__nv_bfloat16>();
         float *q_norm = reinterpret_cast<float *>(ctx->qstate.as<unsigned char>() + off_norm);
         UCFP_TRY(ctx->cand.reserve(4 * (size_t)kCap * nqp));
-        size_t misc2 = (size_t)nqp * (8 * k + 4 + 4 + 4 + 4) + 256;
+        size_t misc2 = (size_t)nqp * (8 * k + 4 + 4 + 4 + 4 + 4) + 256;
         UCFP_TRY(ctx->cand_count.reserve(misc2));
         CosState S;
         S.cand = ctx->cand.as<uint32_t>();
@@ -436,6 +445,7 @@ int cosine_scan(ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_
         S.kept_n = S.count + nqp;
         S.thr = reinterpret_cast<float *>(S.kept_n + nqp);
         S.flags = reinterpret_cast<uint32_t *>(S.thr + nqp);
+        S.big = S.flags + nqp;
         const float *qp = q_dev + q0 * dim;
         uint64_t *ids_out = ids_out_dev + q0 * k;
         float *score_out = score_out_dev + q0 * k;
@@ -447,9 +457,11 @@ int cosine_scan(ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_
         cosine_seed_kernel<<<dim3((seed + 255) / 256, nqp), 256, 0, st>>>(S, seed);
         count_launch(ctx, 3);
         auto rescore = [&](bool final_pass) {
+            cosine_rescore_kernel<<<nqp, 512, 16 * kSmallList, st>>>(S, (uint32_t)k, rows, row_norm, dim, qp, q_norm, ids, c->id_base,
+                                                                    final_pass ? 1 : 0, ids_out, score_out, kSmallList, 0);
             cosine_rescore_kernel<<<nqp, 512, 16 * 8192, st>>>(S, (uint32_t)k, rows, row_norm, dim, qp, q_norm, ids, c->id_base,
-                                                              final_pass ? 1 : 0, ids_out, score_out);
-            count_launch(ctx);
+                                                              final_pass ? 1 : 0, ids_out, score_out, 8192, 1);
+            count_launch(ctx, 2);
         };
         rescore(seed == N);
 

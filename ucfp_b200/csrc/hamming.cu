@@ -527,7 +527,7 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
         UCFP_TRY(ctx->qstate.reserve(sizeof(QSlot) * nqp + sizeof(uint64_t) * nqp));
         UCFP_TRY(ctx->cand.reserve(sizeof(uint64_t) * (size_t)cap * nqp));
         UCFP_TRY(ctx->cand_count.reserve(sizeof(uint32_t) * nqp));
-        UCFP_TRY(ctx->flags.reserve(sizeof(uint32_t) * (nqp + 1)));
+        UCFP_TRY(ctx->flags.reserve(sizeof(uint32_t) * (2 * nqp + 1)));
         QSlot *slots = ctx->qstate.as<QSlot>();
         uint64_t *kth = reinterpret_cast<uint64_t *>(slots + nqp);
         uint64_t *cand = ctx->cand.as<uint64_t>();
@@ -547,12 +547,10 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
         hamming_seed_kernel<<<dim3((seed + 255) / 256, nqp), 256, 0, st>>>(codes, seed, slots, cand, count, cap);
         count_launch(ctx, 2);
 
-        SelectState sel{cand, count, &slots[0].thr, 4, kth, flags, cap};
+        SelectState sel{cand, count, &slots[0].thr, 4, kth, flags, cap, flags + nqp};
         auto compact = [&](bool final_pass) {
-            // smem: 16 B per element of the padded list; lists hold <= cap entries
-            compact_kernel<<<nqp, 512, 16 * (size_t)cap, st>>>(sel, (uint32_t)k, ids, c->id_base, final_pass ? 1 : 0, 0u,
-                                                              ids_out, dist_out);
-            count_launch(ctx);
+            compact_lists(sel, nqp, (uint32_t)k, ids, c->id_base, final_pass, 0u, ids_out, dist_out, st);
+            count_launch(ctx, 2);
         };
         compact(seed == N);
 

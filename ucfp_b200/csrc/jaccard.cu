@@ -269,7 +269,7 @@ int jaccard_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
         UCFP_TRY(ctx->qstate.reserve((size_t)nqp * (2 * kSketchWords * 4 + 4 + 8) + 64));
         UCFP_TRY(ctx->cand.reserve(sizeof(uint64_t) * (size_t)cap * nqp));
         UCFP_TRY(ctx->cand_count.reserve(sizeof(uint32_t) * nqp));
-        UCFP_TRY(ctx->flags.reserve(sizeof(uint32_t) * (nqp + 1)));
+        UCFP_TRY(ctx->flags.reserve(sizeof(uint32_t) * (2 * nqp + 1)));
         uint64_t *kth = ctx->qstate.as<uint64_t>();
         uint32_t *qsk = reinterpret_cast<uint32_t *>(kth + nqp);
         uint32_t *thr = qsk + 2 * (size_t)nqp * kSketchWords;   // two query sketch planes precede the bounds
@@ -279,15 +279,15 @@ int jaccard_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
         const uint64_t *qp = q_dev + q0 * kSlots;
         uint64_t *ids_out = ids_out_dev + q0 * k;
         uint32_t *m_out = m_out_dev + q0 * k;
-        SelectState sel{cand, count, thr, 1, kth, flags, cap};
+        SelectState sel{cand, count, thr, 1, kth, flags, cap, flags + nqp};
 
         jaccard_init_kernel<<<(nqp * kSketchWords + 255) / 256, 256, 0, st>>>(qp, nqp, qsk, thr, kth, count, flags);
         const uint32_t seed = (uint32_t)(N < kSeedRows ? N : kSeedRows);
         jaccard_seed_kernel<<<dim3((seed + 7) / 8, nqp), 256, 0, st>>>(sigs, seed, qp, cand, count, cap);
         count_launch(ctx, 2);
         auto compact = [&](bool final_pass) {
-            compact_kernel<<<nqp, 512, 16 * (size_t)cap, st>>>(sel, (uint32_t)k, ids, c->id_base, final_pass ? 1 : 0, 128u, ids_out, m_out);
-            count_launch(ctx);
+            compact_lists(sel, nqp, (uint32_t)k, ids, c->id_base, final_pass, 128u, ids_out, m_out, st);
+            count_launch(ctx, 2);
         };
         compact(seed == N);
         // Chunks scanned under a loose bound cost ~8x more per row (no early exit, every chance collision is verified), and the

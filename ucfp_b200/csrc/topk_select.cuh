@@ -19,7 +19,10 @@ struct SelectState {      // per query pass, all device pointers
     uint64_t *kth_id;     // [nq]
     uint32_t *flags;      // [nq] 1 = list overflowed, needs exact_select
     uint32_t cap;
+    uint32_t *big;        // [nq] list too long for the small compaction launch
 };
+
+constexpr uint32_t kSmallList = 1024;   // entries the small compaction launch sorts (16 KiB of shared memory)
 
 __device__ __forceinline__ bool cand_before(uint64_t dra, uint64_t ida, uint64_t drb, uint64_t idb) {
     uint32_t da = (uint32_t)(dra >> 40), db = (uint32_t)(drb >> 40);
@@ -27,12 +30,20 @@ __device__ __forceinline__ bool cand_before(uint64_t dra, uint64_t ida, uint64_t
 }
 
 // key_flip: 0 -> the reported value is the key itself; otherwise reported = key_flip - key (Jaccard matches).
+// Two launches per step (compact_lists): the first with shared memory for kSmallList entries (many CTAs per SM, one wave)
+// handles the usual short lists and leaves longer ones, marked in S.big, to the second launch (16 B x cap of shared memory),
+// whose other CTAs return at once.
 __global__ void compact_kernel(SelectState S, uint32_t k, const uint64_t *__restrict__ ids, uint64_t id_base, int final_pass,
-                               uint32_t key_flip, uint64_t *ids_out, uint32_t *keys_out) {
+                               uint32_t key_flip, uint64_t *ids_out, uint32_t *keys_out, uint32_t smem_entries, int second_launch) {
     extern __shared__ uint64_t sm[];
     const uint32_t q = blockIdx.x;
     const uint32_t n_raw = S.count[q];
     const uint32_t n = min(n_raw, S.cap);
+    if (!second_launch) {
+        const bool big = n > smem_entries;
+        if (threadIdx.x == 0) S.big[q] = big ? 1u : 0u;
+        if (big) return;
+    } else if (!S.big[q]) return;
     uint32_t P = 1;
     while (P < n) P <<= 1;
     uint64_t *s_id = sm, *s_dr = sm + P;
@@ -71,6 +82,12 @@ __global__ void compact_kernel(SelectState S, uint32_t k, const uint64_t *__rest
         if (n_raw > S.cap) S.flags[q] = 1;
         if (n >= k) { S.thr[(size_t)q * S.thr_stride] = (uint32_t)(s_dr[k - 1] >> 40); S.kth_id[q] = s_id[k - 1]; }
     }
+}
+
+static inline void compact_lists(const SelectState &S, uint32_t nq, uint32_t k, const uint64_t *ids, uint64_t id_base, bool final_pass,
+                                 uint32_t key_flip, uint64_t *ids_out, uint32_t *keys_out, cudaStream_t st) {
+    compact_kernel<<<nq, 256, 16 * (size_t)kSmallList, st>>>(S, k, ids, id_base, final_pass ? 1 : 0, key_flip, ids_out, keys_out, kSmallList, 0);
+    compact_kernel<<<nq, 512, 16 * (size_t)S.cap, st>>>(S, k, ids, id_base, final_pass ? 1 : 0, key_flip, ids_out, keys_out, S.cap, 1);
 }
 
 __global__ void fill_sentinel_u32_kernel(uint64_t *ids_out, uint32_t *key_out, size_t n) {
