@@ -207,7 +207,7 @@ cosine_rescore_kernel(CosState S, uint32_t k, const float *__restrict__ rows, co
 // the query's admission bound while the next tile's MMAs are already running.
 __global__ void __launch_bounds__(kGemmThreads, 1)
 cosine_coarse_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_q,
-                     uint64_t row0, uint64_t row_end, uint32_t nq, uint32_t n_tile, uint32_t k_chunks, CosState S) {
+                     uint64_t row0, uint64_t row_end, uint32_t nq, uint32_t n_tile, uint32_t k_chunks, uint32_t q_groups, CosState S) {
     extern __shared__ unsigned char smem_raw[];
     // 128B-swizzled operand tiles must start on a 1024-byte boundary of the shared window
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -226,6 +226,11 @@ cosine_coarse_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
     // persistent: this CTA takes corpus tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the three roles walk the same
     // (tile, query tile, K chunk) sequence, so the TMA ring and the two TMEM stages stay full across tile boundaries
     const uint32_t n_tiles = (uint32_t)((row_end - row0 + kTileRows - 1) / kTileRows);
+    // Small chunks (the first of a batch) have fewer row tiles than the GPU has SMs: the query tiles are then split over
+    // q_groups CTAs per row tile (grid = tiles x groups).  Large chunks use q_groups == 1 and a persistent grid.
+    const uint32_t grp = blockIdx.x % q_groups;
+    const uint32_t tile_first = blockIdx.x / q_groups, tile_step = gridDim.x / q_groups;
+    const uint32_t qt0 = q_tiles * grp / q_groups, qt1 = q_tiles * (grp + 1) / q_groups;
 
     for (uint32_t i = threadIdx.x; i < ((nq + 31) & ~31u); i += blockDim.x) s_tau[i] = i < nq ? S.thr[i] - kCoarseEps : INFINITY;
     if (warp == 0 && lane == 0) {
@@ -245,9 +250,9 @@ cosine_coarse_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t it = 0;
-            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (uint32_t tile = tile_first; tile < n_tiles; tile += tile_step) {
                 const uint64_t tile_row = row0 + (uint64_t)tile * kTileRows;
-                for (uint32_t qt = 0; qt < q_tiles; ++qt)
+                for (uint32_t qt = qt0; qt < qt1; ++qt)
                     for (uint32_t kc = 0; kc < k_chunks; ++kc, ++it) {
                         const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                         mbar_wait(&empty[s], ph ^ 1);
@@ -262,8 +267,8 @@ cosine_coarse_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
         // instruction descriptor: D = f32, A = B = bf16, both K-major, N = n_tile, M = 128
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((n_tile >> 3) << 17) | ((kTileRows >> 4) << 24);
         uint32_t it = 0, acc_it = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-            for (uint32_t qt = 0; qt < q_tiles; ++qt, ++acc_it) {
+        for (uint32_t tile = tile_first; tile < n_tiles; tile += tile_step)
+            for (uint32_t qt = qt0; qt < qt1; ++qt, ++acc_it) {
                 const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
                 mbar_wait(&tempty[as], aph ^ 1);
                 tcgen05_fence_after();
@@ -288,10 +293,10 @@ cosine_coarse_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
         // ===== epilogue: 4 warps, warp w reads TMEM lanes 32*(w%4).. (its hardware quadrant) =====
         const uint32_t quad = warp & 3;
         uint32_t acc_it = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t tile = tile_first; tile < n_tiles; tile += tile_step) {
             const uint64_t my_row = row0 + (uint64_t)tile * kTileRows + quad * 32 + lane;
             const bool valid = my_row < row_end;
-            for (uint32_t qt = 0; qt < q_tiles; ++qt, ++acc_it) {
+            for (uint32_t qt = qt0; qt < qt1; ++qt, ++acc_it) {
                 const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
                 mbar_wait(&tfull[as], aph);
                 tcgen05_fence_after();
@@ -457,7 +462,7 @@ int cosine_scan(ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_
         cosine_seed_kernel<<<dim3((seed + 255) / 256, nqp), 256, 0, st>>>(S, seed);
         count_launch(ctx, 3);
         auto rescore = [&](bool final_pass) {
-            cosine_rescore_kernel<<<nqp, 512, 16 * kSmallList, st>>>(S, (uint32_t)k, rows, row_norm, dim, qp, q_norm, ids, c->id_base,
+            cosine_rescore_kernel<<<nqp, 256, 16 * kSmallList, st>>>(S, (uint32_t)k, rows, row_norm, dim, qp, q_norm, ids, c->id_base,
                                                                     final_pass ? 1 : 0, ids_out, score_out, kSmallList, 0);
             cosine_rescore_kernel<<<nqp, 512, 16 * 8192, st>>>(S, (uint32_t)k, rows, row_norm, dim, qp, q_norm, ids, c->id_base,
                                                               final_pass ? 1 : 0, ids_out, score_out, 8192, 1);
@@ -473,8 +478,14 @@ int cosine_scan(ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_
             uint32_t tiles = (uint32_t)((n + kTileRows - 1) / kTileRows);
             {
                 ProfScope ps(ctx, UCFP_PROF_COSINE_SCAN, 2.0 * (double)n * dim * nqp);
-                const uint32_t grid = tiles < (uint32_t)ctx->sm_count ? tiles : (uint32_t)ctx->sm_count;   // 1 CTA per SM (smem), persistent
-                cosine_coarse_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(map_rows, map_q, pos, pos + n, nqp, n_tile, dim_pad / kBlockK, S);
+                uint32_t grid = tiles < (uint32_t)ctx->sm_count ? tiles : (uint32_t)ctx->sm_count;   // 1 CTA per SM (smem), persistent
+                uint32_t q_groups = 1;
+                const uint32_t q_tiles = (nqp + n_tile - 1) / n_tile;
+                if (2 * tiles <= (uint32_t)ctx->sm_count && q_tiles > 1) {   // small chunk: one CTA per (row tile, group of query tiles)
+                    q_groups = (uint32_t)ctx->sm_count / tiles < q_tiles ? (uint32_t)ctx->sm_count / tiles : q_tiles;
+                    grid = tiles * q_groups;
+                }
+                cosine_coarse_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(map_rows, map_q, pos, pos + n, nqp, n_tile, dim_pad / kBlockK, q_groups, S);
             }
             count_launch(ctx);
             pos += n;
