@@ -192,7 +192,7 @@ constexpr int kMmaColsPerWarp = kMmaRows / (kMmaEpiWarps / 4);
 constexpr uint32_t kMmaMaxQueries = 1024;
 constexpr uint32_t kMmaMinQueries = 64;              // measured crossover: the POPC scan costs 0.24 ms per query and 1 B rows, the tensor scan >= 15 ms per batch
 constexpr uint64_t kMmaMinChunkRows = 1ULL << 16;    // smaller chunks (fewer tiles than SMs, very loose bounds) stay on the POPC scan
-constexpr size_t kMmaSmem = (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes + kMmaStages * kMmaCBytes + kMmaMaxQueries * (16 + 8 + 4) + 256 + 1024;
+constexpr size_t kMmaSmem = (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes + kMmaStages * kMmaCBytes + kMmaMaxQueries * (16 + 8 + 4 + 4) + 256 + 1024;
 static_assert(kMmaMaxQueries <= kMaxQueriesPerPass || kMaxQueriesPerPass <= kMmaMaxQueries, "");
 static_assert(kMmaColsPerWarp == 64, "one packed tcgen05.ld per warp and accumulator tile");
 
@@ -318,7 +318,8 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
     uint4 *s_q = reinterpret_cast<uint4 *>(smem + (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes + kMmaStages * kMmaCBytes);   // [1024] query slots {lo, hi, thr, -}
     uint64_t *s_kid = reinterpret_cast<uint64_t *>(s_q + kMmaMaxQueries);              // [1024] id of the current k-th result
     uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_kid + kMmaMaxQueries);            // [1024] bound of the hot test, 0xFFFFFFFF = never
-    uint64_t *cfull = reinterpret_cast<uint64_t *>(s_thr + kMmaMaxQueries);
+    uint32_t *s_bnd = s_thr + kMmaMaxQueries;                                          // [1024] the hot test's two s16 bounds, see below
+    uint64_t *cfull = reinterpret_cast<uint64_t *>(s_bnd + kMmaMaxQueries);
     uint64_t *cempty = cfull + kMmaMaxImgStages, *tfull = cempty + kMmaMaxImgStages, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
     const uint32_t n_tiles = (uint32_t)((A.row_end - A.row0 + kMmaTileCodes - 1) / kMmaTileCodes);
@@ -333,7 +334,17 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
         // admitted: the hot test may use thr - 1 (about 4x fewer trips through the cold path).
         uint32_t hot = s.thr;
         if (A.ids == nullptr && kid != UINT64_MAX) hot = s.thr == 0 ? 0xFFFFFFFFu : s.thr - 1;
-        s_thr[q] = q < A.nq ? hot : 0xFFFFFFFFu;
+        if (q >= A.nq) hot = 0xFFFFFFFFu;
+        s_thr[q] = hot;
+        // The hot test works on the 16-bit image of an accumulator: field y = the value itself, field x = its low 7 bits moved to
+        // the top of the halfword by * 512 (the upper halfword of a register then carries < 512 of junk from the lower one, hence
+        // the | 0x1FF).  It fires when  max(y) >= hi16  or  min(x) <= lo16;  stored as hi16 - 1 and lo16 + 1 so that both become
+        // "max/min against the bound changes the bound".  never: neither bound can be crossed by |D| <= 4160; thr >= 64: always.
+        const int32_t tau = 64 - 2 * (int32_t)hot;
+        int32_t hi16 = 64 * (tau - 1), lo16 = (-tau * 512) | 0x1FF;
+        if (hot == 0xFFFFFFFFu) { hi16 = 0x7FFF; lo16 = -0x7FFF; }
+        else if (hot >= 64) { hi16 = -0x7FFF; lo16 = 0; }
+        s_bnd[q] = ((uint32_t)(uint16_t)(lo16 + 1) << 16) | (uint32_t)(uint16_t)(hi16 - 1);
     }
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < n_stages; ++s) { mbar_init(&cfull[s], kPreExpanded ? 1 : kMmaExpWarps * 32); mbar_init(&cempty[s], 1); }
@@ -423,13 +434,8 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
             for (uint32_t mt = 0; mt < q_tiles; ++mt, ++acc_it) {
                 const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
                 const uint32_t q = mt * kMmaQTile + quad * 32 + lane;
-                const uint32_t thr = s_thr[q];
-                const bool pad = thr == 0xFFFFFFFFu;
-                const int32_t tau = 64 - 2 * (int32_t)thr;
-                // s16 bounds for the two fields of a 16-bit accumulator image: y = the value itself, x = its low 7 bits moved to the top
-                // of the halfword by * 512 (the upper halfword then carries < 512 of junk from the lower one, hence the | 0x1FF)
-                const int32_t hi16 = pad ? 0x7FFF : 64 * (tau - 1);
-                const int32_t lo16 = pad ? -0x8000 : (thr >= 64 ? 0x7FFF : ((-tau * 512) | 0x1FF));
+                const uint32_t bnd = s_bnd[q];
+                const uint32_t hi_pk = __byte_perm(bnd, bnd, 0x1010), lo_pk = __byte_perm(bnd, bnd, 0x3232);   // hi16 - 1, lo16 + 1 in both halfwords
                 mbar_wait_sleep(&tfull[as], aph);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * kMmaRows + part * kMmaColsPerWarp;
@@ -448,14 +454,13 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
                     }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { mx[j] = __vmaxs2(mx[j], p[28 + j]); mn[j] = __vmins2(mn[j], p[28 + j] * 512u); }
-                const uint32_t m2 = __vmaxs2(__vimax3_s16x2(mx[0], mx[1], mx[2]), mx[3]);
-                const uint32_t n2 = __vmins2(__vimin3_s16x2(mn[0], mn[1], mn[2]), mn[3]);
-                const bool fired = (int32_t)(int16_t)(m2 & 0xFFFFu) >= hi16 || ((int32_t)m2 >> 16) >= hi16 ||
-                                   (int32_t)(int16_t)(n2 & 0xFFFFu) <= lo16 || ((int32_t)n2 >> 16) <= lo16;
+                const uint32_t m2 = __vimax3_s16x2(__vimax3_s16x2(mx[0], mx[1], mx[2]), mx[3], hi_pk);
+                const uint32_t n2 = __vimin3_s16x2(__vimin3_s16x2(mn[0], mn[1], mn[2]), mn[3], lo_pk);
+                const bool fired = (m2 != hi_pk) | (n2 != lo_pk);   // some halfword exceeded hi16 - 1 / fell below lo16 + 1
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);   // the accumulators now live in registers: release the stage first
-                if (fired) hamming_mma_settle(p, first_row, pad ? 0u : thr, q, A, s_q, s_kid);
+                if (fired) { const uint32_t thr = s_thr[q]; hamming_mma_settle(p, first_row, thr == 0xFFFFFFFFu ? 0u : thr, q, A, s_q, s_kid); }
             }
         }
     }
