@@ -317,8 +317,7 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
     const uint32_t stage_bytes = kPreExpanded ? kMmaImgBytes : kMmaCBytes;
     uint4 *s_q = reinterpret_cast<uint4 *>(smem + (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes + kMmaStages * kMmaCBytes);   // [1024] query slots {lo, hi, thr, -}
     uint64_t *s_kid = reinterpret_cast<uint64_t *>(s_q + kMmaMaxQueries);              // [1024] id of the current k-th result
-    uint32_t *s_thr = reinterpret_cast<uint32_t *>(s_kid + kMmaMaxQueries);            // [1024] bound of the hot test, 0xFFFFFFFF = never
-    uint32_t *s_bnd = s_thr + kMmaMaxQueries;                                          // [1024] the hot test's two s16 bounds, see below
+    uint2 *s_bnd = reinterpret_cast<uint2 *>(s_kid + kMmaMaxQueries);                  // [1024] the hot test's two s16 bounds, see below
     uint64_t *cfull = reinterpret_cast<uint64_t *>(s_bnd + kMmaMaxQueries);
     uint64_t *cempty = cfull + kMmaMaxImgStages, *tfull = cempty + kMmaMaxImgStages, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
@@ -335,7 +334,6 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
         uint32_t hot = s.thr;
         if (A.ids == nullptr && kid != UINT64_MAX) hot = s.thr == 0 ? 0xFFFFFFFFu : s.thr - 1;
         if (q >= A.nq) hot = 0xFFFFFFFFu;
-        s_thr[q] = hot;
         // The hot test works on the 16-bit image of an accumulator: field y = the value itself, field x = its low 7 bits moved to
         // the top of the halfword by * 512 (the upper halfword of a register then carries < 512 of junk from the lower one, hence
         // the | 0x1FF).  It fires when  max(y) >= hi16  or  min(x) <= lo16;  stored as hi16 - 1 and lo16 + 1 so that both become
@@ -344,7 +342,8 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
         int32_t hi16 = 64 * (tau - 1), lo16 = (-tau * 512) | 0x1FF;
         if (hot == 0xFFFFFFFFu) { hi16 = 0x7FFF; lo16 = -0x7FFF; }
         else if (hot >= 64) { hi16 = -0x7FFF; lo16 = 0; }
-        s_bnd[q] = ((uint32_t)(uint16_t)(lo16 + 1) << 16) | (uint32_t)(uint16_t)(hi16 - 1);
+        const uint32_t hi1 = (uint16_t)(hi16 - 1), lo1 = (uint16_t)(lo16 + 1);
+        s_bnd[q] = make_uint2(hi1 << 16 | hi1, lo1 << 16 | lo1);   // both halfwords
     }
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < n_stages; ++s) { mbar_init(&cfull[s], kPreExpanded ? 1 : kMmaExpWarps * 32); mbar_init(&cempty[s], 1); }
@@ -428,17 +427,17 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
     } else {
         // ===== epilogue: warp -> TMEM lane quadrant (warp % 4) and 64 of the 256 columns =====
         const uint32_t quad = warp & 3, part = (warp - 1 - kMmaExpWarps) >> 2;
-        uint32_t acc_it = 0;
+        uint32_t as = 0, aph = 0;   // accumulator stage in use and its mbarrier phase
+        const uint32_t taddr0 = tmem_base + ((quad * 32u) << 16) + part * kMmaColsPerWarp;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const uint64_t first_row = A.row0 + (uint64_t)tile * kMmaTileCodes + 2 * part * kMmaColsPerWarp;
-            for (uint32_t mt = 0; mt < q_tiles; ++mt, ++acc_it) {
-                const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+            for (uint32_t mt = 0; mt < q_tiles; ++mt) {
                 const uint32_t q = mt * kMmaQTile + quad * 32 + lane;
-                const uint32_t bnd = s_bnd[q];
-                const uint32_t hi_pk = __byte_perm(bnd, bnd, 0x1010), lo_pk = __byte_perm(bnd, bnd, 0x3232);   // hi16 - 1, lo16 + 1 in both halfwords
+                const uint2 bnd = s_bnd[q];
+                const uint32_t hi_pk = bnd.x, lo_pk = bnd.y;   // hi16 - 1, lo16 + 1 in both halfwords
                 mbar_wait_sleep(&tfull[as], aph);
                 tcgen05_fence_after();
-                const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * kMmaRows + part * kMmaColsPerWarp;
+                const uint32_t taddr = taddr0 + as * kMmaRows;
                 uint32_t p[32];   // register c = (D of column 2c+1) << 16 | (D of column 2c) & 0xFFFF
                 tmem_ld64_pack16_async(taddr, p);
                 tmem_ld_wait(p);
@@ -460,7 +459,11 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);   // the accumulators now live in registers: release the stage first
-                if (fired) { const uint32_t thr = s_thr[q]; hamming_mma_settle(p, first_row, thr == 0xFFFFFFFFu ? 0u : thr, q, A, s_q, s_kid); }
+                as ^= 1; aph ^= as ^ 1;
+                if (fired) {   // the bound of the hot test, recomputed: thr - 1 under implicit ids (0 when nothing can be admitted)
+                    const uint32_t thr = s_q[q].z;
+                    hamming_mma_settle(p, first_row, (A.ids == nullptr && s_kid[q] != UINT64_MAX) ? (thr == 0 ? 0u : thr - 1) : thr, q, A, s_q, s_kid);
+                }
             }
         }
     }
