@@ -529,6 +529,7 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
     UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
     static const bool env_no_mma = getenv("UCFP_HAMMING_NO_MMA") != nullptr;   // developer switches: POPC scan only /
     static const bool env_no_ops = getenv("UCFP_HAMMING_NO_OPS") != nullptr;   // expand codes in the kernel although operand rows exist
+    static const long env_img_maxq = getenv("UCFP_HAMMING_IMG_MAXQ") ? atol(getenv("UCFP_HAMMING_IMG_MAXQ")) : 7 * kMmaQTile;
 
     for (size_t q0 = 0; q0 < nq; q0 += kMaxQueriesPerPass) {
         const uint32_t nqp = (uint32_t)((nq - q0 < kMaxQueriesPerPass) ? nq - q0 : kMaxQueriesPerPass);
@@ -591,7 +592,7 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
                 const MmaScanArgs margs{codes, reinterpret_cast<const uint4 *>(c->ham_ops), ids, c->id_base, pos, pos + n, slots, kth, nqp, cand, count, cap};
                 // With all eight query tiles in use a 512-code stage lasts ~3 300 clk and the in-kernel expansion hides completely
                 // behind it (measured 41.8 vs 43.0 ms per 1 B rows); below that the ready-made images win (7.6 vs 13.5 ms at 64-128 queries).
-                if (c->ham_ops && !env_no_ops && pos % kMmaTileCodes == 0 && nqp <= 7 * kMmaQTile) hamming_mma_scan_kernel<true><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
+                if (c->ham_ops && !env_no_ops && pos % kMmaTileCodes == 0 && (long)nqp <= env_img_maxq) hamming_mma_scan_kernel<true><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
                 else hamming_mma_scan_kernel<false><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
             } else {
                 ProfScope ps(ctx, UCFP_PROF_HAMMING_SCAN, 8.0 * (double)n * nqp);
