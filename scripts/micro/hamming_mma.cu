@@ -1,8 +1,19 @@
-// Developer microbenchmark: batched Hamming filter on the int8 tensor pipe (tcgen05.mma kind::i8, sm_100a).
-// Codes and queries are expanded to +-1 int8 vectors, so that  D = sum a_i b_i = 64 - 2 * dist  lands in TMEM
-// as an exact s32; the epilogue keeps only "any D >= 64 - 2 thr_q" per 32 columns.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o hamming_mma hamming_mma.cu
-//   ./hamming_mma [rows_log2=26] [nq=1024] [mode=0]     mode 1: epilogue without TMEM loads, 2: loads only
+// Developer microbenchmark: batched Hamming filter on the int8 tensor pipe (tcgen05.mma kind::i8, sm_100a).  This is the
+// playground the product kernel (ucfp_b200/csrc/hamming.cu, hamming_mma_scan_kernel) was developed in; it checks every
+// variant against a brute-force POPC kernel (count + checksum of admitted pairs) and times it.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo [-DVARIANT=v -DEPI_WARPS=w -DSPLIT=s -DSW64=b] -o hm hamming_mma.cu
+//   ./hm [rows_log2=26] [nq=1024] [mode=0]     mode 1: epilogue without TMEM loads (MMA-only bound), 2: loads + trivial max
+// Variants (all measured on one B200, 134 M rows x 1024 queries, thr 10-14, 10^12 pairs/s):
+//   VARIANT 3      one code per operand row, packed 16-bit tcgen05.ld, half2 max ................. 13.3   (MMA-only 22.6)
+//   VARIANT 0      two codes per row (-a + 64 b), 32-bit tcgen05.ld, s32 min/max, 8 / 16 warps ... 14.7 / 14.1
+//   VARIANT 2      two codes per row, packed 16-bit tcgen05.ld, four shifted s32 fields ........... 12.6 / 15.3
+//   VARIANT 4      as 2 with the y fields by half2 max on the raw s16 patterns .................... 15.8
+//   VARIANT 5      as 2 with VIMNMX3.S16x2 on both halfwords (1 multiply + 1 min/max per register) . 18.0 / 18.8   <- product
+//   VARIANT 5 + SPLIT=1   four 128-column TMEM stages, two epilogue groups on alternate tiles ..... 17.0
+//   VARIANT 5 + SW64=1    operand rows as 64-byte rows, SWIZZLE_64B descriptor (validates the stage-image layout) 18.8
+//   MMA only (mode 1), two codes per row: 44-49; MMA + packed tcgen05.ld (mode 2): 34; unpacked: 20-26.
+// The product adds: sleeping mbarrier waits, cold path from registers after the stage hand-back, per-query bounds in shared
+// memory, stage images via TMA: 28 x 10^12 pairs/s in the full top-k scan.
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>
