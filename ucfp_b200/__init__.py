@@ -9,3 +9,4 @@ from .runtime import Context, Corpus  # noqa: F401
 from . import image, sharding  # noqa: F401,E402
 from .index import GpuIndexBackend  # noqa: F401,E402
 from .matcher import Matcher, rrf, rrf_with_sources  # noqa: F401,E402
+from . import server  # noqa: F401,E402

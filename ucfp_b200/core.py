@@ -63,6 +63,10 @@ class Query:
     filter: Optional[bytes] = None
     rrf_k: int = 60
     explain: bool = False
+    # not in the reference: the two query kinds its stored fingerprints call for
+    hash: Optional[int] = None              # 64-bit perceptual-hash code -> Hamming top-k
+    hash_algorithm: Optional[str] = None    # algorithm tag of the stored fingerprints to search (image.rs:38-46)
+    signature: Optional[List[int]] = None   # MinHash-128 slots -> Jaccard top-k
 
 
 class Error(Exception):

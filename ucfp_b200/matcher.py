@@ -56,6 +56,10 @@ class Matcher:
             fused = self.index.knn(q.tenant_id, q.vector, q.k, q.filter)
         elif has_terms:
             fused = self.index.bm25(q.tenant_id, q.terms, q.k, q.filter)
+        elif q.hash is not None:           # new arms (absent upstream): the HashIndex queries of SURVEY 8b
+            fused = self.index.hamming_knn(q.tenant_id, q.hash_algorithm, q.hash, q.k)
+        elif q.signature is not None:
+            fused = self.index.jaccard_knn(q.tenant_id, q.signature, q.k)
         else:
             fused = []
         fused = fused[: q.k]
