@@ -11,6 +11,7 @@
 
 #include <cstdint>
 #include <cstring>
+#include <array>
 #include <map>
 #include <optional>
 #include <stdexcept>
@@ -61,6 +62,10 @@ struct Query {  // src/core/mod.rs:153-189
     std::vector<std::string> terms;
     uint32_t rrf_k = 60;
     bool explain = false;
+    // not in the reference: the two query kinds its stored fingerprints call for
+    std::optional<uint64_t> hash;                       // 64-bit perceptual-hash code -> Hamming top-k
+    std::string hash_algorithm;                         // algorithm tag of the stored fingerprints to search (image.rs:38-46)
+    std::optional<std::array<uint64_t, 128>> signature; // MinHash-128 slots -> Jaccard top-k
 };
 
 namespace detail {
@@ -137,7 +142,11 @@ inline std::vector<Record> fingerprint_batch_rgb(const Gpu &gpu, const std::vect
 class GpuIndexBackend {
    public:
     explicit GpuIndexBackend(const Gpu &gpu, uint64_t capacity_per_tenant = 1u << 20) : gpu_(gpu), cap_(capacity_per_tenant) {}
-    ~GpuIndexBackend() { for (auto &kv : vec_) ucfp_corpus_destroy(kv.second); }
+    ~GpuIndexBackend() {
+        for (auto &kv : vec_) ucfp_corpus_destroy(kv.second);
+        for (auto &kv : ham_) ucfp_corpus_destroy(kv.second);
+        for (auto &kv : mh_) ucfp_corpus_destroy(kv.second);
+    }
 
     void upsert(const std::vector<Record> &batch) {  // src/index/mod.rs:20
         for (const Record &r : batch) {
@@ -161,10 +170,49 @@ class GpuIndexBackend {
         return hits;
     }
 
+    // ---- new: HashIndex (SURVEY 8b "new API the reference lacks") ----
+    // 64-bit global hash of a stored image fingerprint (offset 32 of the 168-byte blob; PHash of a 536-byte bundle = offset 232)
+    void upsert_hash(uint32_t tenant_id, const std::string &algorithm, uint64_t record_id, uint64_t code) {
+        ucfp_corpus *&c = ham_[{tenant_id, algorithm}];
+        if (!c) detail::check(ucfp_corpus_create(gpu_.raw(), UCFP_KIND_HAMMING64, 0, cap_, &c), "Index");
+        detail::check(ucfp_corpus_append(c, &record_id, &code, 1), "Index");
+    }
+    void upsert_signature(uint32_t tenant_id, uint64_t record_id, const std::array<uint64_t, 128> &slots) {
+        ucfp_corpus *&c = mh_[tenant_id];
+        if (!c) detail::check(ucfp_corpus_create(gpu_.raw(), UCFP_KIND_MINHASH128, 0, cap_, &c), "Index");
+        detail::check(ucfp_corpus_append(c, &record_id, slots.data(), 1), "Index");
+    }
+    // Hit.score = 1 - dist / 64
+    std::vector<Hit> hamming_knn(uint32_t tenant_id, const std::string &algorithm, uint64_t code, size_t k) const {
+        std::vector<Hit> hits;
+        auto it = ham_.find({tenant_id, algorithm});
+        if (it == ham_.end() || k == 0) return hits;
+        std::vector<uint64_t> ids(k);
+        std::vector<uint32_t> dist(k);
+        detail::check(ucfp_scan_hamming(it->second, &code, 1, k, ids.data(), dist.data()), "Index");
+        for (size_t i = 0; i < k && ids[i] != UCFP_ID_NONE; ++i)
+            hits.push_back(Hit{tenant_id, ids[i], 1.0f - (float)dist[i] / 64.0f, HitSource::Vector, {}, {}, {}, {}});
+        return hits;
+    }
+    // Hit.score = matches / 128
+    std::vector<Hit> jaccard_knn(uint32_t tenant_id, const std::array<uint64_t, 128> &slots, size_t k) const {
+        std::vector<Hit> hits;
+        auto it = mh_.find(tenant_id);
+        if (it == mh_.end() || k == 0) return hits;
+        std::vector<uint64_t> ids(k);
+        std::vector<uint32_t> matches(k);
+        detail::check(ucfp_scan_jaccard(it->second, slots.data(), 1, k, ids.data(), matches.data()), "Index");
+        for (size_t i = 0; i < k && ids[i] != UCFP_ID_NONE; ++i)
+            hits.push_back(Hit{tenant_id, ids[i], (float)matches[i] / 128.0f, HitSource::Vector, {}, {}, {}, {}});
+        return hits;
+    }
+
    private:
     const Gpu &gpu_;
     uint64_t cap_;
     std::map<std::pair<uint32_t, size_t>, ucfp_corpus *> vec_;
+    std::map<std::pair<uint32_t, std::string>, ucfp_corpus *> ham_;
+    std::map<uint32_t, ucfp_corpus *> mh_;
 };
 
 class Matcher {  // src/matcher/mod.rs:140-207, vector arm; BM25 / hybrid stay on the host backend
@@ -174,6 +222,8 @@ class Matcher {  // src/matcher/mod.rs:140-207, vector arm; BM25 / hybrid stay o
         std::vector<Hit> fused;
         if (q.vector && q.terms.empty()) fused = index_.knn(q.tenant_id, *q.vector, q.k);
         else if (q.vector || !q.terms.empty()) throw Error("Unsupported", "bm25 / hybrid arms run on the host backend");
+        else if (q.hash) fused = index_.hamming_knn(q.tenant_id, q.hash_algorithm, *q.hash, q.k);      // new arms, absent upstream
+        else if (q.signature) fused = index_.jaccard_knn(q.tenant_id, *q.signature, q.k);
         if (fused.size() > q.k) fused.resize(q.k);
         return fused;
     }
