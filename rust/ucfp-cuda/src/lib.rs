@@ -97,8 +97,43 @@ pub mod image {
     }
 }
 
-/// Scan seam: cosine k-NN behind `IndexBackend::knn`, one HBM corpus per (tenant, dim).
-pub struct GpuIndexBackend { gpu: Gpu, vectors: Mutex<HashMap<(u32, usize), *mut sys::ucfp_corpus>> }
+/// Scan seam: cosine k-NN behind `IndexBackend::knn`, one HBM corpus per (tenant, dim); Hamming corpora per
+/// (tenant, algorithm tag) and MinHash corpora per tenant behind `HashIndex`.
+pub struct GpuIndexBackend {
+    gpu: Gpu,
+    vectors: Mutex<HashMap<(u32, usize), *mut sys::ucfp_corpus>>,
+    hashes: Mutex<HashMap<(u32, String), *mut sys::ucfp_corpus>>,
+    signatures: Mutex<HashMap<u32, *mut sys::ucfp_corpus>>,
+}
+
+/// The queries the reference stores fingerprints for but cannot ask (`src/index/mod.rs:29-35` has `knn` only).
+/// `Hit::score` = `1 - dist / 64` (Hamming) or `matches / 128` (Jaccard), `source = HitSource::Vector`.
+pub trait HashIndex {
+    fn hamming_knn_blocking(&self, tenant_id: u32, algorithm: &str, code: u64, k: usize) -> Result<Vec<Hit>>;
+    fn jaccard_knn_blocking(&self, tenant_id: u32, signature: &[u64; 128], k: usize) -> Result<Vec<Hit>>;
+}
+
+fn hit(tenant_id: u32, record_id: u64, score: f32) -> Hit {
+    Hit { tenant_id, record_id, score, source: HitSource::Vector, vector_score: None, bm25_score: None, vector_rank: None,
+          bm25_rank: None, term_hits: Vec::new() }
+}
+
+impl HashIndex for GpuIndexBackend {
+    fn hamming_knn_blocking(&self, tenant_id: u32, algorithm: &str, code: u64, k: usize) -> Result<Vec<Hit>> {
+        if k == 0 { return Ok(Vec::new()); }
+        let Some(&corpus) = self.hashes.lock().unwrap().get(&(tenant_id, algorithm.to_string())) else { return Ok(Vec::new()) };
+        let (mut ids, mut dist) = (vec![0u64; k], vec![0u32; k]);
+        check_index(unsafe { sys::ucfp_scan_hamming(corpus, &code, 1, k, ids.as_mut_ptr(), dist.as_mut_ptr()) })?;
+        Ok(ids.into_iter().zip(dist).filter(|(id, _)| *id != sys::UCFP_ID_NONE).map(|(id, d)| hit(tenant_id, id, 1.0 - d as f32 / 64.0)).collect())
+    }
+    fn jaccard_knn_blocking(&self, tenant_id: u32, signature: &[u64; 128], k: usize) -> Result<Vec<Hit>> {
+        if k == 0 { return Ok(Vec::new()); }
+        let Some(&corpus) = self.signatures.lock().unwrap().get(&tenant_id) else { return Ok(Vec::new()) };
+        let (mut ids, mut m) = (vec![0u64; k], vec![0u32; k]);
+        check_index(unsafe { sys::ucfp_scan_jaccard(corpus, signature.as_ptr(), 1, k, ids.as_mut_ptr(), m.as_mut_ptr()) })?;
+        Ok(ids.into_iter().zip(m).filter(|(id, _)| *id != sys::UCFP_ID_NONE).map(|(id, x)| hit(tenant_id, id, x as f32 / 128.0)).collect())
+    }
+}
 unsafe impl Send for GpuIndexBackend {} unsafe impl Sync for GpuIndexBackend {}
 
 impl GpuIndexBackend {
