@@ -154,7 +154,10 @@ enum {
     UCFP_KIND_COSINE = 3      /* row = dim f32 (Record::embedding, src/core/mod.rs:58)     */
 };
 
-/* Allocates HBM for up to `capacity` rows.  `dim` is used by UCFP_KIND_COSINE only. */
+/* Allocates HBM for up to `capacity` rows.  `dim` is used by UCFP_KIND_COSINE only.  Bytes per row of capacity, side
+ * arrays included: HAMMING64 8 + 32 (operand rows of the tensor-core scan; optional -- if that allocation is refused the
+ * corpus still works and the scan expands codes on the fly), +8 once explicit ids are appended; MINHASH128 1024 + 256
+ * (two sketch planes); COSINE 4*dim + 2*dim_pad + 4. */
 UCFP_API int ucfp_corpus_create(ucfp_ctx *ctx, int kind, uint32_t dim, uint64_t capacity, ucfp_corpus **out);
 UCFP_API void ucfp_corpus_destroy(ucfp_corpus *c);
 /* Appends n rows (copied).  ids == NULL means record_id = id_base + row index, where id_base is the
