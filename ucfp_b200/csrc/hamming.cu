@@ -18,7 +18,7 @@
 //   compact   after every chunk (tightens thr); the last one writes the results.
 //   Batches of >= kMmaMinQueries queries run the large chunks on the int8 tensor pipe instead
 //   (hamming_mma_scan_kernel below): the POPC pipe (16 lanes/clk/SM) caps the loop above at ~14
-//   pairs/clk/SM, the tensor-core form filters ~57 pairs/clk/SM; same admission rule, same lists.
+//   pairs/clk/SM, the tensor-core form filters ~96 pairs/clk/SM; same admission rule, same lists.
 // A list that overflows its capacity (adversarial duplicates with descending ids) is
 // flagged; flagged queries are recomputed by the exact multi-pass selection in
 // topk_select.cuh (histogram of distances + radix select on ids), so the result is
@@ -39,7 +39,7 @@ namespace {
 constexpr int kScanThreads = 256;
 constexpr int kCodesPerThread = 8;                 // 4 x LDG.128 in flight per thread
 constexpr int kTileCodes = kScanThreads * kCodesPerThread;
-constexpr uint32_t kSeedRows = 1024;               // multiple of 2 (keeps 16-byte alignment of chunk starts); raised to k when k is larger
+constexpr uint32_t kSeedRows = 1024;               // a multiple of 512: chunk starts stay aligned to the tensor scan's stage images; 2k for large k
 constexpr uint32_t kMaxQueriesPerPass = 1024;      // POPC scan: 16 B/query of shared memory; tensor scan: 8 resident 128-query tiles
 constexpr uint64_t kMaxChunkRows = 1ULL << 28;
 
@@ -173,10 +173,11 @@ hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restri
 // with tau = 64 - 2 * thr.  The epilogue never decodes distances: per thread (= one query) it reads 64 accumulators
 // as 32 registers of s16 pairs (tcgen05.ld ... pack::16b) and keeps a per-halfword signed max of D (the x_b test) and
 // min of D * 512 (x_a's 7 bits at the top of each halfword) with VIMNMX3.S16x2: 1 multiply + 1 min/max lane-op per
-// register = per four (query, code) pairs; one vote per 128 codes.
+// register = per four (query, code) pairs, and the per-query bounds come ready-made from shared memory.
 // Only when a bound is crossed does that lane take the cold path, which decodes the distances from its registers and
 // applies the same admission rule as hamming_survivors.  Queries stay resident in shared memory as
-// eight 128-row A tiles; codes are expanded to operand rows by four producer warps, two stages ahead of the MMAs.
+// eight 128-row A tiles; operand rows are either expanded from the codes by four producer warps (<false>, used at 897-1024
+// queries) or copied ready-made from corpus->ham_ops by TMA bulk copies (<true>, 64-896 queries).
 constexpr int kMmaQTile = 128;                       // UMMA M: queries per accumulator tile (TMEM lanes)
 constexpr int kMmaRows = 256;                        // UMMA N: operand rows per stage = 512 codes (TMEM columns)
 constexpr int kMmaTileCodes = 2 * kMmaRows;
