@@ -110,6 +110,40 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bench_config(n_total: int, nq: int, world: int) -> dict:
+    """The `config` object of the JSON line.  Both arms (ours and --impl reference) print exactly this dict."""
+    return {"workload": f"hamming top-{K}, {nq}-query batch over {n_total} synthetic 64-bit codes with planted neighbours",
+            "k": K, "queries": nq, "codes": n_total, "codes_per_gpu": n_total * 1 // world if world else n_total,
+            "parallelism": f"record-range shards x{world}, NCCL all-gather of top-k + merge",
+            "l2": "inputs larger than L2 (corpus slice >= 1 GB per GPU vs 126 MB L2), no flush needed"}
+
+
+# ---------------------------------------------------------------- parity (oracle as the checker) ------
+def oracle_topk_full_corpus(n_total: int, nq: int, sel: np.ndarray, chunk: int = 100_000_000):
+    """CPU oracle (oracle/, the executable form of docs/HASH_SPEC.md section 6) over ALL n_total rows of the bench
+    corpus -- regenerated on the host chunk by chunk with the same PRNG and the same planting -- for the queries
+    `sel`.  Returns (ids [len(sel), K] u64, dist [len(sel), K] u32).  Never inside a timed region."""
+    import oracle
+    threads = oracle.host_threads()
+    q = make_queries(nq)[sel]
+    prow, pcode = planted(nq, n_total)
+    best_i = np.full((len(sel), K), np.uint64(2**64 - 1), dtype=np.uint64)
+    best_d = np.full((len(sel), K), np.uint32(2**32 - 1), dtype=np.uint32)
+    for lo in range(0, n_total, chunk):
+        m = min(chunk, n_total - lo)
+        codes = oracle.fill_u64(m, SEED_CORPUS, start=lo)
+        inside = (prow >= np.uint64(lo)) & (prow < np.uint64(lo + m))
+        codes[(prow[inside] - np.uint64(lo)).astype(np.int64)] = pcode[inside]
+        oi, od = oracle.hamming_topk(codes, q, K, id_base=lo, threads=threads)
+        # merge under (dist asc, id asc); sentinels (id = 2^64 - 1, dist = 2^32 - 1) sort last by construction
+        ci, cd = np.concatenate([best_i, oi], axis=1), np.concatenate([best_d, od], axis=1)
+        for r in range(len(sel)):
+            order = np.lexsort((ci[r], cd[r]))[:K]
+            best_i[r], best_d[r] = ci[r][order], cd[r][order]
+        del codes
+    return best_i, best_d
+
+
 # ---------------------------------------------------------------- CPU arm -----------------------------
 def cpu_arm(n_total: int, nq: int, steps: int, warmup: int, sample_rows: int, sample_queries: int):
     """The reference's CPU path for this metric.  The Rust reference has no Hamming scan at all and cannot
@@ -146,6 +180,8 @@ def main() -> int:
     ap.add_argument("--cpu-sample-queries", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-images", action="store_true", help="skip the secondary images-hashed/s measurement")
+    ap.add_argument("--parity-queries", type=int, default=64,
+                    help="queries of the batch checked against the CPU oracle over the FULL corpus (untimed; 0 = skip)")
     args = ap.parse_args()
 
     # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are sent to stderr
@@ -159,7 +195,6 @@ def main() -> int:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_total, nq = int(args.codes), args.queries
-    workload = f"hamming top-{K}, {nq}-query batch over {n_total} synthetic 64-bit codes with planted neighbours"
 
     if args.impl == "reference":
         if rank != 0:
@@ -168,7 +203,7 @@ def main() -> int:
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-                "config": {"workload": workload, "k": K, "queries": nq, "codes": n_total},
+                "config": bench_config(n_total, nq, max(args.gpus, 1)),
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
@@ -176,7 +211,7 @@ def main() -> int:
 
     import torch
     import torch.distributed as dist
-    from ucfp_b200 import Context, Corpus, _ffi
+    from ucfp_b200 import Context, Corpus, Group, _ffi
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: ucfp_b200 has no CPU fallback")
@@ -187,6 +222,13 @@ def main() -> int:
         dist.init_process_group("nccl", device_id=dev)
 
     ctx = Context(local_rank)  # shares torch's current stream
+    # N > 1: one process per GPU.  torch.distributed is the rendezvous only (it ships the NCCL id and keeps the barriers);
+    # the data path -- bound exchange, all-gather of packed top-k records, merge -- runs inside the library's group scan.
+    group = None
+    if world > 1:
+        uid = [Group.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        group = Group.join(ctx, uid[0], rank, world)
     lo, hi = n_total * rank // world, n_total * (rank + 1) // world
     shard = hi - lo
     corpus = Corpus(ctx, _ffi.KIND_HAMMING64, shard)
@@ -209,10 +251,6 @@ def main() -> int:
     queries = make_queries(nq)
     q_host = torch.from_numpy(queries.view(np.int64)).pin_memory()
     q_dev = q_host.to(dev)
-    ids_loc = torch.empty((nq, K), dtype=torch.int64, device=dev)
-    dist_loc = torch.empty((nq, K), dtype=torch.int32, device=dev)
-    ids_all = torch.empty((world, nq, K), dtype=torch.int64, device=dev)
-    dist_all = torch.empty((world, nq, K), dtype=torch.int32, device=dev)
     ids_out = torch.empty((nq, K), dtype=torch.int64, device=dev)
     dist_out = torch.empty((nq, K), dtype=torch.int32, device=dev)
     ids_host = torch.empty((nq, K), dtype=torch.int64).pin_memory()
@@ -223,20 +261,14 @@ def main() -> int:
         if world == 1:
             corpus.scan_hamming(q_dev, K, ids_out, dist_out)
         else:
-            corpus.scan_hamming(q_dev, K, ids_loc, dist_loc)
-            dist.all_gather_into_tensor(ids_all, ids_loc)
-            dist.all_gather_into_tensor(dist_all, dist_loc)
-            ctx.merge_topk_u32(ids_all, dist_all, world, nq, K, False, ids_out, dist_out)
+            group.scan_hamming([corpus], q_dev, K, ids_out, dist_out)
 
     def step_e2e():
         """pinned host queries in, pinned host results out, through the C ABI's host-buffer path"""
         if world == 1:
             corpus.scan_hamming(q_host.numpy(), K, ids_host.numpy(), dist_host.numpy())
         else:
-            corpus.scan_hamming(q_host.numpy(), K, ids_loc, dist_loc)
-            dist.all_gather_into_tensor(ids_all, ids_loc)
-            dist.all_gather_into_tensor(dist_all, dist_loc)
-            ctx.merge_topk_u32(ids_all, dist_all, world, nq, K, False, ids_host.numpy(), dist_host.numpy())
+            group.scan_hamming([corpus], q_host.numpy(), K, ids_host.numpy(), dist_host.numpy())
 
     def barrier():
         if world > 1:
@@ -275,19 +307,23 @@ def main() -> int:
         dist.all_reduce(lt)
     value = args.steps * nq / (total_ms / 1e3)
 
-    # sanity of the result that was just timed: planted distance-0 row must be hit 0 of every query
-    d0 = dist_out[:, 0].cpu().numpy()
-    if not (d0 == 0).all():
+    # the result that was just timed (all N ranks hold the same merged answer); checked against the oracle below
+    got_ids_dev = ids_out.cpu().numpy().view(np.uint64).copy()
+    got_dist_dev = dist_out.cpu().numpy().view(np.uint32).copy()
+    if not (got_dist_dev[:, 0] == 0).all():
         raise SystemExit("bench self-check failed: planted exact duplicates not found")
 
     for _ in range(2):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
     e2e_value = args.steps * nq / (e2e_ms / 1e3)
+    got_ids_e2e = ids_host.numpy().view(np.uint64).copy()
+    got_dist_e2e = dist_host.numpy().view(np.uint32).copy()
     if len(clocks.rows) < 3:   # very short runs: keep the same scan going until the sampler has seen it.  LOCAL work only --
         t_end = time.time() + 1.0   # ranks may disagree about needing this, so no collective may run in here
+        scratch_i, scratch_d = torch.empty_like(ids_out), torch.empty_like(dist_out)
         while time.time() < t_end:
-            corpus.scan_hamming(q_dev, K, ids_loc, dist_loc)
+            corpus.scan_hamming(q_dev, K, scratch_i, scratch_d)
         torch.cuda.synchronize()
     clocks.__exit__(None, None, None)
 
@@ -395,6 +431,25 @@ def main() -> int:
                     "kernel_ms_per_step": k_ms / args.steps, "pairs_per_s": pairs / (k_ms / 1e3) if k_ms else None,
                     "note": "algorithmic bytes = 8 B x rows x queries per launch", "streaming": streaming}
 
+    # Parity of the configuration that was measured, on the hardware path that was measured (N ranks, NCCL gather,
+    # merge): the CPU oracle scans ALL n_total rows for every (nq / parity_queries)-th query and both the device-resident
+    # and the end-to-end answers must equal it byte for byte.  Untimed; rank 0 only (every rank holds the same answer).
+    parity = None
+    if rank == 0 and args.parity_queries > 0:
+        t0 = time.perf_counter()
+        sel = np.arange(nq)[:: max(nq // args.parity_queries, 1)][: args.parity_queries]
+        want_i, want_d = oracle_topk_full_corpus(n_total, nq, sel)
+        ok_dev = bool((got_ids_dev[sel] == want_i).all() and (got_dist_dev[sel] == want_d).all())
+        ok_e2e = bool((got_ids_e2e[sel] == want_i).all() and (got_dist_e2e[sel] == want_d).all())
+        all_same = bool((got_ids_dev == got_ids_e2e).all() and (got_dist_dev == got_dist_e2e).all())
+        parity = {"queries": int(len(sel)), "rows": n_total, "ok": ok_dev and ok_e2e and all_same, "device_path_ok": ok_dev,
+                  "e2e_path_ok": ok_e2e, "device_equals_e2e_all_queries": all_same, "n_gpus": world,
+                  "against": "oracle/ (CPU restatement of docs/HASH_SPEC.md section 6) over the full corpus, regenerated on the host",
+                  "seconds": round(time.perf_counter() - t0, 1)}
+        if not parity["ok"]:
+            bad = [int(x) for x in sel[((got_ids_dev[sel] != want_i) | (got_dist_dev[sel] != want_d)).any(axis=1)]][:8]
+            sys.stderr.write(f"PARITY FAILURE against the oracle: {parity}; first differing queries {bad}\n")
+
     if rank == 0:
         cb = None
         if world == 1 and not args.no_cpu_baseline:
@@ -403,9 +458,7 @@ def main() -> int:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload, "k": K, "queries": nq, "codes": n_total, "codes_per_gpu": shard,
-                       "parallelism": f"record-range shards x{world}, NCCL all-gather of top-k + merge",
-                       "l2": "inputs larger than L2 (corpus slice >= 1 GB per GPU vs 126 MB L2), no flush needed"},
+            "config": bench_config(n_total, nq, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nq * 8, "d2h_bytes_per_step": nq * K * 12,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(lt.item()),
@@ -416,10 +469,14 @@ def main() -> int:
         }
         if cb is not None:
             line["cpu_baseline"] = cb
+        if parity is not None:
+            line["parity_check"] = parity
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        return 3   # a fast answer that differs from the oracle is not a result
     return 0
 
 

@@ -12,11 +12,21 @@
  *
  * Buffers may live in host memory (pageable or pinned) or in device memory of
  * the context's GPU; the library inspects each pointer
- * (cudaPointerGetAttributes) and stages host buffers itself.  All work is
- * enqueued on the context's stream (ucfp_ctx_set_stream lets a host that
- * already owns a CUDA stream, e.g. a torch stream in the test harness, share
- * it).  Calls that take host output buffers synchronise that stream before
- * returning; calls whose outputs are all device buffers return asynchronously.
+ * (cudaPointerGetAttributes) and stages host buffers itself.
+ *
+ * Threading (the reference calls this path from a multi-thread tokio runtime
+ * with <= 512 requests in flight, src/bin/ucfp.rs:207,262-267): every entry
+ * point is thread-safe.  A call leases a "lane" of its context -- a private
+ * CUDA stream plus private scratch, up to 16 per context -- so calls from
+ * different host threads run concurrently on the GPU.  A corpus is read under
+ * a shared lock (any number of concurrent scans) and mutated (append, clear,
+ * delete, upsert, reserve, refresh) under an exclusive one.  In this default
+ * ("pooled") mode every call returns with its work complete, whatever memory
+ * its outputs live in.
+ * ucfp_ctx_set_stream switches the context to "shared-stream" mode for hosts
+ * that own a CUDA stream (a torch stream in the test harness): all calls are
+ * then enqueued on that stream, one at a time, and calls whose outputs are all
+ * device buffers return asynchronously; calls with host outputs synchronise.
  *
  * There is NO CPU fallback: without a usable sm_100 device every call fails
  * with UCFP_E_CUDA.
@@ -44,7 +54,7 @@ extern "C" {
 #define UCFP_API __attribute__((visibility("default")))
 #endif
 
-#define UCFP_ABI_VERSION 1
+#define UCFP_ABI_VERSION 2
 
 /* ---- status codes (map onto src/error.rs:9-61 on the Rust side) ---------- */
 enum {
@@ -69,10 +79,10 @@ typedef struct ucfp_corpus ucfp_corpus; /* one per (tenant, kind, dim): HBM-resi
  * device is missing or is not compute capability 10.x. */
 UCFP_API int ucfp_init(int device, ucfp_ctx **out);
 UCFP_API void ucfp_destroy(ucfp_ctx *ctx);
-/* Use the caller's cudaStream_t (passed as void*) for all subsequent work.  NULL
- * is CUDA's default stream, exactly as in the runtime API. */
+/* Shared-stream mode: use the caller's cudaStream_t (passed as void*) for all subsequent work of this context, one
+ * call at a time.  NULL is CUDA's default stream, exactly as in the runtime API. */
 UCFP_API int ucfp_ctx_set_stream(ucfp_ctx *ctx, void *cuda_stream);
-/* Go back to the context's own non-blocking stream (the state after ucfp_init). */
+/* Back to pooled mode (the state after ucfp_init): per-call lanes with their own non-blocking streams. */
 UCFP_API int ucfp_ctx_reset_stream(ucfp_ctx *ctx);
 /* Blocks until everything enqueued by this context has finished. */
 UCFP_API int ucfp_ctx_synchronize(ucfp_ctx *ctx);
@@ -172,6 +182,21 @@ UCFP_API int ucfp_corpus_append(ucfp_corpus *c, const uint64_t *ids, const void 
 UCFP_API int ucfp_corpus_append_strided(ucfp_corpus *c, const uint64_t *ids, const void *records, uint64_t record_stride,
                                         uint64_t field_offset, uint64_t n);
 UCFP_API int ucfp_corpus_set_id_base(ucfp_corpus *c, uint64_t id_base);
+/* Insert-or-replace by record id -- IndexBackend::upsert, src/index/mod.rs:20-22 ("Insert-or-replace by (tenant_id,
+ * record_id)"): rows whose id is already resident are overwritten in place (side arrays re-derived), the others are
+ * appended; within one batch the last occurrence of an id wins.  A full corpus grows by itself (reallocation + device-to-
+ * device copy, at least doubling; UCFP_E_OOM when HBM refuses).  ids: host or device memory; rows: host or device.  An
+ * implicit-id corpus becomes an explicit-id corpus (ids = id_base + row materialised) the first time it is mutated
+ * through upsert or delete.  *n_replaced (may be NULL) = rows overwritten. */
+UCFP_API int ucfp_corpus_upsert(ucfp_corpus *c, const uint64_t *ids, const void *rows, uint64_t n, uint64_t *n_replaced);
+/* Removes the rows with these record ids -- IndexBackend::delete, src/index/mod.rs:23-25 (idempotent: unknown ids are
+ * ignored).  The rows are found on the device (one pass over the id column), the corpus's LAST rows move into the freed
+ * slots and their side arrays are re-derived: the corpus stays dense, no scan ever sees a tombstone, and since every
+ * scan's total order breaks ties by record id the results do not depend on the row order.  *n_removed may be NULL. */
+UCFP_API int ucfp_corpus_delete(ucfp_corpus *c, const uint64_t *ids, uint64_t n, uint64_t *n_removed);
+/* Grows the allocation to at least `capacity` rows (no-op when it already is that large). */
+UCFP_API int ucfp_corpus_reserve(ucfp_corpus *c, uint64_t capacity);
+UCFP_API uint64_t ucfp_corpus_capacity(const ucfp_corpus *c);
 UCFP_API int ucfp_corpus_clear(ucfp_corpus *c);
 UCFP_API uint64_t ucfp_corpus_size(const ucfp_corpus *c);
 /* Bench/test support: appends n synthetic rows generated on the device with the counter PRNG of
@@ -202,6 +227,55 @@ UCFP_API int ucfp_scan_jaccard(ucfp_corpus *c, const uint64_t *queries, size_t n
  * rows and queries with zero norm never match (:284, :328); sentinel score = -inf.  queries = nq x dim f32. */
 UCFP_API int ucfp_scan_cosine(ucfp_corpus *c, const float *queries, size_t nq, size_t k,
                               uint64_t *ids_out, float *score_out);
+
+/* Limits: k <= 2048 (Hamming, Jaccard) and k <= 1024 (cosine) per call -- larger k returns UCFP_E_UNSUPPORTED; callers
+ * that mirror IndexBackend::knn clamp k to min(k, ucfp_corpus_size) first (EmbeddedBackend::knn returns min(k, N) hits). */
+
+/* ---- query batcher ----------------------------------------------------------
+ * The reference serves one query per request with up to 512 requests in flight (src/bin/ucfp.rs:262-267,
+ * handlers::query src/server/handlers.rs:143-187).  One query per scan call wastes the GPU: a scan of N rows costs the
+ * same HBM pass for 1 query as for 64.  A batcher coalesces the single-query calls of many host threads into batched
+ * scans: ucfp_batcher_query blocks its caller; worker threads owned by the batcher collect the queries that arrive while
+ * the previous batch is scanning (at most max_batch; a first-in-line query waits at most max_delay_us for company) and
+ * run them as ONE scan with k = the largest k of the batch; every caller gets the first k entries of its query's list
+ * (the top-k' list is a prefix of the top-k list under the scans' total orders). */
+typedef struct ucfp_batcher ucfp_batcher;
+UCFP_API int ucfp_batcher_create(ucfp_corpus *c, uint32_t max_batch, uint32_t max_delay_us, ucfp_batcher **out);
+UCFP_API void ucfp_batcher_destroy(ucfp_batcher *b);
+/* query = one row of the corpus's kind (8 B code, 128 u64 slots, dim f32) in HOST memory; ids_out[k], keys_out[k] (u32
+ * distances / matches, or f32 scores) in HOST memory.  Thread-safe; blocks until the result is there. */
+UCFP_API int ucfp_batcher_query(ucfp_batcher *b, const void *query, size_t k, uint64_t *ids_out, void *keys_out);
+UCFP_API int ucfp_batcher_stats(const ucfp_batcher *b, uint64_t *queries, uint64_t *batches, uint64_t *largest_batch);
+
+/* ---- multi-GPU group --------------------------------------------------------
+ * Record-range shards over the GPUs of one box: rank r holds rows [r*N/G, (r+1)*N/G) with GLOBAL record ids
+ * (ucfp_corpus_set_id_base or explicit ids); every rank scans its shard against the whole query batch, the per-rank
+ * top-k lists are exchanged as packed 16-byte (id, key) records in ONE NCCL all-gather and every rank runs the same
+ * deterministic merge, so the result is byte-identical to the single-corpus scan.  While a Hamming batch walks its
+ * shard the ranks also exchange their per-query admission bounds (one small all-gather per chunk boundary), so every
+ * shard filters at the best bound any rank has found so far.
+ * NCCL is loaded at the first group call (dlopen of libnccl.so.2, the copy already in the process if there is one),
+ * not at library load: hosts that never form a group do not need it. */
+typedef struct ucfp_group ucfp_group;
+/* Single process driving n GPUs (the FFI use-case): one context per device, ncclCommInitAll over them. */
+UCFP_API int ucfp_group_create(const int *devices, int n, ucfp_group **out);
+/* One process per GPU: rank 0 obtains an id, ships its 128 bytes to the other ranks by any means, every rank joins
+ * with its own context. */
+UCFP_API int ucfp_group_unique_id(void *id128);
+UCFP_API int ucfp_group_join(ucfp_ctx *ctx, const void *id128, int rank, int world, ucfp_group **out);
+UCFP_API void ucfp_group_destroy(ucfp_group *g);
+UCFP_API int ucfp_group_local_size(const ucfp_group *g);           /* GPUs this process drives */
+UCFP_API int ucfp_group_world_size(const ucfp_group *g);
+UCFP_API ucfp_ctx *ucfp_group_ctx(ucfp_group *g, int local_rank);  /* owned by the group when created by ucfp_group_create */
+/* corpora[i] = shard of local rank i (created on ucfp_group_ctx(g, i)).  queries: host memory, or device memory of any
+ * local GPU.  Outputs: host memory, or device memory of one local GPU.  Collective over the WORLD: in the multi-process
+ * form every process calls it with the same queries, nq and k. */
+UCFP_API int ucfp_group_scan_hamming(ucfp_group *g, ucfp_corpus *const *corpora, const uint64_t *queries, size_t nq, size_t k,
+                                     uint64_t *ids_out, uint32_t *dist_out);
+UCFP_API int ucfp_group_scan_jaccard(ucfp_group *g, ucfp_corpus *const *corpora, const uint64_t *queries, size_t nq, size_t k,
+                                     uint64_t *ids_out, uint32_t *matches_out);
+UCFP_API int ucfp_group_scan_cosine(ucfp_group *g, ucfp_corpus *const *corpora, const float *queries, size_t nq, size_t k,
+                                    uint64_t *ids_out, float *score_out);
 
 /* Diagnostics of the most recent scan on this context (synchronises the stream): how many of its queries
  * overflowed their candidate list and were recomputed by the exact multi-pass selection.  0 on the fast path. */

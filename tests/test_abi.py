@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ucfp_cuda.h but not exported"
     assert sorted(_ffi.PROTOTYPES) == names, "ucfp_b200/_ffi.py and the header drifted apart"
-    assert _ffi.lib().ucfp_abi_version() == 1
+    assert _ffi.lib().ucfp_abi_version() == 2
 
 
 def test_header_is_plain_c():

@@ -5,7 +5,7 @@ libucfp_cuda.so (include/ucfp_cuda.h); there is no CPU fallback."""
 from . import _ffi  # noqa: F401
 from ._ffi import UcfpError  # noqa: F401
 from .core import Error, Hit, HitSource, Modality, Query, Record  # noqa: F401
-from .runtime import Context, Corpus  # noqa: F401
+from .runtime import Batcher, Context, Corpus, Group  # noqa: F401
 from . import image, sharding  # noqa: F401,E402
 from .index import GpuIndexBackend  # noqa: F401,E402
 from .matcher import Matcher, rrf, rrf_with_sources  # noqa: F401,E402

@@ -61,10 +61,28 @@ PROTOTYPES = {
     "ucfp_corpus_append_synthetic": (_int, [_vp, _u64, _u64, _u64]),
     "ucfp_corpus_device_rows": (_vp, [_vp]),
     "ucfp_corpus_refresh": (_int, [_vp]),
+    "ucfp_corpus_upsert": (_int, [_vp, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "ucfp_corpus_delete": (_int, [_vp, _vp, _u64, C.POINTER(_u64)]),
+    "ucfp_corpus_reserve": (_int, [_vp, _u64]),
+    "ucfp_corpus_capacity": (_u64, [_vp]),
     "ucfp_scan_hamming": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "ucfp_scan_jaccard": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "ucfp_scan_cosine": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "ucfp_ctx_last_scan_fallbacks": (_int, [_vp, C.POINTER(_u64)]),
+    "ucfp_batcher_create": (_int, [_vp, _u32, _u32, C.POINTER(_vp)]),
+    "ucfp_batcher_destroy": (None, [_vp]),
+    "ucfp_batcher_query": (_int, [_vp, _vp, _sz, _vp, _vp]),
+    "ucfp_batcher_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "ucfp_group_create": (_int, [C.POINTER(_int), _int, C.POINTER(_vp)]),
+    "ucfp_group_unique_id": (_int, [_vp]),
+    "ucfp_group_join": (_int, [_vp, _vp, _int, _int, C.POINTER(_vp)]),
+    "ucfp_group_destroy": (None, [_vp]),
+    "ucfp_group_local_size": (_int, [_vp]),
+    "ucfp_group_world_size": (_int, [_vp]),
+    "ucfp_group_ctx": (_vp, [_vp, _int]),
+    "ucfp_group_scan_hamming": (_int, [_vp, C.POINTER(_vp), _vp, _sz, _sz, _vp, _vp]),
+    "ucfp_group_scan_jaccard": (_int, [_vp, C.POINTER(_vp), _vp, _sz, _sz, _vp, _vp]),
+    "ucfp_group_scan_cosine": (_int, [_vp, C.POINTER(_vp), _vp, _sz, _sz, _vp, _vp]),
     "ucfp_merge_topk_u32": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _int, _vp, _vp]),
     "ucfp_merge_topk_f32": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp]),
 }

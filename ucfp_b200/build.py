@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 SO = os.path.join(HERE, "libucfp_cuda.so")
-SOURCES = ["api.cu", "hamming.cu", "jaccard.cu", "cosine.cu", "image.cu", "merge.cu"]
+SOURCES = ["api.cu", "corpus.cu", "batcher.cu", "group.cu", "hamming.cu", "jaccard.cu", "cosine.cu", "image.cu", "merge.cu"]
 # Per-file extra flags.  image.cu must not contract a*b+c into FMA: the hash spec fixes
 # separately rounded mul and add (docs/HASH_SPEC.md section 2).
 EXTRA = {"image.cu": ["-fmad=false"], "cosine.cu": ["-fmad=false"]}
@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    link = [cc, "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lcuda"]
+    link = [cc, "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lcuda", "-ldl", "-lpthread"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

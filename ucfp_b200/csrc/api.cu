@@ -1,8 +1,13 @@
 // api.cu -- the extern "C" surface of libucfp_cuda.so (declared in include/ucfp_cuda.h):
-// context and corpus lifetime, host/device staging, dispatch into the per-path kernels.
+// context and lane pool, corpus lifetime, host/device staging, dispatch into the per-path kernels.
+//
+// Threading model (SURVEY 8b "Threading"): every entry point leases a LANE (one stream + its own scratch) for its
+// duration, so calls from different host threads run concurrently; a corpus is read under a shared lock and
+// mutated (append / clear / delete / upsert / refresh) under an exclusive one.  Nothing may unwind across the ABI:
+// every body sits inside UCFP_API_BEGIN / UCFP_API_END, which turn any C++ exception into a status code.
 #include <stdarg.h>
 
-#include "common.cuh"
+#include "api_util.cuh"
 
 namespace ucfp {
 
@@ -15,24 +20,70 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-namespace {
+// ---- lane pool ----------------------------------------------------------------------------------------------------
+static ucfp_lane *lane_create(ucfp_ctx *ctx) {
+    ucfp_lane *ln = new (std::nothrow) ucfp_lane();
+    if (!ln) return nullptr;
+    ln->owner = ctx; ln->device = ctx->device; ln->sm_count = ctx->sm_count; ln->smem_optin = ctx->smem_optin;
+    if (cudaStreamCreateWithFlags(&ln->own_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete ln; return nullptr; }
+    ln->stream = ln->own_stream;
+    return ln;
+}
 
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = true;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
-        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) { ok = false; cudaGetLastError(); }
+static void lane_destroy(ucfp_lane *ln) {
+    if (!ln) return;
+    cudaStreamSynchronize(ln->own_stream);
+    DevBuf *bufs[] = {&ln->q_dev, &ln->out_ids_dev, &ln->out_keys_dev, &ln->cand, &ln->cand_count, &ln->qstate, &ln->flags, &ln->misc,
+                      &ln->img_desc_dev, &ln->img_out_dev, &ln->img_status_dev, &ln->img_tables_dev, &ln->img_stage_dev, &ln->stats};
+    for (DevBuf *b : bufs) b->release();
+    ln->pin_a.release(); ln->pin_b.release();
+    cudaStreamDestroy(ln->own_stream);
+    delete ln;
+}
+
+LaneLease::LaneLease(ucfp_ctx *c) : ctx(c) {
+    if (cudaGetDevice(&prev_device) != cudaSuccess) { prev_device = -1; cudaGetLastError(); }
+    if (prev_device != ctx->device && cudaSetDevice(ctx->device) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaSetDevice(%d) failed", ctx->device);
+        return;
     }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    for (;;) {
+        if (ctx->shared_stream) {   // one call at a time, on the caller's stream, through lane 0
+            if (!ctx->lanes[0]->busy) { lane = ctx->lanes[0]; lane->stream = ctx->user_stream; break; }
+        } else {
+            for (int i = 0; i < ctx->n_lanes && !lane; ++i)
+                if (!ctx->lanes[i]->busy) lane = ctx->lanes[i];
+            if (!lane && ctx->n_lanes < kUcfpMaxLanes) {
+                ucfp_lane *fresh = lane_create(ctx);
+                if (fresh) { ctx->lanes[ctx->n_lanes++] = fresh; lane = fresh; }
+                else if (ctx->n_lanes == 0) { set_error("cannot create a stream"); return; }
+            }
+            if (lane) { lane->stream = lane->own_stream; break; }
+        }
+        ctx->cv.wait(lk);
+    }
+    lane->busy = true;
+}
+
+LaneLease::~LaneLease() {
+    if (lane) {
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            lane->busy = false;
+        }
+        ctx->cv.notify_one();
+    }
+    if (prev_device >= 0 && prev_device != ctx->device) cudaSetDevice(prev_device);
+}
 
 // Makes `user` (host or device) readable on the device.  Host data is copied into `buf`.
-int stage_in(ucfp_ctx *ctx, DevBuf &buf, const void *user, size_t bytes, const void **dev) {
+int stage_in(ucfp_lane *ln, DevBuf &buf, const void *user, size_t bytes, const void **dev) {
     if (bytes == 0) { *dev = buf.ptr; return UCFP_OK; }
     if (classify(user) == Mem::Device) { *dev = user; return UCFP_OK; }
     UCFP_TRY(buf.reserve(bytes));
-    UCFP_CUDA_TRY(cudaMemcpyAsync(buf.ptr, user, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    UCFP_CUDA_TRY(cudaMemcpyAsync(buf.ptr, user, bytes, cudaMemcpyHostToDevice, ln->stream));
     *dev = buf.ptr;
     return UCFP_OK;
 }
@@ -46,8 +97,15 @@ int stage_out(DevBuf &buf, void *user, size_t bytes, void **dev, bool *is_host) 
     return UCFP_OK;
 }
 
-int copy_back(ucfp_ctx *ctx, void *user, const void *dev, size_t bytes) {
-    if (bytes) UCFP_CUDA_TRY(cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+int copy_back(ucfp_lane *ln, void *user, const void *dev, size_t bytes) {
+    if (bytes) UCFP_CUDA_TRY(cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, ln->stream));
+    return UCFP_OK;
+}
+
+// End of a call: pooled mode always completes the work (the lane goes back to the pool, its scratch may be reused by
+// another thread at once); shared-stream mode synchronises only when the caller reads host memory afterwards.
+int finish_call(ucfp_lane *ln, bool host_outputs) {
+    if (host_outputs || !ln->owner->shared_stream) UCFP_CUDA_TRY(cudaStreamSynchronize(ln->stream));
     return UCFP_OK;
 }
 
@@ -60,16 +118,16 @@ size_t row_bytes(const ucfp_corpus *c) {
     return 0;
 }
 
-}  // namespace
+int after_append(ucfp_lane *ln, ucfp_corpus *c, uint64_t first, uint64_t n) {
+    if (c->kind == UCFP_KIND_HAMMING64) return hamming_on_append(ln, c, first, n);
+    if (c->kind == UCFP_KIND_MINHASH128) return jaccard_on_append(ln, c, first, n);
+    if (c->kind == UCFP_KIND_COSINE) return cosine_on_append(ln, c, first, n);
+    return UCFP_OK;
+}
+
 }  // namespace ucfp
 
 using namespace ucfp;
-
-#define UCFP_GUARD(ctxp)                                                              \
-    UCFP_REQUIRE((ctxp) != nullptr, UCFP_E_INVALID, "null context");                  \
-    DeviceGuard _dg((ctxp)->device);                                                  \
-    UCFP_REQUIRE(_dg.ok, UCFP_E_CUDA, "cudaSetDevice(%d) failed", (ctxp)->device);    \
-    std::lock_guard<std::mutex> _lk((ctxp)->mu)
 
 extern "C" {
 
@@ -78,6 +136,7 @@ int ucfp_abi_version(void) { return UCFP_ABI_VERSION; }
 const char *ucfp_last_error(void) { return g_err; }
 
 int ucfp_init(int device, ucfp_ctx **out) {
+    UCFP_API_BEGIN
     UCFP_REQUIRE(out != nullptr, UCFP_E_INVALID, "ucfp_init: out is NULL");
     *out = nullptr;
     int ndev = 0;
@@ -98,46 +157,74 @@ int ucfp_init(int device, ucfp_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     DeviceGuard dg(device);
-    cudaError_t se = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
-    if (se != cudaSuccess) { delete ctx; set_error("cudaStreamCreate failed: %s", cudaGetErrorString(se)); return UCFP_E_CUDA; }
-    ctx->stream = ctx->own_stream;
+    ctx->lanes[0] = lane_create(ctx);
+    if (!ctx->lanes[0]) { delete ctx; set_error("cudaStreamCreate failed"); return UCFP_E_CUDA; }
+    ctx->n_lanes = 1;
+    // per-device kernel attributes and occupancies, once
+    int rc = hamming_device_init(ctx);
+    if (rc == UCFP_OK) rc = jaccard_device_init(ctx);
+    if (rc == UCFP_OK) rc = cosine_device_init(ctx);
+    if (rc == UCFP_OK) rc = image_device_init(ctx);
+    if (rc == UCFP_OK) rc = merge_device_init(ctx);
+    if (rc == UCFP_OK) rc = corpus_device_init(ctx);
+    if (rc != UCFP_OK) { lane_destroy(ctx->lanes[0]); delete ctx; return rc; }
     *out = ctx;
     return UCFP_OK;
+    UCFP_API_END
 }
 
 void ucfp_destroy(ucfp_ctx *ctx) {
     if (!ctx) return;
-    DeviceGuard dg(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->q_dev, &ctx->out_ids_dev, &ctx->out_keys_dev, &ctx->cand, &ctx->cand_count, &ctx->qstate, &ctx->flags,
-                      &ctx->misc, &ctx->img_desc_dev, &ctx->img_out_dev, &ctx->img_status_dev, &ctx->img_tables_dev, &ctx->img_stage_dev, &ctx->stats};
-    for (DevBuf *b : bufs) b->release();
-    ctx->pin_a.release(); ctx->pin_b.release();
-    image_cache_destroy(ctx);
-    for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-    delete ctx;
+    try {
+        DeviceGuard dg(ctx->device);
+        for (int i = 0; i < ctx->n_lanes; ++i) lane_destroy(ctx->lanes[i]);
+        image_cache_destroy(ctx);
+        for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        delete ctx;
+    } catch (...) {
+    }
 }
 
 int ucfp_ctx_set_stream(ucfp_ctx *ctx, void *cuda_stream) {
-    UCFP_GUARD(ctx);
-    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    UCFP_API_BEGIN
+    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    UCFP_LEASE(ctx);   // waits for running calls of shared-stream mode; pooled calls in flight finish on their own lanes
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->shared_stream = true;
+    ctx->user_stream = static_cast<cudaStream_t>(cuda_stream);
     return UCFP_OK;
+    UCFP_API_END
 }
 
 int ucfp_ctx_reset_stream(ucfp_ctx *ctx) {
-    UCFP_GUARD(ctx);
-    ctx->stream = ctx->own_stream;
+    UCFP_API_BEGIN
+    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    UCFP_LEASE(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->shared_stream = false;
+    ctx->user_stream = nullptr;
     return UCFP_OK;
+    UCFP_API_END
 }
 
 int ucfp_ctx_synchronize(ucfp_ctx *ctx) {
-    UCFP_GUARD(ctx);
-    UCFP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    UCFP_API_BEGIN
+    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    DeviceGuard dg(ctx->device);
+    UCFP_REQUIRE(dg.ok, UCFP_E_CUDA, "cudaSetDevice(%d) failed", ctx->device);
+    cudaStream_t streams[kUcfpMaxLanes + 1];
+    int n = 0;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (int i = 0; i < ctx->n_lanes; ++i) streams[n++] = ctx->lanes[i]->own_stream;
+        if (ctx->shared_stream) streams[n++] = ctx->user_stream;
+    }
+    for (int i = 0; i < n; ++i) UCFP_CUDA_TRY(cudaStreamSynchronize(streams[i]));
     return UCFP_OK;
+    UCFP_API_END
 }
 
-uint64_t ucfp_ctx_kernel_launches(const ucfp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t ucfp_ctx_kernel_launches(const ucfp_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 
 static void prof_clear(ucfp_ctx *ctx) {
     for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -145,339 +232,387 @@ static void prof_clear(ucfp_ctx *ctx) {
 }
 
 int ucfp_ctx_profile_begin(ucfp_ctx *ctx) {
-    UCFP_GUARD(ctx);
+    UCFP_API_BEGIN
+    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    std::lock_guard<std::mutex> lk(ctx->prof_mu);
     prof_clear(ctx);
-    ctx->profiling = true;
+    ctx->profiling.store(true);
+    return UCFP_OK;
+    UCFP_API_END
+}
+
+static int prof_sum(ucfp_ctx *ctx, int kernel_class, double *kernel_ms, double *alg_units, uint64_t *launches, bool end) {
+    UCFP_TRY(ucfp_ctx_synchronize(ctx));
+    DeviceGuard dg(ctx->device);
+    std::lock_guard<std::mutex> lk(ctx->prof_mu);
+    double ms = 0, units = 0; uint64_t n = 0;
+    for (auto &r : ctx->prof) {
+        if (r.kind != kernel_class) continue;
+        float t = 0;
+        UCFP_CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
+        ms += t; units += r.units; n++;
+    }
+    if (kernel_ms) *kernel_ms = ms;
+    if (alg_units) *alg_units = units;
+    if (launches) *launches = n;
+    if (end) { ctx->profiling.store(false); prof_clear(ctx); }
     return UCFP_OK;
 }
 
 int ucfp_ctx_profile_read(ucfp_ctx *ctx, int kernel_class, double *kernel_ms, double *alg_units, uint64_t *launches) {
-    UCFP_GUARD(ctx);
-    UCFP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    double ms = 0, units = 0; uint64_t n = 0;
-    for (auto &r : ctx->prof) {
-        if (r.kind != kernel_class) continue;
-        float t = 0;
-        UCFP_CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
-        ms += t; units += r.units; n++;
-    }
-    if (kernel_ms) *kernel_ms = ms;
-    if (alg_units) *alg_units = units;
-    if (launches) *launches = n;
-    return UCFP_OK;
+    UCFP_API_BEGIN
+    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    return prof_sum(ctx, kernel_class, kernel_ms, alg_units, launches, false);
+    UCFP_API_END
 }
 
 int ucfp_ctx_profile_end(ucfp_ctx *ctx, int kernel_class, double *kernel_ms, double *alg_units, uint64_t *launches) {
-    UCFP_GUARD(ctx);
-    UCFP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    double ms = 0, units = 0; uint64_t n = 0;
-    for (auto &r : ctx->prof) {
-        if (r.kind != kernel_class) continue;
-        float t = 0;
-        UCFP_CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
-        ms += t; units += r.units; n++;
-    }
-    if (kernel_ms) *kernel_ms = ms;
-    if (alg_units) *alg_units = units;
-    if (launches) *launches = n;
-    ctx->profiling = false;
-    prof_clear(ctx);
-    return UCFP_OK;
+    UCFP_API_BEGIN
+    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    return prof_sum(ctx, kernel_class, kernel_ms, alg_units, launches, true);
+    UCFP_API_END
 }
 
 // ---- corpus -------------------------------------------------------------------------------
 
+static void corpus_free_arrays(ucfp_corpus *c) {
+    if (c->rows) cudaFree(c->rows);
+    if (c->ids) cudaFree(c->ids);
+    if (c->ham_ops) cudaFree(c->ham_ops);
+    if (c->mh_sketch) cudaFree(c->mh_sketch);
+    if (c->cos_bf16) cudaFree(c->cos_bf16);
+    if (c->cos_inv_norm) cudaFree(c->cos_inv_norm);
+    c->rows = nullptr; c->ids = nullptr; c->ham_ops = nullptr; c->mh_sketch = nullptr; c->cos_bf16 = nullptr; c->cos_inv_norm = nullptr;
+}
+
 int ucfp_corpus_create(ucfp_ctx *ctx, int kind, uint32_t dim, uint64_t capacity, ucfp_corpus **out) {
+    UCFP_API_BEGIN
     UCFP_REQUIRE(out != nullptr, UCFP_E_INVALID, "ucfp_corpus_create: out is NULL");
     *out = nullptr;
-    UCFP_GUARD(ctx);
+    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    UCFP_LEASE(ctx);
     UCFP_REQUIRE(kind == UCFP_KIND_HAMMING64 || kind == UCFP_KIND_MINHASH128 || kind == UCFP_KIND_COSINE, UCFP_E_INVALID,
                  "unknown corpus kind %d", kind);
     UCFP_REQUIRE(capacity > 0, UCFP_E_INVALID, "capacity must be > 0");
     if (kind == UCFP_KIND_COSINE) UCFP_REQUIRE(dim > 0 && dim <= 4096, UCFP_E_INVALID, "cosine dim must be in 1..4096 (got %u)", dim);
     ucfp_corpus *c = new (std::nothrow) ucfp_corpus();
     UCFP_REQUIRE(c != nullptr, UCFP_E_OOM, "out of host memory");
-    c->ctx = ctx; c->kind = kind; c->dim = kind == UCFP_KIND_COSINE ? dim : 0; c->capacity = capacity;
-    size_t rb = row_bytes(c);
-    // +16 rows of slack so that vector loads of the last partial tile never leave the allocation
-    cudaError_t e = cudaMalloc(&c->rows, rb * (capacity + 16));
-    if (e == cudaSuccess && kind == UCFP_KIND_MINHASH128) e = cudaMalloc((void **)&c->mh_sketch, 2 * 128 * ((capacity + 31) / 32 * 32 + 512));  // two planes (byte 0, byte 1 of every slot); whole 256-row tiles stay readable
-    if (e == cudaSuccess && kind == UCFP_KIND_COSINE) {
-        c->dim_pad = (dim + 63) / 64 * 64;
-        e = cudaMalloc(&c->cos_bf16, 2 * (size_t)c->dim_pad * (capacity + 256));
-        if (e == cudaSuccess) e = cudaMalloc((void **)&c->cos_inv_norm, 4 * (capacity + 256));
-    }
-    if (e == cudaSuccess && kind == UCFP_KIND_HAMMING64) {
-        // Operand rows of the tensor-core scan, 32 B per code on top of the 8 B code.  Optional: without them (allocation
-        // refused) the scan expands the codes on the fly in its producer warps, slower for 64-512-query batches.
-        const size_t ops_bytes = 64 * ((capacity + 1) / 2 + 512);   // whole 256-row stages stay readable
-        if (cudaMalloc((void **)&c->ham_ops, ops_bytes) != cudaSuccess) { cudaGetLastError(); c->ham_ops = nullptr; }
-        else if (cudaMemsetAsync(c->ham_ops, 0, ops_bytes, ctx->stream) != cudaSuccess) { cudaGetLastError(); cudaFree(c->ham_ops); c->ham_ops = nullptr; }
-    }
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        set_error("corpus allocation of %llu rows failed: %s", (unsigned long long)capacity, cudaGetErrorString(e));
-        if (c->rows) cudaFree(c->rows);
-        if (c->mh_sketch) cudaFree(c->mh_sketch);
-        if (c->cos_bf16) cudaFree(c->cos_bf16);
-        if (c->cos_inv_norm) cudaFree(c->cos_inv_norm);
-        delete c;
-        return UCFP_E_OOM;
-    }
+    c->ctx = ctx; c->kind = kind; c->dim = kind == UCFP_KIND_COSINE ? dim : 0;
+    int rc = corpus_alloc_arrays(lane, c, capacity);
+    if (rc != UCFP_OK) { delete c; return rc; }
+    UCFP_TRY(finish_call(lane, false));
     *out = c;
     return UCFP_OK;
+    UCFP_API_END
 }
 
 void ucfp_corpus_destroy(ucfp_corpus *c) {
     if (!c) return;
-    {
-        DeviceGuard dg(c->ctx->device);
-        std::lock_guard<std::mutex> lk(c->ctx->mu);
-        cudaStreamSynchronize(c->ctx->stream);
-        if (c->rows) cudaFree(c->rows);
-        if (c->ids) cudaFree(c->ids);
-        if (c->ham_ops) cudaFree(c->ham_ops);
-        if (c->mh_sketch) cudaFree(c->mh_sketch);
-        if (c->cos_bf16) cudaFree(c->cos_bf16);
-        if (c->cos_inv_norm) cudaFree(c->cos_inv_norm);
+    try {
+        {
+            std::unique_lock<std::shared_mutex> wl(c->rw);   // waits for scans in flight
+            ucfp_ctx_synchronize(c->ctx);
+            DeviceGuard dg(c->ctx->device);
+            corpus_free_arrays(c);
+        }
+        delete c;
+    } catch (...) {
     }
-    delete c;
 }
 
 uint64_t ucfp_corpus_size(const ucfp_corpus *c) { return c ? c->size : 0; }
+uint64_t ucfp_corpus_capacity(const ucfp_corpus *c) { return c ? c->capacity : 0; }
 
 void *ucfp_corpus_device_rows(ucfp_corpus *c) { return c ? c->rows : nullptr; }
 
 int ucfp_corpus_set_id_base(ucfp_corpus *c, uint64_t id_base) {
+    UCFP_API_BEGIN
     UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
-    UCFP_GUARD(c->ctx);
+    std::unique_lock<std::shared_mutex> wl(c->rw);
     c->id_base = id_base;
     return UCFP_OK;
+    UCFP_API_END
 }
 
 int ucfp_corpus_clear(ucfp_corpus *c) {
+    UCFP_API_BEGIN
     UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
-    UCFP_GUARD(c->ctx);
+    std::unique_lock<std::shared_mutex> wl(c->rw);
     c->size = 0;
     c->id_mode = 0;
     return UCFP_OK;
-}
-
-static int after_append(ucfp_corpus *c, uint64_t first, uint64_t n) {
-    if (c->kind == UCFP_KIND_HAMMING64) return hamming_on_append(c, first, n);
-    if (c->kind == UCFP_KIND_MINHASH128) return jaccard_on_append(c, first, n);
-    if (c->kind == UCFP_KIND_COSINE) return cosine_on_append(c, first, n);
-    return UCFP_OK;
+    UCFP_API_END
 }
 
 int ucfp_corpus_refresh(ucfp_corpus *c) {
+    UCFP_API_BEGIN
     UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
-    UCFP_GUARD(c->ctx);
-    return after_append(c, 0, c->size);
+    std::unique_lock<std::shared_mutex> wl(c->rw);
+    UCFP_LEASE(c->ctx);
+    UCFP_TRY(after_append(lane, c, 0, c->size));
+    return finish_call(lane, false);
+    UCFP_API_END
 }
 
-int ucfp_corpus_append(ucfp_corpus *c, const uint64_t *ids, const void *rows, uint64_t n) {
-    UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
-    UCFP_GUARD(c->ctx);
+static int append_common(ucfp_corpus *c, const uint64_t *ids, const void *src, uint64_t src_stride, uint64_t field_offset, uint64_t n,
+                         bool strided) {
+    std::unique_lock<std::shared_mutex> wl(c->rw);
+    UCFP_LEASE(c->ctx);
     if (n == 0) return UCFP_OK;
-    UCFP_REQUIRE(rows != nullptr, UCFP_E_INVALID, "rows is NULL");
+    UCFP_REQUIRE(src != nullptr, UCFP_E_INVALID, "rows is NULL");
+    const size_t rb = row_bytes(c);
+    if (strided)
+        UCFP_REQUIRE(src_stride >= field_offset + rb, UCFP_E_INVALID, "record stride %llu cannot hold a %zu-byte field at offset %llu",
+                     (unsigned long long)src_stride, rb, (unsigned long long)field_offset);
     UCFP_REQUIRE(c->size + n <= c->capacity, UCFP_E_CAPACITY, "append of %llu rows exceeds capacity %llu (size %llu)",
                  (unsigned long long)n, (unsigned long long)c->capacity, (unsigned long long)c->size);
-    int mode = ids ? 1 : 2;
+    const int mode = ids ? 1 : 2;
     UCFP_REQUIRE(c->id_mode == 0 || c->id_mode == mode, UCFP_E_STATE, "corpus mixes explicit and implicit record ids");
-    cudaStream_t st = c->ctx->stream;
-    size_t rb = row_bytes(c);
+    cudaStream_t st = lane->stream;
     if (mode == 1 && !c->ids) UCFP_CUDA_TRY(cudaMalloc((void **)&c->ids, 8 * (c->capacity + 16)));
-    cudaMemcpyKind kr = classify(rows) == Mem::Device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    UCFP_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(c->rows) + rb * c->size, rows, rb * n, kr, st));
+    const bool dev_src = classify(src) == Mem::Device;
+    const cudaMemcpyKind kr = dev_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    char *dst = static_cast<char *>(c->rows) + rb * c->size;
+    if (strided)   // a pitched copy gathers the field of every record: source pitch = record stride, width = one row
+        UCFP_CUDA_TRY(cudaMemcpy2DAsync(dst, rb, static_cast<const char *>(src) + field_offset, src_stride, rb, n, kr, st));
+    else
+        UCFP_CUDA_TRY(cudaMemcpyAsync(dst, src, rb * n, kr, st));
+    bool host_ids = false;
     if (mode == 1) {
-        cudaMemcpyKind ki = classify(ids) == Mem::Device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        UCFP_CUDA_TRY(cudaMemcpyAsync(c->ids + c->size, ids, 8 * n, ki, st));
+        host_ids = classify(ids) != Mem::Device;
+        UCFP_CUDA_TRY(cudaMemcpyAsync(c->ids + c->size, ids, 8 * n, host_ids ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
     }
-    UCFP_TRY(after_append(c, c->size, n));
+    UCFP_TRY(after_append(lane, c, c->size, n));
     // host sources may be reused by the caller as soon as we return
-    if (kr == cudaMemcpyHostToDevice || mode == 1) UCFP_CUDA_TRY(cudaStreamSynchronize(st));
+    UCFP_TRY(finish_call(lane, !dev_src || host_ids));
     c->id_mode = mode;
     c->size += n;
     return UCFP_OK;
+}
+
+int ucfp_corpus_append(ucfp_corpus *c, const uint64_t *ids, const void *rows, uint64_t n) {
+    UCFP_API_BEGIN
+    UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
+    return append_common(c, ids, rows, 0, 0, n, false);
+    UCFP_API_END
 }
 
 int ucfp_corpus_append_strided(ucfp_corpus *c, const uint64_t *ids, const void *records, uint64_t record_stride,
                                uint64_t field_offset, uint64_t n) {
+    UCFP_API_BEGIN
     UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
-    UCFP_GUARD(c->ctx);
-    if (n == 0) return UCFP_OK;
-    UCFP_REQUIRE(records != nullptr, UCFP_E_INVALID, "records is NULL");
-    size_t rb = row_bytes(c);
-    UCFP_REQUIRE(record_stride >= field_offset + rb, UCFP_E_INVALID, "record stride %llu cannot hold a %zu-byte field at offset %llu",
-                 (unsigned long long)record_stride, rb, (unsigned long long)field_offset);
-    UCFP_REQUIRE(c->size + n <= c->capacity, UCFP_E_CAPACITY, "append of %llu rows exceeds capacity %llu (size %llu)",
-                 (unsigned long long)n, (unsigned long long)c->capacity, (unsigned long long)c->size);
-    int mode = ids ? 1 : 2;
-    UCFP_REQUIRE(c->id_mode == 0 || c->id_mode == mode, UCFP_E_STATE, "corpus mixes explicit and implicit record ids");
-    cudaStream_t st = c->ctx->stream;
-    if (mode == 1 && !c->ids) UCFP_CUDA_TRY(cudaMalloc((void **)&c->ids, 8 * (c->capacity + 16)));
-    const bool dev_src = classify(records) == Mem::Device;
-    // a pitched copy gathers the field of every record: source pitch = record stride, width = one row
-    UCFP_CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(c->rows) + rb * c->size, rb, static_cast<const char *>(records) + field_offset,
-                                    record_stride, rb, n, dev_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-    if (mode == 1) {
-        cudaMemcpyKind ki = classify(ids) == Mem::Device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        UCFP_CUDA_TRY(cudaMemcpyAsync(c->ids + c->size, ids, 8 * n, ki, st));
-    }
-    UCFP_TRY(after_append(c, c->size, n));
-    if (!dev_src || mode == 1) UCFP_CUDA_TRY(cudaStreamSynchronize(st));
-    c->id_mode = mode;
-    c->size += n;
-    return UCFP_OK;
+    return append_common(c, ids, records, record_stride, field_offset, n, true);
+    UCFP_API_END
 }
 
 int ucfp_corpus_append_synthetic(ucfp_corpus *c, uint64_t seed, uint64_t start_row, uint64_t n) {
+    UCFP_API_BEGIN
     UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
-    UCFP_GUARD(c->ctx);
+    std::unique_lock<std::shared_mutex> wl(c->rw);
+    UCFP_LEASE(c->ctx);
     UCFP_REQUIRE(c->kind == UCFP_KIND_HAMMING64 || c->kind == UCFP_KIND_MINHASH128, UCFP_E_UNSUPPORTED,
                  "synthetic rows exist for HAMMING64 and MINHASH128 corpora only");
     UCFP_REQUIRE(c->size + n <= c->capacity, UCFP_E_CAPACITY, "append of %llu rows exceeds capacity", (unsigned long long)n);
     UCFP_REQUIRE(c->id_mode == 0 || c->id_mode == 2, UCFP_E_STATE, "corpus mixes explicit and implicit record ids");
     uint64_t wpr = c->kind == UCFP_KIND_HAMMING64 ? 1 : 128;
-    UCFP_TRY(synth_fill_u64(c->ctx, static_cast<uint64_t *>(c->rows) + c->size * wpr, n * wpr, seed, start_row * wpr));
-    UCFP_TRY(after_append(c, c->size, n));
+    UCFP_TRY(synth_fill_u64(lane, static_cast<uint64_t *>(c->rows) + c->size * wpr, n * wpr, seed, start_row * wpr));
+    UCFP_TRY(after_append(lane, c, c->size, n));
+    UCFP_TRY(finish_call(lane, false));
     c->id_mode = 2;
     c->size += n;
     return UCFP_OK;
+    UCFP_API_END
 }
 
-// ---- scans --------------------------------------------------------------------------------
+int ucfp_corpus_reserve(ucfp_corpus *c, uint64_t capacity) {
+    UCFP_API_BEGIN
+    UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
+    std::unique_lock<std::shared_mutex> wl(c->rw);
+    UCFP_LEASE(c->ctx);
+    if (capacity <= c->capacity) return UCFP_OK;
+    UCFP_TRY(corpus_grow(lane, c, capacity));
+    return finish_call(lane, true);
+    UCFP_API_END
+}
+
+int ucfp_corpus_delete(ucfp_corpus *c, const uint64_t *ids, uint64_t n, uint64_t *n_removed) {
+    UCFP_API_BEGIN
+    UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
+    if (n_removed) *n_removed = 0;
+    std::unique_lock<std::shared_mutex> wl(c->rw);
+    UCFP_LEASE(c->ctx);
+    if (n == 0) return UCFP_OK;
+    UCFP_REQUIRE(ids != nullptr, UCFP_E_INVALID, "ids is NULL");
+    UCFP_TRY(corpus_delete_ids(lane, c, ids, n, n_removed));
+    return finish_call(lane, true);
+    UCFP_API_END
+}
+
+int ucfp_corpus_upsert(ucfp_corpus *c, const uint64_t *ids, const void *rows, uint64_t n, uint64_t *n_replaced) {
+    UCFP_API_BEGIN
+    UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
+    if (n_replaced) *n_replaced = 0;
+    std::unique_lock<std::shared_mutex> wl(c->rw);
+    UCFP_LEASE(c->ctx);
+    if (n == 0) return UCFP_OK;
+    UCFP_REQUIRE(ids != nullptr && rows != nullptr, UCFP_E_INVALID, "ids or rows is NULL");
+    UCFP_TRY(corpus_upsert_rows(lane, c, ids, rows, n, n_replaced));
+    return finish_call(lane, true);
+    UCFP_API_END
+}
 
 }  // extern "C"
 
-template <typename Key, typename ScanFn>
-static int run_scan(ucfp_corpus *c, int want_kind, const void *queries, size_t q_bytes, size_t nq, size_t k, uint64_t *ids_out,
-                    Key *keys_out, ScanFn scan) {
+// ---- scans --------------------------------------------------------------------------------
+namespace ucfp {
+
+// Shared by the scan entry points and the batcher (batcher.cu): one batch of queries against one corpus.
+int run_scan_any(ucfp_corpus *c, int want_kind, const void *queries, size_t nq, size_t k, uint64_t *ids_out, void *keys_out) {
     UCFP_REQUIRE(c != nullptr, UCFP_E_INVALID, "null corpus");
-    ucfp_ctx *ctx = c->ctx;
-    UCFP_GUARD(ctx);
+    std::shared_lock<std::shared_mutex> rl(c->rw);
+    UCFP_LEASE(c->ctx);
     UCFP_REQUIRE(c->kind == want_kind, UCFP_E_STATE, "corpus kind %d cannot serve this scan (needs kind %d)", c->kind, want_kind);
     if (nq == 0 || k == 0) return UCFP_OK;
     UCFP_REQUIRE(queries && ids_out && keys_out, UCFP_E_INVALID, "NULL query or output buffer");
+    const size_t q_bytes = nq * row_bytes(c);
     const void *q_dev = nullptr;
-    UCFP_TRY(stage_in(ctx, ctx->q_dev, queries, q_bytes, &q_dev));
+    UCFP_TRY(stage_in(lane, lane->q_dev, queries, q_bytes, &q_dev));
     void *ids_dev = nullptr, *keys_dev = nullptr;
     bool ids_host = false, keys_host = false;
-    UCFP_TRY(stage_out(ctx->out_ids_dev, ids_out, 8 * nq * k, &ids_dev, &ids_host));
-    UCFP_TRY(stage_out(ctx->out_keys_dev, keys_out, sizeof(Key) * nq * k, &keys_dev, &keys_host));
-    UCFP_TRY(stats_reset(ctx));
-    UCFP_TRY(scan(q_dev, static_cast<uint64_t *>(ids_dev), static_cast<Key *>(keys_dev)));
-    if (ids_host) UCFP_TRY(copy_back(ctx, ids_out, ids_dev, 8 * nq * k));
-    if (keys_host) UCFP_TRY(copy_back(ctx, keys_out, keys_dev, sizeof(Key) * nq * k));
-    if (ids_host || keys_host) UCFP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    return UCFP_OK;
+    UCFP_TRY(stage_out(lane->out_ids_dev, ids_out, 8 * nq * k, &ids_dev, &ids_host));
+    UCFP_TRY(stage_out(lane->out_keys_dev, keys_out, 4 * nq * k, &keys_dev, &keys_host));
+    UCFP_TRY(stats_reset(lane));
+    if (want_kind == UCFP_KIND_HAMMING64)
+        UCFP_TRY(hamming_scan(lane, c, static_cast<const uint64_t *>(q_dev), nq, k, static_cast<uint64_t *>(ids_dev), static_cast<uint32_t *>(keys_dev)));
+    else if (want_kind == UCFP_KIND_MINHASH128)
+        UCFP_TRY(jaccard_scan(lane, c, static_cast<const uint64_t *>(q_dev), nq, k, static_cast<uint64_t *>(ids_dev), static_cast<uint32_t *>(keys_dev)));
+    else
+        UCFP_TRY(cosine_scan(lane, c, static_cast<const float *>(q_dev), nq, k, static_cast<uint64_t *>(ids_dev), static_cast<float *>(keys_dev)));
+    if (ids_host) UCFP_TRY(copy_back(lane, ids_out, ids_dev, 8 * nq * k));
+    if (keys_host) UCFP_TRY(copy_back(lane, keys_out, keys_dev, 4 * nq * k));
+    {
+        std::lock_guard<std::mutex> lk(c->ctx->mu);
+        for (int i = 0; i < c->ctx->n_lanes; ++i) if (c->ctx->lanes[i] == lane) c->ctx->last_scan_lane = i;
+    }
+    return finish_call(lane, ids_host || keys_host);
 }
+
+}  // namespace ucfp
 
 extern "C" {
 
 int ucfp_scan_hamming(ucfp_corpus *c, const uint64_t *queries, size_t nq, size_t k, uint64_t *ids_out, uint32_t *dist_out) {
-    return run_scan<uint32_t>(c, UCFP_KIND_HAMMING64, queries, 8 * nq, nq, k, ids_out, dist_out,
-                              [&](const void *q, uint64_t *io, uint32_t *ko) {
-                                  return hamming_scan(c, static_cast<const uint64_t *>(q), nq, k, io, ko);
-                              });
+    UCFP_API_BEGIN
+    return run_scan_any(c, UCFP_KIND_HAMMING64, queries, nq, k, ids_out, dist_out);
+    UCFP_API_END
 }
 
 int ucfp_scan_jaccard(ucfp_corpus *c, const uint64_t *queries, size_t nq, size_t k, uint64_t *ids_out, uint32_t *matches_out) {
-    return run_scan<uint32_t>(c, UCFP_KIND_MINHASH128, queries, 1024 * nq, nq, k, ids_out, matches_out,
-                              [&](const void *q, uint64_t *io, uint32_t *ko) {
-                                  return jaccard_scan(c, static_cast<const uint64_t *>(q), nq, k, io, ko);
-                              });
+    UCFP_API_BEGIN
+    return run_scan_any(c, UCFP_KIND_MINHASH128, queries, nq, k, ids_out, matches_out);
+    UCFP_API_END
 }
 
 int ucfp_scan_cosine(ucfp_corpus *c, const float *queries, size_t nq, size_t k, uint64_t *ids_out, float *score_out) {
-    size_t dim = c ? c->dim : 0;
-    return run_scan<float>(c, UCFP_KIND_COSINE, queries, 4 * dim * nq, nq, k, ids_out, score_out,
-                           [&](const void *q, uint64_t *io, float *ko) {
-                               return cosine_scan(c, static_cast<const float *>(q), nq, k, io, ko);
-                           });
+    UCFP_API_BEGIN
+    return run_scan_any(c, UCFP_KIND_COSINE, queries, nq, k, ids_out, score_out);
+    UCFP_API_END
+}
+
+int ucfp_ctx_last_scan_fallbacks(ucfp_ctx *ctx, uint64_t *queries_recomputed) {
+    UCFP_API_BEGIN
+    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    UCFP_REQUIRE(queries_recomputed != nullptr, UCFP_E_INVALID, "NULL output");
+    *queries_recomputed = 0;
+    UCFP_TRY(ucfp_ctx_synchronize(ctx));
+    DeviceGuard dg(ctx->device);
+    void *stats = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        stats = ctx->lanes[ctx->last_scan_lane]->stats.ptr;
+    }
+    if (!stats) return UCFP_OK;
+    UCFP_CUDA_TRY(cudaMemcpy(queries_recomputed, stats, 8, cudaMemcpyDeviceToHost));
+    return UCFP_OK;
+    UCFP_API_END
 }
 
 }  // extern "C"
 
-extern "C" int ucfp_ctx_last_scan_fallbacks(ucfp_ctx *ctx, uint64_t *queries_recomputed) {
-    UCFP_GUARD(ctx);
-    UCFP_REQUIRE(queries_recomputed != nullptr, UCFP_E_INVALID, "NULL output");
-    *queries_recomputed = 0;
-    if (!ctx->stats.ptr) return UCFP_OK;
-    UCFP_CUDA_TRY(cudaMemcpyAsync(queries_recomputed, ctx->stats.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    UCFP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    return UCFP_OK;
-}
-
 template <typename Key, typename MergeFn>
 static int run_merge(ucfp_ctx *ctx, const uint64_t *ids_in, const Key *keys_in, size_t parts, size_t nq, size_t k,
                      uint64_t *ids_out, Key *keys_out, MergeFn merge) {
-    UCFP_GUARD(ctx);
+    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    UCFP_LEASE(ctx);
     if (nq == 0 || k == 0 || parts == 0) return UCFP_OK;
     UCFP_REQUIRE(ids_in && keys_in && ids_out && keys_out, UCFP_E_INVALID, "NULL buffer");
     size_t n_in = parts * nq * k;
     const void *ids_in_dev = nullptr, *keys_in_dev = nullptr;
-    UCFP_TRY(stage_in(ctx, ctx->cand, ids_in, 8 * n_in, &ids_in_dev));
-    UCFP_TRY(stage_in(ctx, ctx->misc, keys_in, sizeof(Key) * n_in, &keys_in_dev));
+    UCFP_TRY(stage_in(lane, lane->cand, ids_in, 8 * n_in, &ids_in_dev));
+    UCFP_TRY(stage_in(lane, lane->misc, keys_in, sizeof(Key) * n_in, &keys_in_dev));
     void *ids_dev = nullptr, *keys_dev = nullptr;
     bool ids_host = false, keys_host = false;
-    UCFP_TRY(stage_out(ctx->out_ids_dev, ids_out, 8 * nq * k, &ids_dev, &ids_host));
-    UCFP_TRY(stage_out(ctx->out_keys_dev, keys_out, sizeof(Key) * nq * k, &keys_dev, &keys_host));
-    UCFP_TRY(merge(static_cast<const uint64_t *>(ids_in_dev), static_cast<const Key *>(keys_in_dev),
+    UCFP_TRY(stage_out(lane->out_ids_dev, ids_out, 8 * nq * k, &ids_dev, &ids_host));
+    UCFP_TRY(stage_out(lane->out_keys_dev, keys_out, sizeof(Key) * nq * k, &keys_dev, &keys_host));
+    UCFP_TRY(merge(lane, static_cast<const uint64_t *>(ids_in_dev), static_cast<const Key *>(keys_in_dev),
                    static_cast<uint64_t *>(ids_dev), static_cast<Key *>(keys_dev)));
-    if (ids_host) UCFP_TRY(copy_back(ctx, ids_out, ids_dev, 8 * nq * k));
-    if (keys_host) UCFP_TRY(copy_back(ctx, keys_out, keys_dev, sizeof(Key) * nq * k));
-    if (ids_host || keys_host) UCFP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    return UCFP_OK;
+    if (ids_host) UCFP_TRY(copy_back(lane, ids_out, ids_dev, 8 * nq * k));
+    if (keys_host) UCFP_TRY(copy_back(lane, keys_out, keys_dev, sizeof(Key) * nq * k));
+    return finish_call(lane, ids_host || keys_host);
 }
 
 extern "C" {
 
 int ucfp_merge_topk_u32(ucfp_ctx *ctx, const uint64_t *ids_in, const uint32_t *keys_in, size_t parts, size_t nq, size_t k,
                         int descending, uint64_t *ids_out, uint32_t *keys_out) {
-    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    UCFP_API_BEGIN
     return run_merge<uint32_t>(ctx, ids_in, keys_in, parts, nq, k, ids_out, keys_out,
-                               [&](const uint64_t *ii, const uint32_t *ki, uint64_t *io, uint32_t *ko) {
-                                   return merge_u32(ctx, ii, ki, parts, nq, k, descending, io, ko);
+                               [&](ucfp_lane *ln, const uint64_t *ii, const uint32_t *ki, uint64_t *io, uint32_t *ko) {
+                                   return merge_u32(ln, ii, ki, parts, nq, k, descending, io, ko);
                                });
+    UCFP_API_END
 }
 
 int ucfp_merge_topk_f32(ucfp_ctx *ctx, const uint64_t *ids_in, const float *scores_in, size_t parts, size_t nq, size_t k,
                         uint64_t *ids_out, float *scores_out) {
-    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    UCFP_API_BEGIN
     return run_merge<float>(ctx, ids_in, scores_in, parts, nq, k, ids_out, scores_out,
-                            [&](const uint64_t *ii, const float *ki, uint64_t *io, float *ko) {
-                                return merge_f32(ctx, ii, ki, parts, nq, k, io, ko);
+                            [&](ucfp_lane *ln, const uint64_t *ii, const float *ki, uint64_t *io, float *ko) {
+                                return merge_f32(ln, ii, ki, parts, nq, k, io, ko);
                             });
+    UCFP_API_END
 }
 
 // ---- image hashing ------------------------------------------------------------------------
 
 int ucfp_image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *imgs, size_t n, uint32_t algo_mask, ucfp_image_hashes *out,
                           int32_t *status) {
-    UCFP_GUARD(ctx);
+    UCFP_API_BEGIN
+    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    UCFP_LEASE(ctx);
     if (n == 0) return UCFP_OK;
     UCFP_REQUIRE(imgs && out, UCFP_E_INVALID, "NULL image descriptors or output");
     UCFP_REQUIRE((algo_mask & ~UCFP_ALGO_MULTI) == 0 && algo_mask != 0, UCFP_E_INVALID, "bad algo_mask 0x%x", algo_mask);
     void *out_dev = nullptr;
     bool out_host = false;
-    UCFP_TRY(stage_out(ctx->img_out_dev, out, sizeof(ucfp_image_hashes) * n, &out_dev, &out_host));
-    std::vector<int32_t> st_host(n, 0);
-    UCFP_TRY(image_hash_batch(ctx, imgs, n, algo_mask, static_cast<ucfp_image_hashes *>(out_dev), st_host.data()));
-    if (out_host) UCFP_TRY(copy_back(ctx, out, out_dev, sizeof(ucfp_image_hashes) * n));
-    if (status) {
-        if (classify(status) == Mem::Device)
-            UCFP_CUDA_TRY(cudaMemcpyAsync(status, st_host.data(), 4 * n, cudaMemcpyHostToDevice, ctx->stream));
-        else
-            memcpy(status, st_host.data(), 4 * n);
+    UCFP_TRY(stage_out(lane->img_out_dev, out, sizeof(ucfp_image_hashes) * n, &out_dev, &out_host));
+    // per-image status: straight into the caller's array when it is host memory, else through the lane's pinned staging
+    const bool status_dev = status && classify(status) == Mem::Device;
+    int32_t *st_host = status;
+    if (!status || status_dev) {
+        UCFP_TRY(lane->pin_b.reserve(4 * n));
+        st_host = lane->pin_b.as<int32_t>();
     }
-    if (out_host || status) UCFP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    return UCFP_OK;
+    UCFP_TRY(image_hash_batch(lane, imgs, n, algo_mask, static_cast<ucfp_image_hashes *>(out_dev), st_host));
+    if (out_host) UCFP_TRY(copy_back(lane, out, out_dev, sizeof(ucfp_image_hashes) * n));
+    if (status_dev) UCFP_CUDA_TRY(cudaMemcpyAsync(status, st_host, 4 * n, cudaMemcpyHostToDevice, lane->stream));
+    return finish_call(lane, out_host || status_dev);
+    UCFP_API_END
 }
 
 int ucfp_image_hash_uniform(ucfp_ctx *ctx, const uint8_t *pixels, size_t n, uint32_t width, uint32_t height, uint64_t row_stride,
                             uint64_t image_stride, uint32_t algo_mask, ucfp_image_hashes *out) {
+    UCFP_API_BEGIN
     UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
     if (n == 0) return UCFP_OK;
     UCFP_REQUIRE(pixels && out, UCFP_E_INVALID, "NULL pixels or output");
@@ -492,6 +627,7 @@ int ucfp_image_hash_uniform(ucfp_ctx *ctx, const uint8_t *pixels, size_t n, uint
     for (size_t i = 0; i < n; ++i)
         if (st[i] != UCFP_OK) { set_error("image %zu failed with status %d", i, st[i]); return st[i]; }
     return UCFP_OK;
+    UCFP_API_END
 }
 
 }  // extern "C"

@@ -7,8 +7,11 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <new>
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
@@ -85,27 +88,71 @@ struct PinnedBuf {
 }  // namespace ucfp
 
 // ---- the opaque objects of the C ABI ----------------------------------------
+struct ucfp_ctx;
+
+// Hook a group scan (group.cu) installs in the lane: between chunks the scan exchanges its per-query admission bounds with
+// the other ranks through `allgather` (an NCCL all-gather on the lane's stream).
+struct ucfp_exchange {
+    void *comm = nullptr;
+    int world = 1;
+    int (*allgather)(void *comm, const void *send, void *recv, size_t bytes, cudaStream_t st) = nullptr;
+    ucfp::DevBuf send, recv;
+    int done = 0;   // exchanges performed in the query pass in hand
+};
+
+// One stream plus the scratch a call needs.  An entry point LEASES a lane for its whole duration (api.cu, LaneLease), so
+// nothing in here is shared between concurrent calls.  The kernels-side code takes the lane as `ctx` (it is "the context
+// of this call": stream, scratch, SM count).
+struct ucfp_lane {
+    ucfp_ctx *owner = nullptr;
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t own_stream = nullptr;   // created with the lane
+    cudaStream_t stream = nullptr;       // the stream this lease runs on: own_stream, or the caller's (ucfp_ctx_set_stream)
+    bool busy = false;                   // guarded by owner->mu
+    // scratch of the scans
+    ucfp::DevBuf q_dev, out_ids_dev, out_keys_dev, cand, cand_count, qstate, flags, misc;
+    ucfp::DevBuf img_desc_dev, img_out_dev, img_status_dev, img_tables_dev, img_stage_dev;
+    ucfp::PinnedBuf pin_a, pin_b;
+    ucfp::DevBuf stats;                  // u64[4]: [0] queries recomputed by the exact fallback in this lane's last scan
+    ucfp_exchange *xch = nullptr;        // non-null during a group scan with more than one rank
+};
+
+constexpr int kUcfpMaxLanes = 16;
+
 struct ucfp_ctx {
     int device = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    std::mutex mu;                 // serialises entry points that share scratch
-    uint64_t launches = 0;         // kernels launched (gpu_launches in bench.py)
-    bool profiling = false;        // ucfp_ctx_profile_begin/_end
+    // Lane pool.  Default ("pooled") mode: every call leases a free lane -- its own stream and scratch -- so calls from
+    // different host threads run concurrently, and every call returns with its work complete.  After
+    // ucfp_ctx_set_stream ("shared-stream" mode) all calls run on the caller's stream through lane 0, one at a time,
+    // and calls whose outputs are all device buffers return asynchronously (the torch harness and bench.py use this).
+    std::mutex mu;
+    std::condition_variable cv;
+    ucfp_lane *lanes[kUcfpMaxLanes] = {};
+    int n_lanes = 0;
+    bool shared_stream = false;
+    cudaStream_t user_stream = nullptr;
+    int last_scan_lane = 0;              // lane of the most recent scan (ucfp_ctx_last_scan_fallbacks)
+    std::atomic<uint64_t> launches{0};   // kernels launched (gpu_launches in bench.py)
+    // ucfp_ctx_profile_begin/_end
+    std::atomic<bool> profiling{false};
     struct ProfRec { cudaEvent_t a, b; double units; int kind; };
+    std::mutex prof_mu;
     std::vector<ProfRec> prof;
-    // scratch shared by all scans of this context
-    ucfp::DevBuf q_dev, out_ids_dev, out_keys_dev, cand, cand_count, qstate, flags, misc;
-    ucfp::DevBuf img_desc_dev, img_out_dev, img_status_dev, img_tables_dev, img_stage_dev;
-    ucfp::PinnedBuf pin_a, pin_b;
-    ucfp::DevBuf stats;            // u64[4]: [0] queries recomputed by the exact fallback in the last scan
-    void *image_cache = nullptr;   // per-shape tap tables of image.cu (owned by it; freed by image_cache_destroy)
+    // per-shape tap tables of image.cu (owned by it; freed by image_cache_destroy), shared by all lanes
+    std::mutex image_mu;
+    void *image_cache = nullptr;
+    // launch parameters that depend on the device only, computed once by the *_device_init functions at ucfp_init
+    int ham_scan_occ = 1, jac_scan_occ = 1, ham_exact_occ = 1, jac_exact_occ = 1, cos_exact_occ = 1;
 };
 
 struct ucfp_corpus {
     ucfp_ctx *ctx = nullptr;
+    // Scans hold this shared for the whole call, append / clear / delete / upsert / refresh hold it exclusively.
+    std::shared_mutex rw;
     int kind = 0;
     uint32_t dim = 0;
     uint64_t capacity = 0;
@@ -133,20 +180,23 @@ inline Mem classify(const void *p) {
     return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? Mem::Device : Mem::Host;
 }
 
-inline void count_launch(ucfp_ctx *ctx, uint64_t n = 1) { ctx->launches += n; }
+inline void count_launch(ucfp_lane *ctx, uint64_t n = 1) { ctx->owner->launches.fetch_add(n, std::memory_order_relaxed); }
 
 // Brackets one launch of a dominant kernel with events when profiling is on (no-ops otherwise).
 struct ProfScope {
-    ucfp_ctx *ctx; cudaEvent_t a = nullptr, b = nullptr; double units; int kind;
-    ProfScope(ucfp_ctx *c, int kind_, double units_) : ctx(c), units(units_), kind(kind_) {
-        if (!ctx->profiling) return;
+    ucfp_lane *ctx; cudaEvent_t a = nullptr, b = nullptr; double units; int kind;
+    ProfScope(ucfp_lane *c, int kind_, double units_) : ctx(c), units(units_), kind(kind_) {
+        if (!ctx->owner->profiling.load(std::memory_order_relaxed)) return;
         if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; cudaGetLastError(); return; }
         cudaEventRecord(a, ctx->stream);
     }
     ~ProfScope() {
         if (!a) return;
         cudaEventRecord(b, ctx->stream);
-        ctx->prof.push_back(ucfp_ctx::ProfRec{a, b, units, kind});
+        try {
+            std::lock_guard<std::mutex> lk(ctx->owner->prof_mu);
+            ctx->owner->prof.push_back(ucfp_ctx::ProfRec{a, b, units, kind});
+        } catch (...) { cudaEventDestroy(a); cudaEventDestroy(b); }
     }
 };
 
@@ -157,23 +207,32 @@ inline int check_launch(const char *what) {
 }
 
 // ---- kernels-side entry points implemented in the per-path .cu files -------
-int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, uint32_t *dist_out_dev);
-int jaccard_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, uint32_t *m_out_dev);
-int hamming_on_append(ucfp_corpus *c, uint64_t first_row, uint64_t n);
-int jaccard_on_append(ucfp_corpus *c, uint64_t first_row, uint64_t n);
-int cosine_scan(ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, float *score_out_dev);
-int cosine_on_append(ucfp_corpus *c, uint64_t first_row, uint64_t n);
-int merge_u32(ucfp_ctx *ctx, const uint64_t *ids_in, const uint32_t *keys_in, size_t parts, size_t nq, size_t k,
+// `ctx` is the lane the call has leased: its stream, its scratch.
+int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, uint32_t *dist_out_dev);
+int jaccard_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, uint32_t *m_out_dev);
+int cosine_scan(ucfp_lane *ctx, ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, float *score_out_dev);
+int hamming_on_append(ucfp_lane *ctx, ucfp_corpus *c, uint64_t first_row, uint64_t n);
+int jaccard_on_append(ucfp_lane *ctx, ucfp_corpus *c, uint64_t first_row, uint64_t n);
+int cosine_on_append(ucfp_lane *ctx, ucfp_corpus *c, uint64_t first_row, uint64_t n);
+int merge_u32(ucfp_lane *ctx, const uint64_t *ids_in, const uint32_t *keys_in, size_t parts, size_t nq, size_t k,
               int descending, uint64_t *ids_out, uint32_t *keys_out);
-int merge_f32(ucfp_ctx *ctx, const uint64_t *ids_in, const float *keys_in, size_t parts, size_t nq, size_t k,
+int merge_f32(ucfp_lane *ctx, const uint64_t *ids_in, const float *keys_in, size_t parts, size_t nq, size_t k,
               uint64_t *ids_out, float *keys_out);
-int synth_fill_u64(ucfp_ctx *ctx, uint64_t *dst_dev, uint64_t nwords, uint64_t seed, uint64_t start_word);
-int image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *descs_host, size_t n, uint32_t algo_mask,
+int pack_topk(ucfp_lane *ctx, const uint64_t *ids, const void *keys32, size_t n, void *records_out);
+int merge_packed(ucfp_lane *ctx, const void *records, size_t parts, size_t nq, size_t k, int key_is_f32, int descending, uint64_t *ids_out, void *keys_out);
+int synth_fill_u64(ucfp_lane *ctx, uint64_t *dst_dev, uint64_t nwords, uint64_t seed, uint64_t start_word);
+int image_hash_batch(ucfp_lane *ctx, const ucfp_image_desc *descs_host, size_t n, uint32_t algo_mask,
                      ucfp_image_hashes *out_dev, int32_t *status_host);
+// once per context, with the context's device current: kernel attributes (dynamic shared memory opt-in) and occupancies
+int hamming_device_init(ucfp_ctx *ctx);
+int jaccard_device_init(ucfp_ctx *ctx);
+int cosine_device_init(ucfp_ctx *ctx);
+int image_device_init(ucfp_ctx *ctx);
+int merge_device_init(ucfp_ctx *ctx);
 
 void image_cache_destroy(ucfp_ctx *ctx);
-int stats_reset(ucfp_ctx *ctx);
-int stats_add_flags(ucfp_ctx *ctx, const uint32_t *flags_dev, uint32_t nq);
+int stats_reset(ucfp_lane *ctx);
+int stats_add_flags(ucfp_lane *ctx, const uint32_t *flags_dev, uint32_t nq);
 
 // splitmix64 counter PRNG of docs/HASH_SPEC.md section 8
 __host__ __device__ inline uint64_t mix64(uint64_t z) {

@@ -401,17 +401,25 @@ int make_map(CUtensorMap *map, void *base, uint64_t rows, uint32_t dim_pad, uint
 
 }  // namespace
 
-int cosine_on_append(ucfp_corpus *c, uint64_t first_row, uint64_t n) {
+int cosine_on_append(ucfp_lane *ctx, ucfp_corpus *c, uint64_t first_row, uint64_t n) {
     if (n == 0) return UCFP_OK;
     uint64_t threads = n * 8;
-    cosine_prepare_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->ctx->stream>>>(
+    cosine_prepare_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(
         static_cast<const float *>(c->rows), first_row, n, c->dim, c->dim_pad, c->cos_inv_norm, static_cast<__nv_bfloat16 *>(c->cos_bf16));
-    count_launch(c->ctx);
+    count_launch(ctx);
     return check_launch("cosine_prepare");
 }
 
-int cosine_scan(ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, float *score_out_dev) {
-    ucfp_ctx *ctx = c->ctx;
+int cosine_device_init(ucfp_ctx *ctx) {
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(cosine_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(cosine_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
+    int occ = 0;
+    UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exact_select_kernel<CosineKey>, 256, 0));
+    ctx->cos_exact_occ = occ < 1 ? 1 : (occ > 4 ? 4 : occ);
+    return UCFP_OK;
+}
+
+int cosine_scan(ucfp_lane *ctx, ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, float *score_out_dev) {
     cudaStream_t st = ctx->stream;
     const uint64_t N = c->size;
     const uint32_t dim = c->dim, dim_pad = c->dim_pad;
@@ -428,8 +436,6 @@ int cosine_scan(ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_
     const uint64_t *ids = c->id_mode == 1 ? c->ids : nullptr;
     CUtensorMap map_rows;
     UCFP_TRY(make_map(&map_rows, c->cos_bf16, c->capacity + 256, dim_pad, kTileRows));
-    UCFP_CUDA_TRY(cudaFuncSetAttribute(cosine_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-    UCFP_CUDA_TRY(cudaFuncSetAttribute(cosine_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
 
     for (size_t q0 = 0; q0 < nq; q0 += kMaxQueriesPerPass) {
         const uint32_t nqp = (uint32_t)((nq - q0 < kMaxQueriesPerPass) ? nq - q0 : kMaxQueriesPerPass);
@@ -495,7 +501,7 @@ int cosine_scan(ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_
         UCFP_TRY(check_launch("cosine scan"));
         CosineKey key{rows, row_norm, qp, q_norm, dim, nullptr, 0.0f};
         UCFP_TRY(stats_add_flags(ctx, S.flags, nqp));
-        UCFP_TRY(exact_select_fallback(c, key, S.flags, nqp, (uint32_t)k, 0u, ids_out, reinterpret_cast<uint32_t *>(score_out)));
+        UCFP_TRY(exact_select_fallback(ctx, c, ctx->owner->cos_exact_occ, key, S.flags, nqp, (uint32_t)k, 0u, ids_out, reinterpret_cast<uint32_t *>(score_out)));
         size_t tot = (size_t)nqp * k;
         fix_sentinel_scores_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ids_out, score_out, S.flags, (uint32_t)k, tot);
         count_launch(ctx);

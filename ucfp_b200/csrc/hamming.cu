@@ -248,6 +248,7 @@ struct MmaScanArgs {
     uint64_t row0, row_end;                  // rows [row0, row_end), row0 even
     const QSlot *slots; const uint64_t *kth_id; uint32_t nq;
     uint64_t *cand; uint32_t *count; uint32_t cap;
+    uint32_t wait_flags;                     // bit 0: MMA issuer and TMA producer spin on their mbarriers; bit 1: epilogue warps spin
 };
 
 // Cold path of one lane (= one query) whose bounds were crossed somewhere in its 64 accumulators.  It runs AFTER the warp
@@ -255,12 +256,13 @@ struct MmaScanArgs {
 // so a fire delays one warp, not the CTA's MMA pipeline.  Nothing waits on global memory except the list append: query
 // slots and k-th ids sit in shared memory and both distances are decoded from D = -x_a + 64 x_b  (u = 64 - x_a is D's
 // low 7 bits ^ 64; x_b = (D + x_a) / 64).  Only u == 0, where x_a = 64 and -64 alias, reads the two codes.
-__device__ __forceinline__ void hamming_mma_settle(const uint32_t (&p)[32], uint64_t first_row, uint32_t thr_hot, uint32_t q,
+template <int NREG>   // NREG packed registers = 2 NREG accumulator columns = 4 NREG codes starting at first_row
+__device__ __forceinline__ void hamming_mma_settle(const uint32_t (&p)[NREG], uint64_t first_row, uint32_t thr_hot, uint32_t q,
                                                    const MmaScanArgs &A, const uint4 *s_q, const uint64_t *s_kid) {
     const int32_t hi_bound = 64 * (63 - 2 * (int32_t)thr_hot);
     uint32_t m_even = 0, m_odd = 0;   // bit c: column 2c / 2c + 1 can hold an admissible pair
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
+    for (int c = 0; c < NREG; ++c) {
         const int32_t de = (int32_t)(int16_t)(p[c] & 0xFFFFu), dq = (int32_t)p[c] >> 16;
         if (((((uint32_t)de ^ 64u) & 127u) <= 2 * thr_hot) | (de >= hi_bound)) m_even |= 1u << c;
         if (((((uint32_t)dq ^ 64u) & 127u) <= 2 * thr_hot) | (dq >= hi_bound)) m_odd |= 1u << c;
@@ -275,7 +277,7 @@ __device__ __forceinline__ void hamming_mma_settle(const uint32_t (&p)[32], uint
         m &= m - 1;
         uint32_t reg = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) reg = (c == j) ? p[j] : reg;   // register select: no local-memory copy of p[]
+        for (int j = 0; j < NREG; ++j) reg = (c == j) ? p[j] : reg;   // register select: no local-memory copy of p[]
         const int32_t D = odd ? (int32_t)reg >> 16 : (int32_t)(int16_t)(reg & 0xFFFFu);
         const uint64_t r0 = first_row + 2 * (2 * c + (odd ? 1 : 0));
         const uint32_t u = ((uint32_t)D ^ 64u) & 127u;
@@ -309,6 +311,9 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool spin_ctl = A.wait_flags & 1u, spin_epi = A.wait_flags & 2u;   // developer switch (UCFP_HAMMING_WAIT): spin instead of sleeping
+    auto wait_ctl = [&](uint64_t *bar, uint32_t ph) { if (spin_ctl) mbar_wait(bar, ph); else mbar_wait_sleep(bar, ph); };
+    auto wait_epi = [&](uint64_t *bar, uint32_t ph) { if (spin_epi) mbar_wait(bar, ph); else mbar_wait_sleep(bar, ph); };
     const uint32_t q_tiles = (A.nq + kMmaQTile - 1) / kMmaQTile;
     unsigned char *sQ = smem;                                                          // [q_tiles][16 KiB] query tiles
     // operand-row stages: expansion path 2 x 32 KiB after all eight query-tile slots; image path 16 KiB each, starting right
@@ -330,10 +335,11 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
         const uint64_t kid = q < A.nq ? A.kth_id[q] : 0;
         s_q[q] = make_uint4(s.lo, s.hi, s.thr, 0);
         s_kid[q] = kid;
-        // Implicit ids grow with the row index and the k-th result is an earlier row, so a tie at distance thr can never be
-        // admitted: the hot test may use thr - 1 (about 4x fewer trips through the cold path).
+        // Implicit ids grow with the row index; when the k-th result's id precedes every row of this launch (always, in a
+        // single-corpus scan: it is an earlier row; in a group scan the bound may come from a shard with larger ids) a tie
+        // at distance thr can never be admitted: the hot test may use thr - 1 (about 4x fewer trips through the cold path).
         uint32_t hot = s.thr;
-        if (A.ids == nullptr && kid != UINT64_MAX) hot = s.thr == 0 ? 0xFFFFFFFFu : s.thr - 1;
+        if (A.ids == nullptr && kid < A.id_base + A.row0) hot = s.thr == 0 ? 0xFFFFFFFFu : s.thr - 1;
         if (q >= A.nq) hot = 0xFFFFFFFFu;
         // The hot test works on the 16-bit image of an accumulator: field y = the value itself, field x = its low 7 bits moved to
         // the top of the halfword by * 512 (the upper halfword of a register then carries < 512 of junk from the lower one, hence
@@ -364,12 +370,12 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
         uint32_t it = 0, acc_it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
-            mbar_wait_sleep(&cfull[s], ph);
+            wait_ctl(&cfull[s], ph);
             tcgen05_fence_after();
             const uint64_t bdesc = kPreExpanded ? umma_desc_sw64(smem_u32(sC + s * stage_bytes)) : umma_desc_sw128(smem_u32(sC + s * stage_bytes));
             for (uint32_t mt = 0; mt < q_tiles; ++mt, ++acc_it) {
                 const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-                mbar_wait_sleep(&tempty[as], aph ^ 1);
+                wait_ctl(&tempty[as], aph ^ 1);
                 tcgen05_fence_after();
                 if (lane == 0) {
                     const uint64_t adesc = umma_desc_sw128(smem_u32(sQ + mt * kMmaQBytes));
@@ -393,7 +399,7 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(A.ops) + (A.row0 / kMmaTileCodes) * (uint64_t)kMmaImgBytes;
                 for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                     const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
-                    mbar_wait_sleep(&cempty[s], ph ^ 1);
+                    wait_ctl(&cempty[s], ph ^ 1);
                     mbar_expect_tx(&cfull[s], kMmaImgBytes);
                     tma_bulk_g2s(sC + s * kMmaImgBytes, src + (uint64_t)tile * kMmaImgBytes, kMmaImgBytes, &cfull[s]);
                 }
@@ -416,7 +422,7 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
             for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const uint32_t s = it % kMmaStages, ph = (it / kMmaStages) & 1;
                 if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, nxt);   // next tile's codes fly while this one is expanded
-                mbar_wait_sleep(&cempty[s], ph ^ 1);
+                wait_ctl(&cempty[s], ph ^ 1);
                 mma_store_code_row(sC + s * kMmaCBytes, t, cur[0], cur[1]);
                 mma_store_code_row(sC + s * kMmaCBytes, t + 128, cur[2], cur[3]);
                 fence_proxy_async_smem();
@@ -436,7 +442,7 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
                 const uint32_t q = mt * kMmaQTile + quad * 32 + lane;
                 const uint2 bnd = s_bnd[q];
                 const uint32_t hi_pk = bnd.x, lo_pk = bnd.y;   // hi16 - 1, lo16 + 1 in both halfwords
-                mbar_wait_sleep(&tfull[as], aph);
+                wait_epi(&tfull[as], aph);
                 tcgen05_fence_after();
                 const uint32_t taddr = taddr0 + as * kMmaRows;
                 uint32_t p[32];   // register c = (D of column 2c+1) << 16 | (D of column 2c) & 0xFFFF
@@ -463,8 +469,357 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
                 as ^= 1; aph ^= as ^ 1;
                 if (fired) {   // the bound of the hot test, recomputed: thr - 1 under implicit ids (0 when nothing can be admitted)
                     const uint32_t thr = s_q[q].z;
-                    hamming_mma_settle(p, first_row, (A.ids == nullptr && s_kid[q] != UINT64_MAX) ? (thr == 0 ? 0u : thr - 1) : thr, q, A, s_q, s_kid);
+                    hamming_mma_settle<32>(p, first_row, (A.ids == nullptr && s_kid[q] < A.id_base + A.row0) ? (thr == 0 ? 0u : thr - 1) : thr, q, A, s_q, s_kid);
                 }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tcgen05_fence_after();
+        tmem_dealloc_512(tmem_base);
+    }
+}
+
+// ---- second generation of the stage-image scan -----------------------------------------------------------------------
+// Same arithmetic, operand layout and shared-memory layout as hamming_mma_scan_kernel<true>; what changes is the schedule
+// of the epilogue.  Round 1's kernel sat at 656 clk per 128 x 512-pair accumulator tile (tensor pipe 39 % active): all
+// sixteen epilogue warps wait on the same mbarrier, issue their tcgen05.ld together and then stall on it -- the TMEM read
+// port delivers ~64 B/clk per sub-partition, so the last warp of a sub-partition gets its columns ~256 clk after the first
+// and its min/max work runs with nothing left to overlap.  Here every epilogue warp reads its columns as two halves and
+// always has ONE half in flight while it reduces the other: the port stays busy across tile boundaries and the ALU work
+// hides under it.  The TMEM stage is handed back as soon as the second half has landed.  kEpiW = 16: 64 columns per warp,
+// halves of 32 columns (tcgen05.ld x16); kEpiW = 8: 128 columns per warp, halves of 64 columns (x32), half the per-item
+// bookkeeping per column.  Warps: MMA issuer, one TMA thread, kEpiW epilogue warps.
+__device__ __forceinline__ void tmem_ld_pack16_async(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_pack16_async(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld64_pack16_async(taddr, v); }
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]) :: "memory");
+}
+constexpr uint32_t kMmaNeverHiPk = 0x7FFE7FFEu;   // hi16 - 1 of a padding query (no accumulator can cross it)
+// per-halfword signed max of D and min of D << 9 against the query's two bounds (see hamming_mma_scan_kernel)
+template <int NREG>
+__device__ __forceinline__ bool hamming_mma_hot_test(const uint32_t (&p)[NREG], uint32_t hi_pk, uint32_t lo_pk) {
+    // Padding queries skip the reduction.  The branch also pins the schedule: ptxas keeps the tcgen05.ld issued just before
+    // this test AHEAD of the min/max work (without a block boundary it sinks the load to the end of the reduction, reusing
+    // the load's destination registers as temporaries, and nothing overlaps).
+    if (hi_pk == kMmaNeverHiPk) return false;
+    uint32_t mx = hi_pk, mn = lo_pk;
+#pragma unroll
+    for (int c = 0; c < NREG; c += 2) {
+        mx = __vimax3_s16x2(mx, p[c], p[c + 1]);
+        mn = __vimin3_s16x2(mn, p[c] * 512u, p[c + 1] * 512u);
+    }
+    return ((mx ^ hi_pk) | (mn ^ lo_pk)) != 0;
+}
+
+// Cold path of the second-generation kernel: the hot test fired somewhere in one half (n_codes consecutive codes) of this
+// lane's query.  It does NOT decode the accumulators: it re-reads the codes (bytes the TMA has just pulled through L2) and
+// applies the scan's admission rule to their exact distances in a rolled loop -- a dozen live registers, so the hot loop
+// keeps both accumulator halves and its bookkeeping in registers with room to spare.  Fires are ~1e-6 per thread and half
+// once the bounds have tightened.
+__device__ __forceinline__ void hamming_mma_recheck(uint64_t first_row, uint32_t n_codes, uint32_t q, const MmaScanArgs &A,
+                                                    const uint4 *s_q, const uint64_t *s_kid) {
+    const uint4 s = s_q[q];          // {lo, hi, thr, -}
+    const uint64_t kid = s_kid[q];
+#pragma unroll 1
+    for (uint32_t j = 0; j < n_codes; j += 2) {
+        const uint64_t r0 = first_row + j;   // even
+        if (r0 >= A.row_end) break;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r0 + 1 < A.row_end) v = *reinterpret_cast<const uint4 *>(A.codes + r0);
+        else { const uint64_t c = A.codes[r0]; v.x = (uint32_t)c; v.y = (uint32_t)(c >> 32); }
+        const uint32_t d0 = __popc(v.x ^ s.x) + __popc(v.y ^ s.y), d1 = __popc(v.z ^ s.x) + __popc(v.w ^ s.y);
+        if (min(d0, d1) > s.z) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint64_t r = r0 + h;
+            const uint32_t d = h ? d1 : d0;
+            if (r >= A.row_end || d > s.z) continue;
+            const uint64_t id = A.ids ? (d == s.z ? A.ids[r] : 0) : A.id_base + r;
+            if (d < s.z || id < kid) {
+                const uint32_t pos = atomicAdd(&A.count[q], 1u);
+                if (pos < A.cap) A.cand[(size_t)q * A.cap + pos] = ((uint64_t)d << 40) | r;
+            }
+        }
+    }
+}
+
+template <int kEpiW>
+__global__ void __launch_bounds__(32 * (2 + kEpiW), 1)
+hamming_mma_scan2_kernel(const __grid_constant__ MmaScanArgs A) {
+    constexpr int kColsW = kMmaRows / (kEpiW / 4);     // accumulator columns per epilogue warp: 64 or 128
+    constexpr int kHalfRegs = kColsW / 4;                // packed registers per half: 16 or 32
+    constexpr uint32_t kHalfCodes = kColsW;              // codes per half (2 per column, kColsW / 2 columns)
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool spin_ctl = A.wait_flags & 1u, spin_epi = A.wait_flags & 2u;
+    auto wait_ctl = [&](uint64_t *bar, uint32_t ph) { if (spin_ctl) mbar_wait(bar, ph); else mbar_wait_sleep(bar, ph); };
+    auto wait_epi = [&](uint64_t *bar, uint32_t ph) { if (spin_epi) mbar_wait(bar, ph); else mbar_wait_sleep(bar, ph); };
+    const uint32_t q_tiles = (A.nq + kMmaQTile - 1) / kMmaQTile;
+    unsigned char *sQ = smem;
+    unsigned char *sC = smem + (size_t)q_tiles * kMmaQBytes;
+    const uint32_t n_stages = min((uint32_t)kMmaMaxImgStages, 12u - q_tiles);
+    uint4 *s_q = reinterpret_cast<uint4 *>(smem + (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes + kMmaStages * kMmaCBytes);
+    uint64_t *s_kid = reinterpret_cast<uint64_t *>(s_q + kMmaMaxQueries);
+    uint2 *s_bnd = reinterpret_cast<uint2 *>(s_kid + kMmaMaxQueries);
+    uint64_t *cfull = reinterpret_cast<uint64_t *>(s_bnd + kMmaMaxQueries);
+    uint64_t *cempty = cfull + kMmaMaxImgStages, *tfull = cempty + kMmaMaxImgStages, *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    const uint32_t n_tiles = (uint32_t)((A.row_end - A.row0 + kMmaTileCodes - 1) / kMmaTileCodes);
+    const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    for (uint32_t q = threadIdx.x; q < q_tiles * kMmaQTile; q += blockDim.x) {
+        const QSlot s = q < A.nq ? A.slots[q] : QSlot{0, 0, 0, 0};
+        mma_store_query_row(sQ + (q / kMmaQTile) * kMmaQBytes, q % kMmaQTile, s.lo, s.hi, q < A.nq);
+        const uint64_t kid = q < A.nq ? A.kth_id[q] : 0;
+        s_q[q] = make_uint4(s.lo, s.hi, s.thr, 0);
+        s_kid[q] = kid;
+        uint32_t hot = s.thr;   // as in hamming_mma_scan_kernel: thr - 1 under implicit ids, "never" for padding queries
+        if (A.ids == nullptr && kid < A.id_base + A.row0) hot = s.thr == 0 ? 0xFFFFFFFFu : s.thr - 1;
+        if (q >= A.nq) hot = 0xFFFFFFFFu;
+        const int32_t tau = 64 - 2 * (int32_t)hot;
+        int32_t hi16 = 64 * (tau - 1), lo16 = (-tau * 512) | 0x1FF;
+        if (hot == 0xFFFFFFFFu) { hi16 = 0x7FFF; lo16 = -0x7FFF; }
+        else if (hot >= 64) { hi16 = -0x7FFF; lo16 = 0; }
+        const uint32_t hi1 = (uint16_t)(hi16 - 1), lo1 = (uint16_t)(lo16 + 1);
+        s_bnd[q] = make_uint2(hi1 << 16 | hi1, lo1 << 16 | lo1);   // hi1 == 0x7FFE only for "never" (kMmaNeverHiPk)
+    }
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < n_stages; ++s) { mbar_init(&cfull[s], 1); mbar_init(&cempty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpiW); }
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc_512(tmem_slot);
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kMmaRows >> 3) << 17) | ((uint32_t)(kMmaQTile >> 4) << 24);
+        uint32_t acc_it = 0;
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
+            wait_ctl(&cfull[s], ph);
+            tcgen05_fence_after();
+            const uint64_t bdesc = umma_desc_sw64(smem_u32(sC + s * kMmaImgBytes));
+            for (uint32_t mt = 0; mt < q_tiles; ++mt, ++acc_it) {
+                const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                wait_ctl(&tempty[as], aph ^ 1);
+                tcgen05_fence_after();
+                if (lane == 0) {
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(sQ + mt * kMmaQBytes));
+                    umma_i8(tmem_base + as * kMmaRows, adesc, bdesc, idesc, 0u);
+                    umma_i8(tmem_base + as * kMmaRows, adesc + 2, bdesc + 2, idesc, 1u);
+                    umma_commit(&tfull[as]);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) umma_commit(&cempty[s]);
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===== producer: one 16 KiB TMA bulk copy per stage image =====
+        if (lane == 0) {
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(A.ops) + (A.row0 / kMmaTileCodes) * (uint64_t)kMmaImgBytes;
+            for (uint32_t it = 0; it < my_tiles; ++it) {
+                const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
+                const uint64_t tile = blockIdx.x + (uint64_t)it * gridDim.x;
+                wait_ctl(&cempty[s], ph ^ 1);
+                mbar_expect_tx(&cfull[s], kMmaImgBytes);
+                tma_bulk_g2s(sC + s * kMmaImgBytes, src + tile * kMmaImgBytes, kMmaImgBytes, &cfull[s]);
+            }
+        }
+    } else {
+        // ===== epilogue: warp -> TMEM lane quadrant (warp % 4) and kColsW of the 256 columns, read as two halves =====
+        const uint32_t quad = warp & 3, part = (uint32_t)(warp - 2) >> 2;
+        const uint32_t taddr0 = tmem_base + ((quad * 32u) << 16) + part * kColsW;
+        const uint32_t n_items = my_tiles * q_tiles;            // item = (stage tile, query tile); accumulator stage = item & 1
+        const uint32_t bnd0 = smem_u32(s_bnd + quad * 32 + lane), bnd_end = bnd0 + q_tiles * (kMmaQTile * 8u);
+        uint32_t bnd_at = bnd0;                                  // this thread's bounds for the query tile of the item in hand
+        uint32_t par = 0;                                        // mbarrier phase parity of the stage pair in hand
+        uint32_t pa[kHalfRegs], pb[kHalfRegs];
+        // first row of (item, half h); only the cold path needs it
+        auto half_row = [&](uint32_t item, uint32_t h) {
+            const uint32_t it = item / q_tiles;
+            return A.row0 + ((uint64_t)blockIdx.x + (uint64_t)it * gridDim.x) * kMmaTileCodes + 2 * part * kColsW + h * kHalfCodes;
+        };
+        auto q_of = [&](uint32_t item) { return (item % q_tiles) * kMmaQTile + quad * 32 + lane; };
+        // one item on accumulator stage `stg` (compile-time): pa holds its first half, in flight
+        auto do_item = [&](const uint32_t stg, uint32_t item) {
+            uint32_t hi_pk, lo_pk;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(hi_pk), "=r"(lo_pk) : "r"(bnd_at));
+            const uint32_t taddr = taddr0 + stg * kMmaRows;
+            tmem_ld_wait(pa);                                    // first half landed ...
+            tmem_ld_pack16_async(taddr + kColsW / 2, pb);        // ... second half flies while the first is reduced
+            if (hamming_mma_hot_test<kHalfRegs>(pa, hi_pk, lo_pk)) hamming_mma_recheck(half_row(item, 0), kHalfCodes, q_of(item), A, s_q, s_kid);
+            tmem_ld_wait(pb);                                    // the whole stage now lives in registers: hand it back
+            tcgen05_fence_before();
+            if (lane == 0) mbar_arrive(&tempty[stg]);
+            if (item + 1 < n_items) {
+                wait_epi(&tfull[stg ^ 1], stg ? par ^ 1 : par);
+                tcgen05_fence_after();
+                tmem_ld_pack16_async(taddr0 + (stg ^ 1) * kMmaRows, pa);   // next item's first half flies while this one's second is reduced
+            }
+            if (hamming_mma_hot_test<kHalfRegs>(pb, hi_pk, lo_pk)) hamming_mma_recheck(half_row(item, 1), kHalfCodes, q_of(item), A, s_q, s_kid);
+            bnd_at += kMmaQTile * 8u;
+            if (bnd_at == bnd_end) bnd_at = bnd0;
+        };
+        if (n_items) {
+            wait_epi(&tfull[0], 0);
+            tcgen05_fence_after();
+            tmem_ld_pack16_async(taddr0, pa);
+            for (uint32_t item = 0; item < n_items; item += 2) {
+                do_item(0, item);
+                if (item + 1 >= n_items) break;
+                do_item(1, item + 1);
+                par ^= 1;
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tcgen05_fence_after();
+        tmem_dealloc_512(tmem_base);
+    }
+}
+
+// ---- third schedule: one 64-column load per item as in the first generation, but the NEXT item's load is issued before
+// the current item is reduced (two 32-register images per epilogue thread, 18 warps so that ptxas may use 96 registers).
+// The stage is handed back at the top of the step, as early as in the first generation, so the MMA issuer has a whole
+// epilogue period to produce the next accumulator; what disappears is the exposed tcgen05.ld latency that all sixteen
+// epilogue warps used to sit out together once per item.
+__global__ void __launch_bounds__(32 * 18, 1)
+hamming_mma_scan3_kernel(const __grid_constant__ MmaScanArgs A) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool spin_ctl = A.wait_flags & 1u, spin_epi = A.wait_flags & 2u;
+    auto wait_ctl = [&](uint64_t *bar, uint32_t ph) { if (spin_ctl) mbar_wait(bar, ph); else mbar_wait_sleep(bar, ph); };
+    auto wait_epi = [&](uint64_t *bar, uint32_t ph) { if (spin_epi) mbar_wait(bar, ph); else mbar_wait_sleep(bar, ph); };
+    const uint32_t q_tiles = (A.nq + kMmaQTile - 1) / kMmaQTile;
+    unsigned char *sQ = smem;
+    unsigned char *sC = smem + (size_t)q_tiles * kMmaQBytes;
+    const uint32_t n_stages = min((uint32_t)kMmaMaxImgStages, 12u - q_tiles);
+    uint4 *s_q = reinterpret_cast<uint4 *>(smem + (size_t)(kMmaMaxQueries / kMmaQTile) * kMmaQBytes + kMmaStages * kMmaCBytes);
+    uint64_t *s_kid = reinterpret_cast<uint64_t *>(s_q + kMmaMaxQueries);
+    uint2 *s_bnd = reinterpret_cast<uint2 *>(s_kid + kMmaMaxQueries);
+    uint64_t *cfull = reinterpret_cast<uint64_t *>(s_bnd + kMmaMaxQueries);
+    uint64_t *cempty = cfull + kMmaMaxImgStages, *tfull = cempty + kMmaMaxImgStages, *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    const uint32_t n_tiles = (uint32_t)((A.row_end - A.row0 + kMmaTileCodes - 1) / kMmaTileCodes);
+    const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    for (uint32_t q = threadIdx.x; q < q_tiles * kMmaQTile; q += blockDim.x) {
+        const QSlot s = q < A.nq ? A.slots[q] : QSlot{0, 0, 0, 0};
+        mma_store_query_row(sQ + (q / kMmaQTile) * kMmaQBytes, q % kMmaQTile, s.lo, s.hi, q < A.nq);
+        const uint64_t kid = q < A.nq ? A.kth_id[q] : 0;
+        s_q[q] = make_uint4(s.lo, s.hi, s.thr, 0);
+        s_kid[q] = kid;
+        uint32_t hot = s.thr;   // as in hamming_mma_scan_kernel
+        if (A.ids == nullptr && kid < A.id_base + A.row0) hot = s.thr == 0 ? 0xFFFFFFFFu : s.thr - 1;
+        if (q >= A.nq) hot = 0xFFFFFFFFu;
+        const int32_t tau = 64 - 2 * (int32_t)hot;
+        int32_t hi16 = 64 * (tau - 1), lo16 = (-tau * 512) | 0x1FF;
+        if (hot == 0xFFFFFFFFu) { hi16 = 0x7FFF; lo16 = -0x7FFF; }
+        else if (hot >= 64) { hi16 = -0x7FFF; lo16 = 0; }
+        const uint32_t hi1 = (uint16_t)(hi16 - 1), lo1 = (uint16_t)(lo16 + 1);
+        s_bnd[q] = make_uint2(hi1 << 16 | hi1, lo1 << 16 | lo1);
+    }
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < n_stages; ++s) { mbar_init(&cfull[s], 1); mbar_init(&cempty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kMmaEpiWarps); }
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc_512(tmem_slot);
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kMmaRows >> 3) << 17) | ((uint32_t)(kMmaQTile >> 4) << 24);
+        uint32_t acc_it = 0;
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
+            wait_ctl(&cfull[s], ph);
+            tcgen05_fence_after();
+            const uint64_t bdesc = umma_desc_sw64(smem_u32(sC + s * kMmaImgBytes));
+            for (uint32_t mt = 0; mt < q_tiles; ++mt, ++acc_it) {
+                const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                wait_ctl(&tempty[as], aph ^ 1);
+                tcgen05_fence_after();
+                if (lane == 0) {
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(sQ + mt * kMmaQBytes));
+                    umma_i8(tmem_base + as * kMmaRows, adesc, bdesc, idesc, 0u);
+                    umma_i8(tmem_base + as * kMmaRows, adesc + 2, bdesc + 2, idesc, 1u);
+                    umma_commit(&tfull[as]);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) umma_commit(&cempty[s]);
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(A.ops) + (A.row0 / kMmaTileCodes) * (uint64_t)kMmaImgBytes;
+            for (uint32_t it = 0; it < my_tiles; ++it) {
+                const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
+                const uint64_t tile = blockIdx.x + (uint64_t)it * gridDim.x;
+                wait_ctl(&cempty[s], ph ^ 1);
+                mbar_expect_tx(&cfull[s], kMmaImgBytes);
+                tma_bulk_g2s(sC + s * kMmaImgBytes, src + tile * kMmaImgBytes, kMmaImgBytes, &cfull[s]);
+            }
+        }
+    } else {
+        const uint32_t quad = warp & 3, part = (uint32_t)(warp - 2) >> 2;
+        const uint32_t taddr0 = tmem_base + ((quad * 32u) << 16) + part * kMmaColsPerWarp;
+        const uint32_t n_items = my_tiles * q_tiles;
+        const uint32_t bnd0 = smem_u32(s_bnd + quad * 32 + lane), bnd_end = bnd0 + q_tiles * (kMmaQTile * 8u);
+        uint32_t bnd_at = bnd0, par = 0;
+        uint32_t pa[32], pb[32];
+        auto item_row = [&](uint32_t item) {
+            const uint32_t it = item / q_tiles;
+            return A.row0 + ((uint64_t)blockIdx.x + (uint64_t)it * gridDim.x) * kMmaTileCodes + 2 * part * kMmaColsPerWarp;
+        };
+        auto step = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], const uint32_t stg, uint32_t item) {
+            uint32_t hi_pk, lo_pk;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(hi_pk), "=r"(lo_pk) : "r"(bnd_at));
+            tmem_ld_wait(cur);                                   // the only outstanding load of this thread
+            tcgen05_fence_before();
+            if (lane == 0) mbar_arrive(&tempty[stg]);            // accumulators are in registers: hand the stage back at once
+            if (item + 1 < n_items) {
+                wait_epi(&tfull[stg ^ 1], stg ? par ^ 1 : par);
+                tcgen05_fence_after();
+                tmem_ld64_pack16_async(taddr0 + (stg ^ 1) * kMmaRows, nxt);   // lands while `cur` is reduced
+            }
+            if (hamming_mma_hot_test<32>(cur, hi_pk, lo_pk))
+                hamming_mma_recheck(item_row(item), 2 * kMmaColsPerWarp, (item % q_tiles) * kMmaQTile + quad * 32 + lane, A, s_q, s_kid);
+            bnd_at += kMmaQTile * 8u;
+            if (bnd_at == bnd_end) bnd_at = bnd0;
+        };
+        if (n_items) {
+            wait_epi(&tfull[0], 0);
+            tcgen05_fence_after();
+            tmem_ld64_pack16_async(taddr0, pa);
+            for (uint32_t item = 0; item < n_items; item += 2) {
+                step(pa, pb, 0, item);
+                if (item + 1 >= n_items) break;
+                step(pb, pa, 1, item + 1);
+                par ^= 1;
             }
         }
     }
@@ -492,19 +847,37 @@ struct HammingKey {
 }  // namespace
 
 // Called before c->size grows: rows [first_row, first_row + n) were just written.  The pair row of an odd first_row is rebuilt.
-int hamming_on_append(ucfp_corpus *c, uint64_t first_row, uint64_t n) {
+int hamming_on_append(ucfp_lane *ctx, ucfp_corpus *c, uint64_t first_row, uint64_t n) {
     if (!c->ham_ops || n == 0) return UCFP_OK;
     const uint64_t lo = first_row & ~1ULL, hi = first_row + n;
     const uint64_t pairs = (hi - lo + 1) / 2;
-    hamming_ops_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, c->ctx->stream>>>(static_cast<const uint64_t *>(c->rows), lo, hi, hi,
+    // `size` = rows that exist once this call is done: the appended range's end, or the corpus size when rows are rebuilt in place
+    const uint64_t size_after = hi > c->size ? hi : c->size;
+    hamming_ops_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, ctx->stream>>>(static_cast<const uint64_t *>(c->rows), lo, hi, size_after,
                                                                                   reinterpret_cast<uint4 *>(c->ham_ops));
-    count_launch(c->ctx);
+    count_launch(ctx);
     return check_launch("hamming_ops");
 }
 
-int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev,
+// Once per context (ucfp_init): opt the kernels into their dynamic shared memory and measure the occupancies the launch
+// geometry depends on -- per-device properties that used to be set on every scan call.
+int hamming_device_init(ucfp_ctx *ctx) {
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
+    int occ = 0;
+    UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_scan_kernel, kScanThreads, sizeof(QSlot) * kMaxQueriesPerPass));
+    ctx->ham_scan_occ = occ < 1 ? 1 : occ;
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
+    UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exact_select_kernel<HammingKey>, 256, 0));
+    ctx->ham_exact_occ = occ < 1 ? 1 : (occ > 4 ? 4 : occ);
+    return UCFP_OK;
+}
+
+int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev,
                  uint32_t *dist_out_dev) {
-    ucfp_ctx *ctx = c->ctx;
     cudaStream_t st = ctx->stream;
     const uint64_t N = c->size;
     UCFP_REQUIRE(k <= 2048, UCFP_E_UNSUPPORTED, "hamming scan supports k <= 2048 (got %zu)", k);
@@ -513,21 +886,18 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
         size_t tot = nq * k;
         fill_sentinel_u32_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ids_out_dev, dist_out_dev, tot);
         count_launch(ctx);
-        return check_launch("fill_sentinel");
+        UCFP_TRY(check_launch("fill_sentinel"));
+        if (!ctx->xch) return UCFP_OK;   // an empty shard of a group scan still takes part in the bound exchanges below
     }
     uint32_t cap = 4096;
     while (cap < 4 * k) cap <<= 1;
     const uint64_t *codes = static_cast<const uint64_t *>(c->rows);
     const uint64_t *ids = c->id_mode == 1 ? c->ids : nullptr;
 
-    // function attributes are per device: set them on every call (a host-side table write)
-    UCFP_CUDA_TRY(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
-    int scan_occ = 0;
-    UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_occ, hamming_scan_kernel, kScanThreads,
-                                                                 sizeof(QSlot) * kMaxQueriesPerPass));
-    if (scan_occ < 1) scan_occ = 1;
-    UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
-    UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
+    const int scan_occ = ctx->owner->ham_scan_occ;
+    static const long env_wait = getenv("UCFP_HAMMING_WAIT") ? atol(getenv("UCFP_HAMMING_WAIT")) : 0;
+    static const long env_epi_w = getenv("UCFP_HAMMING_EPI_WARPS") ? atol(getenv("UCFP_HAMMING_EPI_WARPS")) : 16;
+    static const long env_mma_v = getenv("UCFP_HAMMING_MMA_V") ? atol(getenv("UCFP_HAMMING_MMA_V")) : 2;   // 1: first-generation kernels
     static const bool env_no_mma = getenv("UCFP_HAMMING_NO_MMA") != nullptr;   // developer switches: POPC scan only /
     static const bool env_no_ops = getenv("UCFP_HAMMING_NO_OPS") != nullptr;   // expand codes in the kernel although operand rows exist
     static const long env_img_maxq = getenv("UCFP_HAMMING_IMG_MAXQ") ? atol(getenv("UCFP_HAMMING_IMG_MAXQ")) : 7 * kMmaQTile;
@@ -547,6 +917,13 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
         uint32_t *dist_out = dist_out_dev + q0 * k;
 
         hamming_init_kernel<<<(nqp + 255) / 256, 256, 0, st>>>(q_dev + q0, nqp, slots, kth, count, flags);
+        if (N == 0) {   // group scan, empty shard: contribute the trivial bound (64, none) to every exchange
+            count_launch(ctx);
+            SelectState none{cand, count, &slots[0].thr, 4, kth, flags, cap, flags + nqp};
+            while (ctx->xch->done < kBoundExchanges) UCFP_TRY(exchange_bounds(ctx, none, nqp));
+            ctx->xch->done = 0;
+            continue;
+        }
         static const long env_seed = getenv("UCFP_HAMMING_SEED") ? atol(getenv("UCFP_HAMMING_SEED")) : 0;   // developer knobs
         static const long env_mma_rows = getenv("UCFP_HAMMING_MMA_MIN_ROWS") ? atol(getenv("UCFP_HAMMING_MMA_MIN_ROWS")) : 0;
         uint32_t seed_rows = env_seed > 0 ? (uint32_t)env_seed : kSeedRows;
@@ -590,10 +967,14 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
                 const unsigned mma_grid = (unsigned)(tiles < (uint64_t)ctx->sm_count ? tiles : (uint64_t)ctx->sm_count);
                 ProfScope ps(ctx, UCFP_PROF_HAMMING_SCAN, 8.0 * (double)n * nqp);
                 ProfScope pt(ctx, UCFP_PROF_HAMMING_TENSOR, 64.0 * (double)n * nqp);
-                const MmaScanArgs margs{codes, reinterpret_cast<const uint4 *>(c->ham_ops), ids, c->id_base, pos, pos + n, slots, kth, nqp, cand, count, cap};
+                const MmaScanArgs margs{codes, reinterpret_cast<const uint4 *>(c->ham_ops), ids, c->id_base, pos, pos + n, slots, kth, nqp, cand, count, cap, (uint32_t)env_wait};
                 // With all eight query tiles in use a 512-code stage lasts ~3 300 clk and the in-kernel expansion hides completely
                 // behind it (measured 41.8 vs 43.0 ms per 1 B rows); below that the ready-made images win (7.6 vs 13.5 ms at 64-128 queries).
-                if (c->ham_ops && !env_no_ops && pos % kMmaTileCodes == 0 && (long)nqp <= env_img_maxq) hamming_mma_scan_kernel<true><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
+                const bool have_images = c->ham_ops && !env_no_ops && pos % kMmaTileCodes == 0;
+                if (have_images && env_mma_v == 3) hamming_mma_scan3_kernel<<<mma_grid, 32 * 18, kMmaSmem, st>>>(margs);
+                else if (have_images && env_mma_v >= 2 && env_epi_w == 8) hamming_mma_scan2_kernel<8><<<mma_grid, 32 * 10, kMmaSmem, st>>>(margs);
+                else if (have_images && env_mma_v >= 2) hamming_mma_scan2_kernel<16><<<mma_grid, 32 * 18, kMmaSmem, st>>>(margs);
+                else if (have_images && (long)nqp <= env_img_maxq) hamming_mma_scan_kernel<true><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
                 else hamming_mma_scan_kernel<false><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
             } else {
                 ProfScope ps(ctx, UCFP_PROF_HAMMING_SCAN, 8.0 * (double)n * nqp);
@@ -603,12 +984,19 @@ int hamming_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
             count_launch(ctx);
             pos += n;
             compact(pos == N);
+            // group scan: fold in the other shards' bounds once this shard has seen enough rows for the next exchange
+            if (ctx->xch && pos < N)
+                while (ctx->xch->done < kBoundExchanges && pos >= kBoundExchangeRows[ctx->xch->done]) UCFP_TRY(exchange_bounds(ctx, sel, nqp));
             chunk = chunk * growth < max_chunk ? chunk * growth : max_chunk;
+        }
+        if (ctx->xch) {   // exchanges this shard was too short for: the other ranks are waiting in theirs
+            while (ctx->xch->done < kBoundExchanges) UCFP_TRY(exchange_bounds(ctx, sel, nqp));
+            ctx->xch->done = 0;
         }
         UCFP_TRY(check_launch("hamming scan"));
         // exact recomputation of any query whose candidate list overflowed (device-side decision, no host sync)
         UCFP_TRY(stats_add_flags(ctx, flags, nqp));
-        UCFP_TRY(exact_select_fallback(c, HammingKey{codes, slots, 0, 0}, flags, nqp, (uint32_t)k, 0u, ids_out, dist_out));
+        UCFP_TRY(exact_select_fallback(ctx, c, ctx->owner->ham_exact_occ, HammingKey{codes, slots, 0, 0}, flags, nqp, (uint32_t)k, 0u, ids_out, dist_out));
     }
     return UCFP_OK;
 }

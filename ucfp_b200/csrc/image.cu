@@ -104,18 +104,23 @@ std::vector<HostTaps> make_taps(int src, int dst) {
 
 struct StreamSmem { uint32_t off_rowbuf, off_ring, off_bars, off_rowtab, stage_bytes, stages, chunk_rows, row_pitch, row_words; };
 
+constexpr size_t kShapeCacheMaxEntries = 256, kShapeCacheMaxBytes = size_t(256) << 20;
+
 struct ShapeTables {
     ShapeDev dev{};
     void *blob = nullptr;
+    size_t blob_bytes = 0;
+    uint32_t in_use = 0;      // calls hashing this shape right now (never evicted while > 0)
+    uint64_t last_use = 0;
     bool streamable = false;
     int threads = 0, cpt = 0;
     StreamSmem lay{};
     size_t stream_smem = 0;
 };
 
-struct ShapeCache { std::map<uint64_t, ShapeTables> m; };   // lives in ucfp_ctx::image_cache, guarded by ctx->mu
+struct ShapeCache { std::map<uint64_t, ShapeTables> m; uint64_t tick = 0; size_t bytes = 0; };   // lives in ucfp_ctx::image_cache, guarded by ucfp_ctx::image_mu
 
-int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
+int build_shape(ucfp_lane *ctx, int w, int h, ShapeTables &st) {
     std::vector<Taps> hout(5 * kHOuts), vout(5 * kVOuts);
     std::vector<float> wts;
     ShapeDev &d = st.dev;
@@ -276,6 +281,7 @@ int build_shape(ucfp_ctx *ctx, int w, int h, ShapeTables &st) {
         memcpy(&host[off_b], band_off.data(), band_off.size() * 4);
     }
     UCFP_CUDA_TRY(cudaMalloc(&st.blob, total));
+    st.blob_bytes = total;
     UCFP_CUDA_TRY(cudaMemcpyAsync(st.blob, host.data(), total, cudaMemcpyHostToDevice, ctx->stream));
     UCFP_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // `host` dies at return
     uint8_t *b = static_cast<uint8_t *>(st.blob);
@@ -651,7 +657,7 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
 // ---------------------------------------------------------------------------------------------
 // Host driver
 // ---------------------------------------------------------------------------------------------
-int image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *descs, size_t n, uint32_t algo_mask, ucfp_image_hashes *out_dev,
+int image_hash_batch(ucfp_lane *ctx, const ucfp_image_desc *descs, size_t n, uint32_t algo_mask, ucfp_image_hashes *out_dev,
                      int32_t *status) {
     cudaStream_t st = ctx->stream;
     UCFP_CUDA_TRY(cudaMemsetAsync(out_dev, 0, sizeof(ucfp_image_hashes) * n, st));
@@ -711,61 +717,117 @@ int image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *descs, size_t n, uint
         groups[(uint64_t)d.width << 32 | d.height].push_back(it);
     }
 
-    if (!ctx->image_cache) ctx->image_cache = new (std::nothrow) ShapeCache();
-    UCFP_REQUIRE(ctx->image_cache != nullptr, UCFP_E_OOM, "out of host memory");
-    ShapeCache &cache = *static_cast<ShapeCache *>(ctx->image_cache);
-    for (auto &kv : groups) {
-        const int w = (int)(kv.first >> 32), h = (int)(kv.first & 0xffffffffu);
-        auto found = cache.m.find(kv.first);
-        if (found == cache.m.end()) {
-            ShapeTables stb;
-            UCFP_TRY(build_shape(ctx, w, h, stb));
-            found = cache.m.emplace(kv.first, stb).first;
+    // ---- tap tables per shape: looked up (or built) under the context's image mutex and pinned by a use count, so that
+    // the bounded cache below can evict shapes nobody is hashing right now without pulling tables from under a running kernel
+    struct GroupRef { uint64_t key; ShapeTables T; std::vector<Item> *items; size_t desc_off; };
+    std::vector<GroupRef> refs;
+    refs.reserve(groups.size());
+    ucfp_ctx *own = ctx->owner;
+    auto release_refs = [&]() {
+        std::lock_guard<std::mutex> lk(own->image_mu);
+        ShapeCache &cache = *static_cast<ShapeCache *>(own->image_cache);
+        for (GroupRef &g : refs) { auto f = cache.m.find(g.key); if (f != cache.m.end() && f->second.in_use) f->second.in_use--; }
+    };
+    size_t n_items = 0;
+    {
+        std::lock_guard<std::mutex> lk(own->image_mu);
+        if (!own->image_cache) own->image_cache = new (std::nothrow) ShapeCache();
+        UCFP_REQUIRE(own->image_cache != nullptr, UCFP_E_OOM, "out of host memory");
+        ShapeCache &cache = *static_cast<ShapeCache *>(own->image_cache);
+        for (auto &kv : groups) {
+            const int w = (int)(kv.first >> 32), h = (int)(kv.first & 0xffffffffu);
+            auto found = cache.m.find(kv.first);
+            if (found == cache.m.end()) {
+                ShapeTables stb;
+                int rc = build_shape(ctx, w, h, stb);
+                if (rc != UCFP_OK) { for (GroupRef &g : refs) cache.m[g.key].in_use--; return rc; }
+                found = cache.m.emplace(kv.first, stb).first;
+                cache.bytes += stb.blob_bytes;
+                // bounded: least recently used shapes that no call is using go first (a service hashing arbitrary upload
+                // sizes would otherwise grow this map, and the device blobs behind it, without limit)
+                while ((cache.m.size() > kShapeCacheMaxEntries || cache.bytes > kShapeCacheMaxBytes)) {
+                    auto victim = cache.m.end();
+                    for (auto it2 = cache.m.begin(); it2 != cache.m.end(); ++it2)
+                        if (it2 != found && it2->second.in_use == 0 && (victim == cache.m.end() || it2->second.last_use < victim->second.last_use)) victim = it2;
+                    if (victim == cache.m.end()) break;
+                    if (victim->second.blob) cudaFree(victim->second.blob);
+                    cache.bytes -= victim->second.blob_bytes;
+                    cache.m.erase(victim);
+                }
+            }
+            found->second.in_use++;
+            found->second.last_use = ++cache.tick;
+            refs.push_back(GroupRef{kv.first, found->second, &kv.second, n_items});
+            n_items += kv.second.size();
         }
-        ShapeTables &T = found->second;
-        std::vector<Item> &items = kv.second;
-        std::vector<ImgDev> hostdesc(items.size());
-        for (size_t j = 0; j < items.size(); ++j) {
-            const uintptr_t base = (uintptr_t)items[j].dev_pixels;
-            uint32_t al = (base % 4 == 0 && items[j].stride % 4 == 0) ? 1u : 0u;
-            if (base % 16 == 0 && items[j].stride % 16 == 0 && (3 * (size_t)w) % 16 == 0) al = 2u;   // TMA bulk staging
-            hostdesc[j] = ImgDev{items[j].dev_pixels, items[j].stride, (uint32_t)items[j].idx, al};
-        }
-        // one descriptor buffer per group: the copy below must finish before the vector dies
-        ScopedDevBuf descbuf;
-        UCFP_TRY(descbuf.reserve(sizeof(ImgDev) * items.size()));
-        UCFP_CUDA_TRY(cudaMemcpyAsync(descbuf.ptr, hostdesc.data(), sizeof(ImgDev) * items.size(), cudaMemcpyHostToDevice, st));
-        uint64_t *out_words = reinterpret_cast<uint64_t *>(out_dev);
-        double units = (3.0 * w * h + 408.0) * (double)items.size();
-        if (T.streamable) {
-            size_t smem = T.stream_smem;
-            ProfScope ps(ctx, UCFP_PROF_IMAGE_HASH, units);
-            auto launch = [&](auto kern) -> int {
-                UCFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-                kern<<<(unsigned)items.size(), T.threads, smem, st>>>(T.dev, T.lay, descbuf.as<ImgDev>(), algo_mask, out_words);
-                return UCFP_OK;
-            };
-            bool all_bulk = true;
-            for (const ImgDev &d : hostdesc) all_bulk = all_bulk && d.aligned4 == 2;
-            if (T.cpt == 1) UCFP_TRY(all_bulk ? launch(image_stream_kernel<1, 512, true>) : launch(image_stream_kernel<1, 512, false>));
-            else if (T.cpt == 4) UCFP_TRY(all_bulk ? launch(image_stream_kernel<4, 256, true>) : launch(image_stream_kernel<4, 256, false>));
-            else UCFP_TRY(all_bulk ? launch(image_stream_kernel<8, 512, true>) : launch(image_stream_kernel<8, 512, false>));
-        } else {
-            size_t per = (((size_t)w * h + 15) & ~size_t(15)) + (size_t)5 * kVOuts * w * 4 + 256;
-            size_t grid = items.size();
-            size_t budget = size_t(1) << 30;
-            if (grid * per > budget) grid = budget / per ? budget / per : 1;
-            if (grid > (size_t)ctx->sm_count * 4) grid = (size_t)ctx->sm_count * 4;
-            UCFP_TRY(ctx->img_tables_dev.reserve(grid * per));
-            UCFP_CUDA_TRY(cudaFuncSetAttribute(image_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGridsBytes + sizeof(HashScratch))));
-            ProfScope ps(ctx, UCFP_PROF_IMAGE_HASH, units);
-            image_generic_kernel<<<(unsigned)grid, 256, kGridsBytes + sizeof(HashScratch), st>>>(T.dev, descbuf.as<ImgDev>(), (uint32_t)items.size(),
-                                                                                  algo_mask, ctx->img_tables_dev.as<uint8_t>(), per, out_words);
-        }
-        count_launch(ctx);
-        UCFP_TRY(check_launch("image hash"));
-        UCFP_CUDA_TRY(cudaStreamSynchronize(st));  // descbuf and hostdesc die at the end of this iteration
     }
+    // ---- one descriptor array for the whole batch (pinned staging owned by the lane, one upload), groups launch back to back
+    int rc = UCFP_OK;
+    do {
+        if ((rc = ctx->pin_a.reserve(sizeof(ImgDev) * n_items)) != UCFP_OK) break;
+        if ((rc = ctx->img_desc_dev.reserve(sizeof(ImgDev) * n_items)) != UCFP_OK) break;
+        ImgDev *hostdesc = ctx->pin_a.as<ImgDev>();
+        for (GroupRef &g : refs) {
+            const int w = (int)(g.key >> 32);
+            for (size_t j = 0; j < g.items->size(); ++j) {
+                const Item &itm = (*g.items)[j];
+                const uintptr_t base = (uintptr_t)itm.dev_pixels;
+                uint32_t al = (base % 4 == 0 && itm.stride % 4 == 0) ? 1u : 0u;
+                if (base % 16 == 0 && itm.stride % 16 == 0 && (3 * (size_t)w) % 16 == 0) al = 2u;   // TMA bulk staging
+                hostdesc[g.desc_off + j] = ImgDev{itm.dev_pixels, itm.stride, (uint32_t)itm.idx, al};
+            }
+        }
+        if (cudaMemcpyAsync(ctx->img_desc_dev.ptr, hostdesc, sizeof(ImgDev) * n_items, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            set_error("descriptor upload failed: %s", cudaGetErrorString(cudaGetLastError())); rc = UCFP_E_CUDA; break;
+        }
+        uint64_t *out_words = reinterpret_cast<uint64_t *>(out_dev);
+        for (GroupRef &g : refs) {
+            const int w = (int)(g.key >> 32), h = (int)(g.key & 0xffffffffu);
+            ShapeTables &T = g.T;
+            const size_t cnt = g.items->size();
+            const ImgDev *descs_dev = ctx->img_desc_dev.as<ImgDev>() + g.desc_off;
+            const double units = (3.0 * w * h + 408.0) * (double)cnt;
+            if (T.streamable) {
+                const size_t smem = T.stream_smem;
+                ProfScope ps(ctx, UCFP_PROF_IMAGE_HASH, units);
+                auto launch = [&](auto kern) { kern<<<(unsigned)cnt, T.threads, smem, st>>>(T.dev, T.lay, descs_dev, algo_mask, out_words); };
+                bool all_bulk = true;
+                for (size_t j = 0; j < cnt; ++j) all_bulk = all_bulk && hostdesc[g.desc_off + j].aligned4 == 2;
+                if (T.cpt == 1) { if (all_bulk) launch(image_stream_kernel<1, 512, true>); else launch(image_stream_kernel<1, 512, false>); }
+                else if (T.cpt == 4) { if (all_bulk) launch(image_stream_kernel<4, 256, true>); else launch(image_stream_kernel<4, 256, false>); }
+                else { if (all_bulk) launch(image_stream_kernel<8, 512, true>); else launch(image_stream_kernel<8, 512, false>); }
+            } else {
+                size_t per = (((size_t)w * h + 15) & ~size_t(15)) + (size_t)5 * kVOuts * w * 4 + 256;
+                size_t grid = cnt;
+                size_t budget = size_t(1) << 30;
+                if (grid * per > budget) grid = budget / per ? budget / per : 1;
+                if (grid > (size_t)ctx->sm_count * 4) grid = (size_t)ctx->sm_count * 4;
+                // generic-kernel groups of one batch share this scratch: they run one after the other on the lane's stream
+                if ((rc = ctx->img_tables_dev.reserve(grid * per)) != UCFP_OK) break;
+                ProfScope ps(ctx, UCFP_PROF_IMAGE_HASH, units);
+                image_generic_kernel<<<(unsigned)grid, 256, kGridsBytes + sizeof(HashScratch), st>>>(T.dev, descs_dev, (uint32_t)cnt, algo_mask,
+                                                                                                    ctx->img_tables_dev.as<uint8_t>(), per, out_words);
+            }
+            count_launch(ctx);
+            if ((rc = check_launch("image hash")) != UCFP_OK) break;
+        }
+    } while (false);
+    // one synchronisation per batch: the pinned descriptors may be rewritten and the shapes evicted after it
+    cudaError_t se = cudaStreamSynchronize(st);
+    release_refs();
+    if (rc == UCFP_OK && se != cudaSuccess) { set_error("image hash failed: %s", cudaGetErrorString(se)); rc = UCFP_E_CUDA; }
+    return rc;
+}
+
+int image_device_init(ucfp_ctx *) {
+    const int optin = 200 * 1024;
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(image_stream_kernel<1, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(image_stream_kernel<1, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(image_stream_kernel<4, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(image_stream_kernel<4, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(image_stream_kernel<8, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(image_stream_kernel<8, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(image_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kGridsBytes + sizeof(HashScratch))));
     return UCFP_OK;
 }
 

@@ -229,18 +229,30 @@ struct JaccardKey {
 
 }  // namespace
 
-int jaccard_on_append(ucfp_corpus *c, uint64_t first_row, uint64_t n) {
+int jaccard_on_append(ucfp_lane *ctx, ucfp_corpus *c, uint64_t first_row, uint64_t n) {
     if (n == 0) return UCFP_OK;
     uint64_t items = n * kSketchWords;
-    sketch_build_kernel<<<(unsigned)((items + 255) / 256), 256, 0, c->ctx->stream>>>(
+    sketch_build_kernel<<<(unsigned)((items + 255) / 256), 256, 0, ctx->stream>>>(
         static_cast<const uint64_t *>(c->rows), reinterpret_cast<uint32_t *>(c->mh_sketch),
         reinterpret_cast<uint32_t *>(c->mh_sketch) + sketch_plane_words(c->capacity), first_row, n);
-    count_launch(c->ctx);
+    count_launch(ctx);
     return check_launch("sketch_build");
 }
 
-int jaccard_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, uint32_t *m_out_dev) {
-    ucfp_ctx *ctx = c->ctx;
+constexpr size_t kJaccardScanSmemMax = (size_t)kMaxQueriesPerPass * (2 * kSketchWords + 1 + 2) * 4 + 8;
+
+int jaccard_device_init(ucfp_ctx *ctx) {
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(jaccard_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJaccardScanSmemMax));
+    int occ = 0;
+    UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jaccard_scan_kernel, kScanThreads, kJaccardScanSmemMax));
+    ctx->jac_scan_occ = occ < 1 ? 1 : occ;
+    UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exact_select_kernel<JaccardKey>, 256, 0));
+    ctx->jac_exact_occ = occ < 1 ? 1 : (occ > 4 ? 4 : occ);
+    return UCFP_OK;
+}
+
+int jaccard_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, uint32_t *m_out_dev) {
     cudaStream_t st = ctx->stream;
     const uint64_t N = c->size;
     UCFP_REQUIRE(k <= 2048, UCFP_E_UNSUPPORTED, "jaccard scan supports k <= 2048 (got %zu)", k);
@@ -257,12 +269,7 @@ int jaccard_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
     const uint32_t *sketch = reinterpret_cast<const uint32_t *>(c->mh_sketch);
     const uint32_t *sketch1 = sketch + sketch_plane_words(c->capacity);
     const uint64_t *ids = c->id_mode == 1 ? c->ids : nullptr;
-    UCFP_CUDA_TRY(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
-    const size_t scan_smem_max = (size_t)kMaxQueriesPerPass * (2 * kSketchWords + 1 + 2) * 4 + 8;
-    UCFP_CUDA_TRY(cudaFuncSetAttribute(jaccard_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_max));
-    int occ = 0;
-    UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jaccard_scan_kernel, kScanThreads, scan_smem_max));
-    if (occ < 1) occ = 1;
+    const int occ = ctx->owner->jac_scan_occ;
 
     for (size_t q0 = 0; q0 < nq; q0 += kMaxQueriesPerPass) {
         const uint32_t nqp = (uint32_t)((nq - q0 < kMaxQueriesPerPass) ? nq - q0 : kMaxQueriesPerPass);
@@ -319,7 +326,7 @@ int jaccard_scan(ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uin
         }
         UCFP_TRY(check_launch("jaccard scan"));
         UCFP_TRY(stats_add_flags(ctx, flags, nqp));
-        UCFP_TRY(exact_select_fallback(c, JaccardKey{sigs, qp, nullptr}, flags, nqp, (uint32_t)k, 128u, ids_out, m_out));
+        UCFP_TRY(exact_select_fallback(ctx, c, ctx->owner->jac_exact_occ, JaccardKey{sigs, qp, nullptr}, flags, nqp, (uint32_t)k, 128u, ids_out, m_out));
     }
     return UCFP_OK;
 }

@@ -42,7 +42,12 @@ __global__ void merge_topk_kernel(const uint64_t *__restrict__ ids_in, const K *
         if (i < n) {
             uint32_t p = i / k, j = i % k;
             size_t src = ((size_t)p * nq + q) * k + j;
-            id = ids_in[src]; key = keys_in[src];
+            if (keys_in) { id = ids_in[src]; key = keys_in[src]; }
+            else {   // packed 16-byte records {u64 id; 32-bit key; pad} as all-gathered by a group scan
+                const ulonglong2 rec = reinterpret_cast<const ulonglong2 *>(ids_in)[src];
+                const uint32_t bits = (uint32_t)rec.y;
+                id = rec.x; key = *reinterpret_cast<const K *>(&bits);
+            }
         }
         s_id[i] = id; s_key[i] = key;
     }
@@ -66,15 +71,14 @@ __global__ void merge_topk_kernel(const uint64_t *__restrict__ ids_in, const K *
 }
 
 template <typename K>
-int merge_impl(ucfp_ctx *ctx, const uint64_t *ids_in, const K *keys_in, size_t parts, size_t nq, size_t k, int descending,
+int merge_impl(ucfp_lane *ctx, const uint64_t *ids_in, const K *keys_in, size_t parts, size_t nq, size_t k, int descending,
                K sentinel, uint64_t *ids_out, K *keys_out) {
     if (nq == 0 || k == 0) return UCFP_OK;
     UCFP_REQUIRE(parts >= 1 && parts * k <= 16384, UCFP_E_UNSUPPORTED, "merge supports parts*k <= 16384 (got %zu)", parts * k);
     size_t P = 1;
     while (P < parts * k) P <<= 1;
     size_t smem = P * (sizeof(uint64_t) + sizeof(K));
-    auto kern = merge_topk_kernel<K>;
-    UCFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16384 * 12)));
+    auto kern = merge_topk_kernel<K>;   // dynamic shared memory opted in by merge_device_init
     kern<<<(unsigned)nq, 256, smem, ctx->stream>>>(ids_in, keys_in, (uint32_t)parts, (uint32_t)nq, (uint32_t)k,
                                                     Order<K>{descending}, sentinel, ids_out, keys_out);
     count_launch(ctx);
@@ -83,14 +87,40 @@ int merge_impl(ucfp_ctx *ctx, const uint64_t *ids_in, const K *keys_in, size_t p
 
 }  // namespace
 
-int merge_u32(ucfp_ctx *ctx, const uint64_t *ids_in, const uint32_t *keys_in, size_t parts, size_t nq, size_t k,
+int merge_device_init(ucfp_ctx *) {
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16384 * 12)));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16384 * 12)));
+    return UCFP_OK;
+}
+
+int merge_u32(ucfp_lane *ctx, const uint64_t *ids_in, const uint32_t *keys_in, size_t parts, size_t nq, size_t k,
               int descending, uint64_t *ids_out, uint32_t *keys_out) {
     return merge_impl<uint32_t>(ctx, ids_in, keys_in, parts, nq, k, descending, UINT32_MAX, ids_out, keys_out);
 }
 
-int merge_f32(ucfp_ctx *ctx, const uint64_t *ids_in, const float *keys_in, size_t parts, size_t nq, size_t k,
+int merge_f32(ucfp_lane *ctx, const uint64_t *ids_in, const float *keys_in, size_t parts, size_t nq, size_t k,
               uint64_t *ids_out, float *keys_out) {
     return merge_impl<float>(ctx, ids_in, keys_in, parts, nq, k, 1, -INFINITY, ids_out, keys_out);
+}
+
+// ---- packed (id, key) records: what a group scan exchanges (one all-gather instead of two) ------------------------
+namespace {
+__global__ void pack_topk_kernel(const uint64_t *__restrict__ ids, const uint32_t *__restrict__ keys, size_t n, ulonglong2 *out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_ulonglong2(ids[i], (unsigned long long)keys[i]);
+}
+}  // namespace
+
+int pack_topk(ucfp_lane *ctx, const uint64_t *ids, const void *keys32, size_t n, void *records_out) {
+    if (n == 0) return UCFP_OK;
+    pack_topk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ids, static_cast<const uint32_t *>(keys32), n, static_cast<ulonglong2 *>(records_out));
+    count_launch(ctx);
+    return check_launch("pack_topk");
+}
+
+int merge_packed(ucfp_lane *ctx, const void *records, size_t parts, size_t nq, size_t k, int key_is_f32, int descending, uint64_t *ids_out, void *keys_out) {
+    if (key_is_f32) return merge_impl<float>(ctx, static_cast<const uint64_t *>(records), nullptr, parts, nq, k, 1, -INFINITY, ids_out, static_cast<float *>(keys_out));
+    return merge_impl<uint32_t>(ctx, static_cast<const uint64_t *>(records), nullptr, parts, nq, k, descending, UINT32_MAX, ids_out, static_cast<uint32_t *>(keys_out));
 }
 
 // ---- scan diagnostics ------------------------------------------------------------------------
@@ -101,13 +131,13 @@ __global__ void add_flags_kernel(const uint32_t *flags, uint32_t nq, unsigned lo
 }
 }  // namespace
 
-int stats_reset(ucfp_ctx *ctx) {
+int stats_reset(ucfp_lane *ctx) {
     UCFP_TRY(ctx->stats.reserve(32));
     UCFP_CUDA_TRY(cudaMemsetAsync(ctx->stats.ptr, 0, 32, ctx->stream));
     return UCFP_OK;
 }
 
-int stats_add_flags(ucfp_ctx *ctx, const uint32_t *flags_dev, uint32_t nq) {
+int stats_add_flags(ucfp_lane *ctx, const uint32_t *flags_dev, uint32_t nq) {
     add_flags_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(flags_dev, nq, ctx->stats.as<unsigned long long>());
     count_launch(ctx);
     return check_launch("add_flags");
@@ -122,7 +152,7 @@ __global__ void synth_fill_kernel(uint64_t *dst, uint64_t n, uint64_t seed, uint
 }
 }  // namespace
 
-int synth_fill_u64(ucfp_ctx *ctx, uint64_t *dst_dev, uint64_t nwords, uint64_t seed, uint64_t start_word) {
+int synth_fill_u64(ucfp_lane *ctx, uint64_t *dst_dev, uint64_t nwords, uint64_t seed, uint64_t start_word) {
     if (nwords == 0) return UCFP_OK;
     uint64_t blocks = (nwords + 255) / 256;
     uint64_t maxb = (uint64_t)ctx->sm_count * 16;

@@ -80,7 +80,14 @@ __global__ void compact_kernel(SelectState S, uint32_t k, const uint64_t *__rest
     if (threadIdx.x == 0) {
         S.count[q] = m;
         if (n_raw > S.cap) S.flags[q] = 1;
-        if (n >= k) { S.thr[(size_t)q * S.thr_stride] = (uint32_t)(s_dr[k - 1] >> 40); S.kth_id[q] = s_id[k - 1]; }
+        // Publish the k-th entry as the admission bound -- unless the bound in force is already tighter: in a multi-GPU group
+        // scan the ranks exchange their bounds between chunks (bounds_min_kernel below), so the bound a shard filters at may
+        // come from another shard and be better than anything this list holds.
+        if (n >= k) {
+            const uint32_t new_thr = (uint32_t)(s_dr[k - 1] >> 40), cur_thr = S.thr[(size_t)q * S.thr_stride];
+            const uint64_t new_kid = s_id[k - 1];
+            if (new_thr < cur_thr || (new_thr == cur_thr && new_kid < S.kth_id[q])) { S.thr[(size_t)q * S.thr_stride] = new_thr; S.kth_id[q] = new_kid; }
+        }
     }
 }
 
@@ -89,6 +96,45 @@ static inline void compact_lists(const SelectState &S, uint32_t nq, uint32_t k, 
     compact_kernel<<<nq, 256, 16 * (size_t)kSmallList, st>>>(S, k, ids, id_base, final_pass ? 1 : 0, key_flip, ids_out, keys_out, kSmallList, 0);
     compact_kernel<<<nq, 512, 16 * (size_t)S.cap, st>>>(S, k, ids, id_base, final_pass ? 1 : 0, key_flip, ids_out, keys_out, S.cap, 1);
 }
+
+// ---- bound exchange between the shards of a group scan (group.cu) -------------------------------------------------
+// Every rank holds, per query, the admission bound (thr, kth_id) = its current k-th best (key, record id): an upper bound
+// of the GLOBAL k-th best.  The lexicographic minimum over the ranks is the tightest bound anyone knows; filtering every
+// shard at it removes the cold-path work a small shard otherwise spends while its own bound is still loose.
+struct __align__(16) BoundRec { uint64_t kth_id; uint32_t thr; uint32_t pad; };
+
+__global__ void bounds_pack_kernel(const uint32_t *__restrict__ thr, uint32_t thr_stride, const uint64_t *__restrict__ kth_id, uint32_t nq, BoundRec *out) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) out[q] = BoundRec{kth_id[q], thr[(size_t)q * thr_stride], 0u};
+}
+__global__ void bounds_min_kernel(const BoundRec *__restrict__ all, uint32_t world, uint32_t nq, uint32_t *thr, uint32_t thr_stride, uint64_t *kth_id) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint32_t t = thr[(size_t)q * thr_stride];
+    uint64_t id = kth_id[q];
+    for (uint32_t r = 0; r < world; ++r) {
+        const BoundRec b = all[(size_t)r * nq + q];
+        if (b.thr < t || (b.thr == t && b.kth_id < id)) { t = b.thr; id = b.kth_id; }
+    }
+    thr[(size_t)q * thr_stride] = t;
+    kth_id[q] = id;
+}
+// One exchange on the lane's stream: pack, all-gather through the hook the group installed, fold the minimum back in.
+static int exchange_bounds(ucfp_lane *ctx, const SelectState &S, uint32_t nq) {
+    ucfp_exchange *x = ctx->xch;
+    UCFP_TRY(x->send.reserve(sizeof(BoundRec) * nq));
+    UCFP_TRY(x->recv.reserve(sizeof(BoundRec) * (size_t)nq * x->world));
+    bounds_pack_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(S.thr, S.thr_stride, S.kth_id, nq, x->send.as<BoundRec>());
+    UCFP_TRY(x->allgather(x->comm, x->send.ptr, x->recv.ptr, sizeof(BoundRec) * nq, ctx->stream));
+    bounds_min_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(x->recv.as<BoundRec>(), (uint32_t)x->world, nq, S.thr, S.thr_stride, S.kth_id);
+    count_launch(ctx, 2);
+    x->done++;
+    return UCFP_OK;
+}
+// Every rank performs exactly kBoundExchanges exchanges per query pass, whatever its shard size: after the chunks that end
+// at or beyond these row counts, and any that are left when its shard ends earlier (collectives must match across ranks).
+constexpr int kBoundExchanges = 4;
+constexpr uint64_t kBoundExchangeRows[kBoundExchanges] = {1ULL << 16, 1ULL << 19, 1ULL << 22, 1ULL << 25};
 
 __global__ void fill_sentinel_u32_kernel(uint64_t *ids_out, uint32_t *key_out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -216,18 +262,14 @@ exact_select_kernel(KeyFn fn, const uint64_t *__restrict__ ids, uint64_t id_base
 }
 
 template <typename KeyFn>
-static int exact_select_fallback(ucfp_corpus *c, KeyFn fn, const uint32_t *flags, uint32_t nq, uint32_t k, uint32_t key_flip,
-                                 uint64_t *ids_out, uint32_t *keys_out) {
-    ucfp_ctx *ctx = c->ctx;
+static int exact_select_fallback(ucfp_lane *ctx, ucfp_corpus *c, int occ, KeyFn fn, const uint32_t *flags, uint32_t nq, uint32_t k,
+                                 uint32_t key_flip, uint64_t *ids_out, uint32_t *keys_out) {
     size_t scratch = sizeof(ExactScratch) + (sizeof(uint64_t) + sizeof(uint32_t)) * (size_t)k + 64;
     UCFP_TRY(ctx->misc.reserve(scratch));
     ExactScratch *scr = ctx->misc.as<ExactScratch>();
     uint64_t *out_id = reinterpret_cast<uint64_t *>(scr + 1);
     uint32_t *out_key = reinterpret_cast<uint32_t *>(out_id + k);
-    int occ = 0;
-    UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exact_select_kernel<KeyFn>, 256, 0));
-    if (occ < 1) occ = 1;
-    if (occ > 4) occ = 4;
+    if (occ < 1) occ = 1;   // measured once per context by the *_device_init functions
     const uint64_t *ids = c->id_mode == 1 ? c->ids : nullptr;
     uint64_t id_base = c->id_base, N = c->size;
     void *args[] = {&fn, &ids, &id_base, &N, &flags, &nq, &k, &key_flip, &scr, &out_id, &out_key, &ids_out, &keys_out};

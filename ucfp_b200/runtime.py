@@ -41,10 +41,17 @@ def _is_device(buf) -> bool:
 class Context:
     """ucfp_ctx: binds one CUDA device.  Raises UcfpError(UCFP_E_CUDA) without an sm_100 GPU."""
 
-    def __init__(self, device: int = 0, use_torch_stream: bool = True):
+    def __init__(self, device: int = 0, use_torch_stream: bool = True, _borrowed=None):
+        """use_torch_stream=True puts the context in shared-stream mode on torch's current stream (work is then ordered with
+        torch ops and device-output calls return asynchronously); False keeps the default pooled mode: per-call lanes with
+        their own streams, concurrent calls from several host threads, every call complete on return."""
         self._L = _ffi.lib()
-        h = C.c_void_p()
-        check(self._L.ucfp_init(device, C.byref(h)))
+        self._owned = _borrowed is None
+        if _borrowed is None:
+            h = C.c_void_p()
+            check(self._L.ucfp_init(device, C.byref(h)))
+        else:
+            h = C.c_void_p(_borrowed)
         self._h = h
         self.device = device
         if use_torch_stream and torch is not None and torch.cuda.is_available():
@@ -87,7 +94,8 @@ class Context:
 
     def close(self) -> None:
         if getattr(self, "_h", None):
-            self._L.ucfp_destroy(self._h)
+            if self._owned:
+                self._L.ucfp_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -161,6 +169,27 @@ class Corpus:
     def append_synthetic(self, seed: int, start_row: int, n: int) -> None:
         check(self._L.ucfp_corpus_append_synthetic(self._h, seed, start_row, n))
 
+    def upsert(self, ids, rows) -> int:
+        """Insert-or-replace by record id (IndexBackend::upsert).  Returns the number of rows replaced in place."""
+        n = len(ids)
+        rep = C.c_uint64(0)
+        check(self._L.ucfp_corpus_upsert(self._h, _ptr(ids), _ptr(rows), n, C.byref(rep)))
+        return int(rep.value)
+
+    def delete(self, ids) -> int:
+        """Removes rows by record id (IndexBackend::delete, idempotent).  Returns the number of rows removed."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        rem = C.c_uint64(0)
+        check(self._L.ucfp_corpus_delete(self._h, _ptr(ids), len(ids), C.byref(rem)))
+        return int(rem.value)
+
+    def reserve(self, capacity: int) -> None:
+        check(self._L.ucfp_corpus_reserve(self._h, capacity))
+
+    @property
+    def allocated(self) -> int:
+        return int(self._L.ucfp_corpus_capacity(self._h))
+
     def set_id_base(self, base: int) -> None:
         check(self._L.ucfp_corpus_set_id_base(self._h, base))
 
@@ -204,6 +233,131 @@ class Corpus:
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._L.ucfp_corpus_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_KEY_DTYPE = {_ffi.KIND_HAMMING64: np.uint32, _ffi.KIND_MINHASH128: np.uint32, _ffi.KIND_COSINE: np.float32}
+
+
+class Batcher:
+    """ucfp_batcher: coalesces single-query calls from many host threads into batched scans.  `query()` blocks and is
+    thread-safe (ctypes releases the GIL for the duration of the call)."""
+
+    def __init__(self, corpus: Corpus, max_batch: int = 512, max_delay_us: int = 200):
+        self.corpus, self._L = corpus, corpus._L
+        h = C.c_void_p()
+        check(self._L.ucfp_batcher_create(corpus._h, max_batch, max_delay_us, C.byref(h)))
+        self._h = h
+
+    def query(self, query, k: int):
+        q = np.ascontiguousarray(query)
+        ids = np.empty(k, dtype=np.uint64)
+        keys = np.empty(k, dtype=_KEY_DTYPE[self.corpus.kind])
+        check(self._L.ucfp_batcher_query(self._h, _ptr(q), k, _ptr(ids), _ptr(keys)))
+        return ids, keys
+
+    def stats(self):
+        """-> (queries served, batches scanned, largest batch)"""
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        check(self._L.ucfp_batcher_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return int(a.value), int(b.value), int(c.value)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.ucfp_batcher_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Group:
+    """ucfp_group: record-range shards over the GPUs of one box, one NCCL all-gather of packed top-k records per scan.
+
+    Group.local(devices)            one process drives several GPUs (ncclCommInitAll); contexts via .ctx(i)
+    Group.join(ctx, id, rank, world) one process per GPU; `id` = Group.unique_id() of rank 0, shipped by the caller"""
+
+    def __init__(self, handle, L):
+        self._h, self._L = handle, L
+        self._ctxs = {}
+
+    @classmethod
+    def local(cls, devices):
+        L = _ffi.lib()
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        check(L.ucfp_group_create(arr, len(devices), C.byref(h)))
+        g = cls(h, L)
+        g.devices = list(devices)
+        return g
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(_ffi.lib().ucfp_group_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def join(cls, ctx: Context, unique_id: bytes, rank: int, world: int):
+        L = _ffi.lib()
+        h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128)
+        check(L.ucfp_group_join(ctx._h, buf, rank, world, C.byref(h)))
+        g = cls(h, L)
+        g.devices = [ctx.device]
+        g._ctxs[0] = ctx
+        return g
+
+    @property
+    def local_size(self) -> int:
+        return int(self._L.ucfp_group_local_size(self._h))
+
+    @property
+    def world_size(self) -> int:
+        return int(self._L.ucfp_group_world_size(self._h))
+
+    def ctx(self, local_rank: int) -> Context:
+        """Context of a local rank (owned by the group; pooled mode)."""
+        if local_rank not in self._ctxs:
+            raw = self._L.ucfp_group_ctx(self._h, local_rank)
+            if not raw:
+                raise IndexError(local_rank)
+            self._ctxs[local_rank] = Context(self.devices[local_rank], use_torch_stream=False, _borrowed=raw)
+        return self._ctxs[local_rank]
+
+    def _scan(self, fn, corpora, queries, k, key_np, key_t, ids_out, keys_out):
+        nq = queries.shape[0]
+        if ids_out is None:
+            if _is_device(queries):
+                ids_out = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
+                keys_out = torch.empty((nq, k), dtype=key_t, device=queries.device)
+            else:
+                ids_out, keys_out = np.empty((nq, k), dtype=np.uint64), np.empty((nq, k), dtype=key_np)
+        arr = (C.c_void_p * len(corpora))(*[c._h for c in corpora])
+        check(fn(self._h, arr, _ptr(queries), nq, k, _ptr(ids_out), _ptr(keys_out)))
+        return ids_out, keys_out
+
+    def scan_hamming(self, corpora, queries, k, ids_out=None, dist_out=None):
+        return self._scan(self._L.ucfp_group_scan_hamming, corpora, queries, k, np.uint32, torch.int32 if torch else None, ids_out, dist_out)
+
+    def scan_jaccard(self, corpora, queries, k, ids_out=None, matches_out=None):
+        return self._scan(self._L.ucfp_group_scan_jaccard, corpora, queries, k, np.uint32, torch.int32 if torch else None, ids_out, matches_out)
+
+    def scan_cosine(self, corpora, queries, k, ids_out=None, score_out=None):
+        return self._scan(self._L.ucfp_group_scan_cosine, corpora, queries, k, np.float32, torch.float32 if torch else None, ids_out, score_out)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.ucfp_group_destroy(self._h)
             self._h = None
 
     def __del__(self):
