@@ -167,6 +167,141 @@ def cpu_arm(n_total: int, nq: int, steps: int, warmup: int, sample_rows: int, sa
                       f"{dt:.1f} s; scaled linearly to {n_total} rows"}, dt / steps * 1e3
 
 
+# ---------------------------------------------------------------- secondary paths (configs 3 and 4) --------
+def _rows_view(torch, corpus, shape, typestr, dev):
+    class _A:
+        __cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (corpus.device_rows_ptr(), False), "version": 2}
+    return torch.as_tensor(_A(), device=dev)
+
+
+def _crc(ids, keys) -> int:
+    import zlib
+    return zlib.crc32(np.ascontiguousarray(keys).tobytes(), zlib.crc32(np.ascontiguousarray(ids).tobytes()))
+
+
+def secondary_jaccard(torch, ctx, group, rank, world, dev, timed, peak, small):
+    """BASELINE configs[2]: MinHash-128 Jaccard top-10 over 50 M synthetic signatures (1 % of the rows copy a query's slots
+    with p in {.9,.7,.5}), 256-query batch, record-range shards over the N ranks.  Row contents depend on the GLOBAL row
+    index only, so `result_crc` must be the same at every N."""
+    from ucfp_b200 import Corpus, _ffi
+    n_total, nq, k = (5_000_000 if small else 50_000_000), 256, 10
+    lo, hi = n_total * rank // world, n_total * (rank + 1) // world
+    corpus = Corpus(ctx, _ffi.KIND_MINHASH128, hi - lo)
+    corpus.set_id_base(lo)
+    corpus.append_synthetic(0x5EED, lo, hi - lo)
+    q = splitmix64(77, np.arange(nq * 128, dtype=np.uint64)).reshape(nq, 128)
+    prow = np.unique(splitmix64(0x9A, np.arange(n_total // 100, dtype=np.uint64)) % np.uint64(n_total))
+    mine = prow[(prow >= lo) & (prow < hi)]
+    view = _rows_view(torch, corpus, (hi - lo, 128), "<i8", dev)
+    qd = torch.from_numpy(q.view(np.int64)).to(dev)
+    for a in range(0, len(mine), 100_000):
+        rows = mine[a:a + 100_000]
+        h = splitmix64(0x9B, rows)
+        qi = torch.from_numpy((h % np.uint64(nq)).astype(np.int64)).to(dev)
+        p = np.array([0.9, 0.7, 0.5])[((h >> np.uint64(20)) % np.uint64(3)).astype(np.int64)]
+        u = (splitmix64(0x9C, (rows[:, None] * np.uint64(128) + np.arange(128, dtype=np.uint64)[None, :]).reshape(-1)) >> np.uint64(40)).astype(np.float64) / float(1 << 24)
+        mask = torch.from_numpy(u.reshape(-1, 128) < p[:, None]).to(dev)
+        loc = torch.from_numpy((rows - np.uint64(lo)).astype(np.int64)).to(dev)
+        view[loc] = torch.where(mask, qd[qi], view[loc])
+    corpus.refresh()
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    m = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    step = (lambda: corpus.scan_jaccard(qd, k, ids, m)) if world == 1 else (lambda: group.scan_jaccard([corpus], qd, k, ids, m))
+    for _ in range(2):
+        step()
+    ctx.profile_begin()
+    ms = timed(step, 3) / 3
+    kms, kbytes, kn = ctx.profile_end(_ffi.PROF_JACCARD_SCAN)
+    gi, gm = ids.cpu().numpy().view(np.uint64), m.cpu().numpy().view(np.uint32)
+    out = {"metric": "jaccard_top10_queries_per_s_over_50M_signatures" if not small else "jaccard_top10_queries_per_s_over_5M_signatures",
+           "value": nq / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "queries": nq, "signatures": n_total, "result_crc": _crc(gi, gm),
+           "best_matches_min": int(gm[:, 0].min()),
+           "roofline": {"bound": "hbm", "kernel": "jaccard_scan_kernel", "achieved": kbytes / (kms / 1e3) / 1e9 if kms else None, "peak": peak,
+                        "unit": "GB/s", "frac": kbytes / (kms / 1e3) / 1e9 / peak if kms else None, "launches": kn,
+                        "note": "algorithmic bytes = 1024 B x rows x queries per launch (this rank's shard); the scan streams the 128 B/row "
+                                "sketch once per batch, so the batched figure exceeds the DRAM peak by design"}}
+    # parity on a bounded sample of THIS data (full-size parity lives in tests/test_configs_gpu.py): first rows of rank 0's shard
+    if rank == 0:
+        import oracle
+        sn = 100_000
+        sample = view[:sn].cpu().numpy().view(np.uint64)
+        sub = Corpus(ctx, _ffi.KIND_MINHASH128, sn)
+        sub.append(sample)
+        si, sm = sub.scan_jaccard(q[:32].copy(), k)
+        oi, om = oracle.jaccard_topk(sample, q[:32].copy(), k, threads=oracle.host_threads())
+        out["parity_check"] = {"rows": sn, "queries": 32, "ok": bool((si == oi).all() and (sm == om).all()), "against": "oracle/ on the first rows of the shard"}
+        sub.close()
+    del view
+    corpus.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def secondary_cosine(torch, ctx, group, rank, world, dev, timed, bf16_peak, small):
+    """BASELINE configs[3]: cosine top-10 over 20 M x 512 unit vectors with bf16-representable values, 8 planted neighbours
+    per query, 1024-query batch, record-range shards.  Rows are generated per global 500 K-row block with a fixed seed."""
+    from ucfp_b200 import Corpus, _ffi
+    n_total, dim, nq, k, blk = (2_000_000 if small else 20_000_000), 512, 1024, 10, 500_000
+    lo, hi = n_total * rank // world, n_total * (rank + 1) // world
+    corpus = Corpus(ctx, _ffi.KIND_COSINE, hi - lo, dim=dim)
+    corpus.set_id_base(lo)
+    g = torch.Generator(device=dev)
+
+    def unit(x):
+        return (x / x.norm(dim=1, keepdim=True)).to(torch.bfloat16).to(torch.float32)
+
+    for b in range(lo // blk, (hi + blk - 1) // blk):
+        g.manual_seed(1000 + b)
+        x = unit(torch.randn((blk, dim), device=dev, generator=g))
+        a, e = max(lo, b * blk), min(hi, (b + 1) * blk)
+        corpus.append(x[a - b * blk: e - b * blk].contiguous())
+    g.manual_seed(7)
+    q = unit(torch.randn((nq, dim), device=dev, generator=g))
+    noise = torch.randn((nq * 8, dim), device=dev, generator=g) * 0.03
+    planted_rows = splitmix64(0xC05, np.arange(nq * 8, dtype=np.uint64)) % np.uint64(n_total)
+    uniq, first = np.unique(planted_rows, return_index=True)
+    sel = first[(uniq >= lo) & (uniq < hi)]
+    if len(sel):
+        view = _rows_view(torch, corpus, (hi - lo, dim), "<f4", dev)
+        pv = unit(q.repeat_interleave(8, dim=0) + noise)
+        seli = torch.from_numpy(sel.astype(np.int64)).to(dev)
+        view[torch.from_numpy((planted_rows[sel] - np.uint64(lo)).astype(np.int64)).to(dev)] = pv[seli]
+        del view
+        corpus.refresh()
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    step = (lambda: corpus.scan_cosine(q, k, ids, sc)) if world == 1 else (lambda: group.scan_cosine([corpus], q, k, ids, sc))
+    for _ in range(2):
+        step()
+    ctx.profile_begin()
+    ms = timed(step, 3) / 3
+    kms, kflop, kn = ctx.profile_end(_ffi.PROF_COSINE_SCAN)
+    gi, gs = ids.cpu().numpy().view(np.uint64), sc.cpu().numpy()
+    tf = kflop / (kms / 1e3) / 1e12 if kms else None
+    out = {"metric": f"cosine_top10_queries_per_s_over_{n_total // 1_000_000}M_x_512", "value": nq / (ms / 1e3), "unit": UNIT, "ms_per_step": ms,
+           "queries": nq, "vectors": n_total, "result_crc": _crc(gi, gs.view(np.uint32)), "best_score_min": float(gs[:, 0].min()),
+           "roofline": {"bound": "tensor", "kernel": "cosine_coarse_kernel", "achieved": tf, "peak": bf16_peak, "unit": "TFLOP/s",
+                        "frac": tf / bf16_peak if tf else None, "launches": kn,
+                        "note": "2 x rows x dim x queries flop per launch (this rank's shard; bf16 tcgen05, f32 accumulate)"}}
+    if rank == 0:
+        import oracle
+        sn, sq = 100_000, 32
+        view = _rows_view(torch, corpus, (hi - lo, dim), "<f4", dev)
+        sample = view[:sn].cpu().numpy()
+        del view
+        qh = q[:sq].cpu().numpy()
+        sub = Corpus(ctx, _ffi.KIND_COSINE, sn, dim=dim)
+        sub.append(sample)
+        si, ss = sub.scan_cosine(qh.copy(), k)
+        oi, osc, _ = oracle.cosine_topk(sample, qh, k, mode=1, threads=oracle.host_threads())
+        out["parity_check"] = {"rows": sn, "queries": sq, "ok": bool((si == oi).all() and (ss.view(np.uint32) == osc.view(np.uint32)).all()),
+                               "against": "oracle/ (restatement of src/index/embedded/mod.rs:268-360) on the first rows of the shard, bit-exact f32 scores"}
+        sub.close()
+    corpus.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------- main --------------------------------
 def main() -> int:
     ap = argparse.ArgumentParser()
@@ -180,6 +315,8 @@ def main() -> int:
     ap.add_argument("--cpu-sample-queries", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-images", action="store_true", help="skip the secondary images-hashed/s measurement")
+    ap.add_argument("--no-paths", action="store_true", help="skip the secondary Jaccard (config 3) and cosine (config 4) measurements")
+    ap.add_argument("--small-paths", action="store_true", help="secondary Jaccard / cosine at a tenth of the config sizes (quick runs)")
     ap.add_argument("--parity-queries", type=int, default=64,
                     help="queries of the batch checked against the CPU oracle over the FULL corpus (untimed; 0 = skip)")
     args = ap.parse_args()
@@ -400,6 +537,16 @@ def main() -> int:
                                      "e2e": {"value": world * n_host / (ms_e / 1e3), "unit": "images/s",
                                              "h2d_bytes_per_step": n_host * 3 * w * h, "d2h_bytes_per_step": n_host * 408}}
             del px, out, px_host
+    # the other two scans of the hot path at BASELINE.json's shapes, sharded like the headline (configs[2], configs[3])
+    if not args.no_paths:
+        try:
+            del view
+        except NameError:
+            pass
+        corpus.close()
+        torch.cuda.empty_cache()
+        secondary["jaccard"] = secondary_jaccard(torch, ctx, group, rank, world, dev, timed, peak, args.small_paths)
+        secondary["cosine"] = secondary_cosine(torch, ctx, group, rank, world, dev, timed, bf16_peak, args.small_paths)
     achieved = k_bytes / (k_ms / 1e3) / 1e9 if k_ms else None
     traffic_path = os.path.join(ROOT, "profiles", "hamming_scan_traffic.json")
     # ncu-measured DRAM bytes per scanned row (profiles/), scaled to this run's rows per launch

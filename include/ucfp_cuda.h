@@ -156,12 +156,29 @@ UCFP_API int ucfp_image_hash_uniform(ucfp_ctx *ctx, const uint8_t *pixels, size_
                                      uint64_t row_stride, uint64_t image_stride, uint32_t algo_mask,
                                      ucfp_image_hashes *out);
 
+/* Batch ingest from ENCODED bytes.  The n JPEG bitstreams (host memory) are decoded on the device by
+ * nvJPEG and hashed where they land: decoded pixels never cross PCIe.  Replaces, for JPEG uploads, the host decode in front
+ * of src/modality/image.rs:68-70 (the reference's benchmark includes that decode, benches/end_to_end.rs:40-53).
+ * status[i] (host memory, required): UCFP_OK; UCFP_E_UNSUPPORTED = not a JPEG or one nvJPEG refuses (decode it on the host
+ * and use ucfp_image_hash_batch); UCFP_E_INVALID = corrupt bitstream / smaller than 4 px.  EXIF orientation is NOT applied
+ * (hosts that honour it rotate the 8x8 / 9x8 / 32x32 semantics themselves or decode such files on the host).
+ * dims_out (may be NULL): 2 n u32 {width, height}.  pixels_out (may be NULL; host or device, pixels_capacity bytes): the
+ * decoded RGB8 of the successfully decoded images, tightly packed, image after image.  nvJPEG is loaded on first use;
+ * UCFP_E_UNSUPPORTED when it is not installed. */
+UCFP_API int ucfp_image_hash_jpeg_batch(ucfp_ctx *ctx, const uint8_t *const *jpegs, const size_t *lengths, size_t n, uint32_t algo_mask,
+                                        ucfp_image_hashes *out, int32_t *status, uint32_t *dims_out, uint8_t *pixels_out,
+                                        size_t pixels_capacity);
+
 /* ---- corpus ---------------------------------------------------------------- */
 
 enum {
     UCFP_KIND_HAMMING64 = 1,  /* row = one u64 code (global_hash @32 of ImageFingerprint) */
     UCFP_KIND_MINHASH128 = 2, /* row = 128 u64 slots (payload @8 of txtfp MinHashSig<128>, src/modality/text.rs:200-204) */
-    UCFP_KIND_COSINE = 3      /* row = dim f32 (Record::embedding, src/core/mod.rs:58)     */
+    UCFP_KIND_COSINE = 3,     /* row = dim f32 (Record::embedding, src/core/mod.rs:58)     */
+    UCFP_KIND_MULTIHASH = 4   /* row = ucfp_image_hashes: the 51 hash words of a `multi` bundle (ahash | phash | dhash, each global + 16
+                                 blocks), for the block-hash-aware re-rank (ucfp_scan_multihash).  ucfp_corpus_append_strided on this kind
+                                 takes 536-byte MultiHashFingerprint records (field_offset = offset of the record's `exact`) and gathers the
+                                 three 136-byte hash runs at +64, +232, +400.  HBM per row of capacity: 408 + 8 + 32 (PHash side corpus) */
 };
 
 /* Allocates HBM for up to `capacity` rows.  `dim` is used by UCFP_KIND_COSINE only.  Bytes per row of capacity, side
@@ -227,6 +244,23 @@ UCFP_API int ucfp_scan_jaccard(ucfp_corpus *c, const uint64_t *queries, size_t n
  * rows and queries with zero norm never match (:284, :328); sentinel score = -inf.  queries = nq x dim f32. */
 UCFP_API int ucfp_scan_cosine(ucfp_corpus *c, const float *queries, size_t nq, size_t k,
                               uint64_t *ids_out, float *score_out);
+
+/* ---- multi-hash compare and re-rank (docs/HASH_SPEC.md section 10) --------------------------------------------
+ * The compare-time MultiHashConfig of the reference (src/modality/image.rs:21-24, 90-104; fields src/server/dto.rs:462-480;
+ * defaults web/src/lib/docs/api-reference-image.md:51-62).  NULL = the defaults 0.1 / 0.4 / 0.3 / 0.1 / 0.1 / 12. */
+typedef struct ucfp_multihash_config {
+    float ahash_weight, phash_weight, dhash_weight; /* per-algorithm weights in [0, 1]; only ratios matter          */
+    float global_weight, block_weight;              /* global-hash vs block-hash similarity inside every algorithm  */
+    uint32_t block_distance_threshold;              /* a block matches when its Hamming distance is <= this (<= 64) */
+} ucfp_multihash_config;
+/* Re-rank: the k_prime rows nearest to each query's PHash global hash (Hamming scan, order of ucfp_scan_hamming) are scored
+ * with the blended global + block similarity against the whole query bundle; the best k <= k_prime <= 2048 are returned
+ * under (score desc, record_id asc), unused slots UCFP_ID_NONE / -inf.  queries: nq bundles, host or device. */
+UCFP_API int ucfp_scan_multihash(ucfp_corpus *c, const ucfp_image_hashes *queries, size_t nq, size_t k_prime, size_t k,
+                                 const ucfp_multihash_config *cfg, uint64_t *ids_out, float *score_out);
+/* score_out[i] = blended similarity of bundles a[i] and b[i] (what imgfprint's compare would be asked; spec section 10). */
+UCFP_API int ucfp_multihash_compare(ucfp_ctx *ctx, const ucfp_image_hashes *a, const ucfp_image_hashes *b, size_t n,
+                                    const ucfp_multihash_config *cfg, float *score_out);
 
 /* Limits: k <= 2048 (Hamming, Jaccard) and k <= 1024 (cosine) per call -- larger k returns UCFP_E_UNSUPPORTED; callers
  * that mirror IndexBackend::knn clamp k to min(k, ucfp_corpus_size) first (EmbeddedBackend::knn returns min(k, N) hits). */

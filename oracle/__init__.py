@@ -39,10 +39,13 @@ def lib() -> C.CDLL:
         L.ucfp_oracle_splitmix64.restype = C.c_uint64
         L.ucfp_oracle_splitmix64.argtypes = [C.c_uint64, C.c_uint64]
         L.ucfp_oracle_fill_u64.argtypes = [u64p, C.c_size_t, C.c_uint64, C.c_uint64]
+        L.ucfp_oracle_fill_u64_mt.argtypes = [u64p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int]
         for name in ("ucfp_oracle_hamming_topk", "ucfp_oracle_jaccard_topk"):
             getattr(L, name).argtypes = [u64p, u64p, C.c_uint64, C.c_size_t, u64p, C.c_size_t, C.c_size_t,
                                          u64p, u32p, C.c_int]
             getattr(L, name).restype = None
+        L.ucfp_oracle_multihash_score.restype = C.c_float
+        L.ucfp_oracle_multihash_score.argtypes = [u64p, u64p, C.POINTER(C.c_float), C.c_uint32]
         L.ucfp_oracle_dot_product.restype = C.c_float
         L.ucfp_oracle_dot_product.argtypes = [f32p, f32p, C.c_size_t]
         L.ucfp_oracle_l2_norm.restype = C.c_float
@@ -82,9 +85,20 @@ def splitmix64(seed: int, index: int) -> int:
     return int(lib().ucfp_oracle_splitmix64(seed & (2**64 - 1), index & (2**64 - 1)))
 
 
-def fill_u64(n: int, seed: int, start: int = 0) -> np.ndarray:
-    out = np.empty(n, dtype=np.uint64)
-    lib().ucfp_oracle_fill_u64(_p(out, u64p), n, seed, start)
+def fill_u64(n: int, seed: int, start: int = 0, threads: int = 0, out: np.ndarray = None) -> np.ndarray:
+    """out[i] = splitmix64(seed, start + i); large fills use all host threads (threads=0: decide by size).
+    `out`: a C-contiguous uint64 array of >= n elements to fill in place (its first n elements are returned)."""
+    if out is None:
+        out = np.empty(n, dtype=np.uint64)
+    else:
+        assert out.dtype == np.uint64 and out.flags["C_CONTIGUOUS"] and out.size >= n
+        out = out.reshape(-1)[:n]
+    if threads == 0:
+        threads = host_threads() if n >= (1 << 22) else 1
+    if threads > 1:
+        lib().ucfp_oracle_fill_u64_mt(_p(out, u64p), n, seed, start, threads)
+    else:
+        lib().ucfp_oracle_fill_u64(_p(out, u64p), n, seed, start)
     return out
 
 
@@ -209,3 +223,41 @@ def image_multihash_batch(rgb: np.ndarray, threads: int = 1) -> np.ndarray:
     out = np.zeros((n, 51), dtype=np.uint64)
     lib().ucfp_oracle_image_multihash_batch(_p(rgb, u8p), n, w, h, 3 * w, 3 * w * h, _p(out, u64p), threads)
     return out
+
+
+# ---------------------------------------------------------------- multi-hash compare / re-rank (spec section 10) ------
+MULTIHASH_DEFAULTS = {"ahash_weight": 0.1, "phash_weight": 0.4, "dhash_weight": 0.3, "global_weight": 0.1, "block_weight": 0.1,
+                      "block_distance_threshold": 12}   # web/src/lib/docs/api-reference-image.md:51-62
+
+
+def _mh_cfg(cfg):
+    c = dict(MULTIHASH_DEFAULTS)
+    c.update(cfg or {})
+    arr = (C.c_float * 5)(c["ahash_weight"], c["phash_weight"], c["dhash_weight"], c["global_weight"], c["block_weight"])
+    return arr, int(c["block_distance_threshold"])
+
+
+def multihash_score(x: np.ndarray, y: np.ndarray, cfg=None) -> float:
+    """x, y: 51 u64 each (ahash[17] | phash[17] | dhash[17])."""
+    arr, thr = _mh_cfg(cfg)
+    x = np.ascontiguousarray(x, dtype=np.uint64).reshape(51)
+    y = np.ascontiguousarray(y, dtype=np.uint64).reshape(51)
+    return float(lib().ucfp_oracle_multihash_score(_p(x, u64p), _p(y, u64p), arr, thr))
+
+
+def multihash_rerank(bundles: np.ndarray, queries: np.ndarray, k_prime: int, k: int, ids=None, cfg=None, threads: int = 1):
+    """Spec section 10: candidates = Hamming top-k' on the PHash global hash (word 17), re-ranked by the blended score;
+    order (score desc, id asc).  -> (ids [nq, k] u64, scores [nq, k] f32)."""
+    bundles = np.ascontiguousarray(bundles, dtype=np.uint64).reshape(-1, 51)
+    queries = np.ascontiguousarray(queries, dtype=np.uint64).reshape(-1, 51)
+    n, nq = len(bundles), len(queries)
+    rows, _ = hamming_topk(np.ascontiguousarray(bundles[:, 17]), np.ascontiguousarray(queries[:, 17]), k_prime, threads=threads)
+    rid = np.arange(n, dtype=np.uint64) if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
+    out_i = np.full((nq, k), np.uint64(2**64 - 1), dtype=np.uint64)
+    out_s = np.full((nq, k), -np.inf, dtype=np.float32)
+    for q in range(nq):
+        cand = [int(r) for r in rows[q] if r != np.uint64(2**64 - 1)]
+        scored = sorted(((-np.float32(multihash_score(bundles[r], queries[q], cfg)), int(rid[r])) for r in cand))[:k]
+        for j, (ns, i) in enumerate(scored):
+            out_i[q, j], out_s[q, j] = i, -ns
+    return out_i, out_s

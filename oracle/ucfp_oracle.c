@@ -91,6 +91,18 @@ static void parallel_ranges(size_t n, int threads, range_fn fn, void *arg) {
     free(th); free(jobs);
 }
 
+/* the same stream, filled by several host threads (large synthetic corpora of the full-size parity checks) */
+typedef struct { uint64_t *out; uint64_t seed, start; } fill_job_t;
+static void fill_range(void *arg, int tid, size_t lo, size_t hi) {
+    (void)tid;
+    fill_job_t *f = (fill_job_t *)arg;
+    for (size_t i = lo; i < hi; ++i) f->out[i] = ucfp_oracle_splitmix64(f->seed, f->start + i);
+}
+UCFP_ORACLE_API void ucfp_oracle_fill_u64_mt(uint64_t *out, size_t n, uint64_t seed, uint64_t start, int threads) {
+    fill_job_t f = {out, seed, start};
+    parallel_ranges(n, threads, fill_range, &f);
+}
+
 /* ------------------------------------------------------------------------ */
 /* Integer-keyed top-k with a total order (key asc, id asc).                  */
 /* Hamming uses key = distance; Jaccard uses key = 128 - matches.             */
@@ -494,3 +506,30 @@ UCFP_ORACLE_API void ucfp_oracle_image_multihash_batch(const uint8_t *rgb, size_
 /* Synthetic images (spec section 8) are the little-endian byte view of
  * ucfp_oracle_fill_u64; the reference ramp of benches/end_to_end.rs:77-85 is
  * produced by the tests. */
+
+/* ------------------------------------------------------------------------ */
+/* Multi-hash compare (docs/HASH_SPEC.md section 10).  The weights are the    */
+/* reference's MultiHashConfigDto (src/server/dto.rs:462-480) with the        */
+/* defaults of web/src/lib/docs/api-reference-image.md:51-62; the compare     */
+/* itself lives in imgfprint (not readable here) and is fixed by the spec.    */
+/* cfg = {ahash_weight, phash_weight, dhash_weight, global_weight,            */
+/*        block_weight}; volatile keeps every f32 operation separately        */
+/* rounded in the order the spec writes them.                                 */
+/* ------------------------------------------------------------------------ */
+UCFP_ORACLE_API float ucfp_oracle_multihash_score(const uint64_t *x, const uint64_t *y, const float *cfg, uint32_t block_thr) {
+    volatile float s[3];
+    for (int a = 0; a < 3; ++a) {
+        const uint64_t *hx = x + 17 * a, *hy = y + 17 * a;
+        int dg = __builtin_popcountll(hx[0] ^ hy[0]), m = 0;
+        for (int i = 1; i <= 16; ++i) m += (uint32_t)__builtin_popcountll(hx[i] ^ hy[i]) <= block_thr;
+        volatile float g = (float)(64 - dg) / 64.0f, b = (float)m / 16.0f;
+        volatile float t1 = cfg[3] * g, t2 = cfg[4] * b, t3 = t1 + t2, den = cfg[3] + cfg[4];
+        s[a] = den == 0.0f ? 0.0f : t3 / den;
+    }
+    volatile float u0 = cfg[0] * s[0], u1 = cfg[1] * s[1], u2 = cfg[2] * s[2];
+    volatile float num = u0 + u1;
+    num = num + u2;
+    volatile float den = cfg[0] + cfg[1];
+    den = den + cfg[2];
+    return den == 0.0f ? 0.0f : num / den;
+}

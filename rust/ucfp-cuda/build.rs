@@ -9,8 +9,8 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     let mut objs = Vec::new();
-    for (src, extra) in [("api.cu", ""), ("hamming.cu", ""), ("jaccard.cu", ""), ("cosine.cu", "-fmad=false"),
-                         ("image.cu", "-fmad=false"), ("merge.cu", "")] {
+    for (src, extra) in [("api.cu", ""), ("corpus.cu", ""), ("batcher.cu", ""), ("group.cu", ""), ("multihash.cu", ""), ("jpeg.cu", ""),
+                         ("hamming.cu", ""), ("jaccard.cu", ""), ("cosine.cu", "-fmad=false"), ("image.cu", "-fmad=false"), ("merge.cu", "")] {
         let obj = out.join(src.replace(".cu", ".o"));
         let mut c = Command::new(&nvcc);
         c.args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
@@ -28,4 +28,9 @@ fn main() {
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=cuda");
     println!("cargo:rustc-link-lib=dylib=stdc++");
+    println!("cargo:rustc-link-lib=dylib=dl");
+    // NCCL (multi-GPU groups) and nvJPEG (device-side JPEG decode) are resolved with dlopen at first use; link them here as well
+    // when the host wants them pinned at load time:
+    if env::var("UCFP_LINK_NCCL").is_ok() { println!("cargo:rustc-link-lib=dylib=nccl"); }
+    if env::var("UCFP_LINK_NVJPEG").is_ok() { println!("cargo:rustc-link-lib=dylib=nvjpeg"); }
 }

@@ -129,3 +129,92 @@ def test_widest_supported_images_take_the_generic_kernel(ctx):
     assert (status == 0).all()
     np.testing.assert_array_equal(got[0], oracle.image_multihash(img))
     np.testing.assert_array_equal(got[1], oracle.image_multihash(tall))
+
+
+# ---- configs 3 and 4 at FULL size, the oracle over ALL rows (the metric configurations themselves were never
+# parity-checked).  The corpus is replayed on the host chunk by chunk, so host memory stays bounded; 16 of the queries are
+# checked end to end (the oracle is O(rows x queries) on CPU cores), all of them through the size-independent properties.
+def _merge_topk(best_i, best_k, new_i, new_k, k, descending):
+    ci, ck = np.concatenate([best_i, new_i], axis=1), np.concatenate([best_k, new_k], axis=1)
+    for r in range(len(ci)):
+        valid = ci[r] != U64(2**64 - 1)
+        primary = np.where(valid, -ck[r].astype(np.float64) if descending else ck[r].astype(np.float64), np.inf)
+        order = np.lexsort((ci[r], primary))[:k]
+        best_i[r], best_k[r] = ci[r][order], ck[r][order]
+
+
+def test_config3_full_50m_signatures_oracle_over_all_rows(ctx):
+    import torch
+    n, nq, k, chunk = 50_000_000, 256, 10, 2_000_000
+    corpus = Corpus(ctx, _ffi.KIND_MINHASH128, n)
+    corpus.append_synthetic(0x5EED, 0, n)
+    q = oracle.fill_u64(nq * 128, 77).reshape(nq, 128)
+    rng = np.random.default_rng(0)
+    rows = np.sort(rng.choice(n, n // 100, replace=False))          # config 3: 1 % of the rows copy a query's slots with p in {.9,.7,.5}
+    base = oracle.fill_u64(len(rows) * 128, 99).reshape(-1, 128)
+    qi, p = rng.integers(0, nq, len(rows)), rng.choice([0.9, 0.7, 0.5], len(rows))
+    for a in range(0, len(rows), 100_000):
+        mask = rng.random((min(100_000, len(rows) - a), 128)) < p[a:a + 100_000, None]
+        blk = base[a:a + 100_000]
+        blk[mask] = q[qi[a:a + 100_000]][mask]
+    view = _view(corpus, (n, 128), "<i8")
+    for a in range(0, len(rows), 100_000):
+        view[torch.from_numpy(rows[a:a + 100_000]).cuda()] = torch.from_numpy(base[a:a + 100_000].view(np.int64)).cuda()
+    corpus.refresh()
+    ids, m = corpus.scan_jaccard(torch.from_numpy(q.view(np.int64)).cuda(), k)
+    torch.cuda.synchronize()
+    ids, m = ids.cpu().numpy().view(U64), m.cpu().numpy().view(np.uint32)
+    assert ctx.last_scan_fallbacks() == 0
+    assert (np.diff(m.astype(np.int64), axis=1) <= 0).all()
+    # the oracle over all 50 M rows for every 16th query
+    sel = np.arange(0, nq, 16)
+    qs = np.ascontiguousarray(q[sel])
+    best_i = np.full((len(sel), k), U64(2**64 - 1), dtype=U64)
+    best_m = np.zeros((len(sel), k), dtype=np.uint32)
+    buf = np.empty(chunk * 128, dtype=U64)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        host = oracle.fill_u64((hi - lo) * 128, 0x5EED, start=lo * 128, out=buf).reshape(hi - lo, 128)
+        a, b = np.searchsorted(rows, lo), np.searchsorted(rows, hi)
+        host[rows[a:b] - lo] = base[a:b]
+        oi, om = oracle.jaccard_topk(host, qs, k, id_base=lo, threads=oracle.host_threads())
+        _merge_topk(best_i, best_m, oi, om, k, descending=True)
+    np.testing.assert_array_equal(m[sel], best_m)
+    np.testing.assert_array_equal(ids[sel], best_i)
+    corpus.close()
+
+
+def test_config4_full_20m_vectors_oracle_over_all_rows(ctx):
+    import torch
+    n, dim, nq, k, blk = 20_000_000, 512, 1024, 10, 500_000
+    corpus = Corpus(ctx, _ffi.KIND_COSINE, n, dim=dim)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for lo in range(0, n, blk):                                      # unit-norm rows with bf16-representable values (config 4)
+        x = torch.randn((blk, dim), device="cuda", generator=g)
+        corpus.append((x / x.norm(dim=1, keepdim=True)).to(torch.bfloat16).to(torch.float32))
+    q = torch.randn((nq, dim), device="cuda", generator=g)
+    q = (q / q.norm(dim=1, keepdim=True)).to(torch.bfloat16).to(torch.float32)
+    view = _view(corpus, (n, dim), "<f4")
+    prow = torch.randperm(n, device="cuda", generator=g)[: nq * 8]
+    pv = q.repeat_interleave(8, dim=0) + 0.03 * torch.randn((nq * 8, dim), device="cuda", generator=g)
+    view[prow] = (pv / pv.norm(dim=1, keepdim=True)).to(torch.bfloat16).to(torch.float32)
+    corpus.refresh()
+    ids, sc = corpus.scan_cosine(q, k)
+    torch.cuda.synchronize()
+    assert ctx.last_scan_fallbacks() == 0
+    ids_h, sc_h = ids.cpu().numpy().view(U64), sc.cpu().numpy()
+    planted = prow.cpu().numpy().astype(U64).reshape(nq, 8)
+    assert all(np.isin(planted[j], ids_h[j]).all() for j in range(nq)), "planted neighbours missing"
+    # the oracle (restatement of src/index/embedded/mod.rs:268-360) over all 20 M rows for every 64th query: bit-exact f32 scores
+    sel = np.arange(0, nq, 64)
+    qs = np.ascontiguousarray(q.cpu().numpy()[sel])
+    best_i = np.full((len(sel), k), U64(2**64 - 1), dtype=U64)
+    best_s = np.full((len(sel), k), -np.inf, dtype=np.float32)
+    for lo in range(0, n, 2 * blk):
+        hi = min(n, lo + 2 * blk)
+        host = view[lo:hi].cpu().numpy()
+        oi, osc, _ = oracle.cosine_topk(host, qs, k, id_base=lo, mode=1, threads=oracle.host_threads())
+        _merge_topk(best_i, best_s, oi, osc, k, descending=True)
+    np.testing.assert_array_equal(ids_h[sel], best_i)
+    np.testing.assert_array_equal(sc_h[sel].view(np.uint32), best_s.view(np.uint32))
+    corpus.close()

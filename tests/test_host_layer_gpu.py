@@ -73,13 +73,13 @@ def test_matcher_vector_arm_and_truncate(ctx):
 def test_ingest_image_round_trip_multi_and_single(ctx):
     png, arr = synthetic_png(64, 64)
     r = image.fingerprint(png, 9, 42)
-    assert r.algorithm == "imgfprint-multihash-v1" and r.modality == Modality.IMAGE and r.config_hash == 0
+    assert r.algorithm == image.ALGORITHM_MULTIHASH == "ucfp-b200-multihash-v1" and r.modality == Modality.IMAGE and r.config_hash == 0
     assert len(r.fingerprint) == 536 and len(r.fingerprint.hex()) == 1072
     words = oracle.image_multihash(arr)
     assert r.fingerprint == image.pack_multihash(image.exact_hash(png), words)
     pre = image.PreprocessConfig()
-    for fn, tag, off in ((image.fingerprint_phash, "imgfprint-phash-v1", 17), (image.fingerprint_dhash, "imgfprint-dhash-v1", 34),
-                         (image.fingerprint_ahash, "imgfprint-ahash-v1", 0)):
+    for fn, tag, off in ((image.fingerprint_phash, image.ALGORITHM_PHASH, 17), (image.fingerprint_dhash, image.ALGORITHM_DHASH, 34),
+                         (image.fingerprint_ahash, image.ALGORITHM_AHASH, 0)):
         s = fn(png, pre, 9, 43)
         assert s.algorithm == tag and len(s.fingerprint) == 168
         assert s.fingerprint == image.pack_image_fingerprint(image.exact_hash(png), words[off:off + 17])
@@ -105,7 +105,7 @@ def test_hash_index_hamming_and_jaccard(ctx):
     recs = [r for r in image.fingerprint_batch(pngs, 3, list(range(10, 16)), ucfp_b200._ffi.ALGO_PHASH)]
     db.upsert(recs)
     code = image.global_hash_of(recs[2].fingerprint, recs[2].algorithm)
-    hits = db.hamming_knn(3, "imgfprint-phash-v1", code, 3)
+    hits = db.hamming_knn(3, image.ALGORITHM_PHASH, code, 3)
     assert hits[0].record_id == 12 and hits[0].score == 1.0 and len(hits) == 3
     sig = oracle.fill_u64(128, 1)
     blob = b"\x01" + bytes(7) + sig.astype("<u8").tobytes()

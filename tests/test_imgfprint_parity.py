@@ -25,3 +25,18 @@ def test_oracle_matches_imgfprint_goldens():
         words = oracle.image_multihash(img)
         from ucfp_b200.image import pack_multihash
         assert pack_multihash(bytes.fromhex(e["hex"][:64]), words).hex() == e["hex"], e
+
+
+def test_spec_v1_hashes_do_not_carry_imgfprint_tags_while_parity_is_unpinned():
+    """The gate: as long as no golden file proves bit parity with imgfprint 0.4.1, records hashed here must not
+    be stamped with imgfprint's algorithm tags -- an index keys its Hamming corpora by tag, and mixing the two hash
+    definitions in one corpus would return meaningless distances."""
+    from ucfp_b200 import image
+    if os.path.exists(PATH):
+        assert image.IMGFPRINT_PARITY_VERIFIED, "goldens are present: run the parity test and flip IMGFPRINT_PARITY_VERIFIED"
+        assert image.ALGORITHM_MULTIHASH == image.REFERENCE_ALGORITHM_MULTIHASH
+    else:
+        assert not image.IMGFPRINT_PARITY_VERIFIED
+        for own, ref in ((image.ALGORITHM_MULTIHASH, image.REFERENCE_ALGORITHM_MULTIHASH), (image.ALGORITHM_PHASH, image.REFERENCE_ALGORITHM_PHASH),
+                         (image.ALGORITHM_DHASH, image.REFERENCE_ALGORITHM_DHASH), (image.ALGORITHM_AHASH, image.REFERENCE_ALGORITHM_AHASH)):
+            assert own != ref and own.startswith("ucfp-b200-") and ref.startswith("imgfprint-")

@@ -5,6 +5,8 @@ import json
 
 import pytest
 
+from ucfp_b200 import image
+
 from ucfp_b200 import Error, Hit, HitSource, Modality, server
 
 
@@ -53,7 +55,7 @@ def test_hash_query_goes_to_the_hamming_arm():
     assert [h["record_id"] for h in out["hits"]] == [7, 9] and out["hits"][1]["score"] == 1.0 - 3 / 64.0
     idx = FakeIndex()
     server.query(idx, {"tenant_id": 3, "modality": "Image", "hash": 2**64 - 1})          # integer form, default algorithm = multi bundle
-    assert idx.calls == [("hamming", 3, "imgfprint-multihash-v1", 2**64 - 1, 10)]
+    assert idx.calls == [("hamming", 3, image.ALGORITHM_MULTIHASH, 2**64 - 1, 10)]
 
 
 def test_signature_query_goes_to_the_jaccard_arm():

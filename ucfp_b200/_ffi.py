@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libucfp_cuda.so")
 
 OK, E_INVALID, E_CUDA, E_OOM, E_UNSUPPORTED, E_STATE, E_CAPACITY = 0, -1, -2, -3, -4, -5, -6
-KIND_HAMMING64, KIND_MINHASH128, KIND_COSINE = 1, 2, 3
+KIND_HAMMING64, KIND_MINHASH128, KIND_COSINE, KIND_MULTIHASH = 1, 2, 3, 4
 ALGO_AHASH, ALGO_PHASH, ALGO_DHASH, ALGO_MULTI = 1, 2, 4, 7
 PROF_HAMMING_SCAN, PROF_JACCARD_SCAN, PROF_COSINE_SCAN, PROF_IMAGE_HASH, PROF_HAMMING_TENSOR = 1, 2, 3, 4, 5
 ID_NONE = 2**64 - 1
@@ -29,6 +29,21 @@ class UcfpError(RuntimeError):
         super().__init__(f"{_CODE_NAMES.get(code, code)}: {message}")
         self.code = code
         self.message = message
+
+
+class MultiHashConfig(C.Structure):
+    """ucfp_multihash_config: the reference's MultiHashConfigDto (src/server/dto.rs:462-480), defaults of
+    web/src/lib/docs/api-reference-image.md:51-62."""
+    _fields_ = [("ahash_weight", C.c_float), ("phash_weight", C.c_float), ("dhash_weight", C.c_float),
+                ("global_weight", C.c_float), ("block_weight", C.c_float), ("block_distance_threshold", C.c_uint32)]
+
+    @classmethod
+    def of(cls, cfg=None):
+        d = {"ahash_weight": 0.1, "phash_weight": 0.4, "dhash_weight": 0.3, "global_weight": 0.1, "block_weight": 0.1,
+             "block_distance_threshold": 12}
+        d.update(cfg or {})
+        return cls(d["ahash_weight"], d["phash_weight"], d["dhash_weight"], d["global_weight"], d["block_weight"],
+                   int(d["block_distance_threshold"]))
 
 
 class ImageDesc(C.Structure):
@@ -51,6 +66,7 @@ PROTOTYPES = {
     "ucfp_ctx_profile_read": (_int, [_vp, _int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_u64)]),
     "ucfp_image_hash_batch": (_int, [_vp, C.POINTER(ImageDesc), _sz, _u32, _vp, _vp]),
     "ucfp_image_hash_uniform": (_int, [_vp, _vp, _sz, _u32, _u32, _u64, _u64, _u32, _vp]),
+    "ucfp_image_hash_jpeg_batch": (_int, [_vp, C.POINTER(_vp), C.POINTER(_sz), _sz, _u32, _vp, _vp, _vp, _vp, _sz]),
     "ucfp_corpus_create": (_int, [_vp, _int, _u32, _u64, C.POINTER(_vp)]),
     "ucfp_corpus_destroy": (None, [_vp]),
     "ucfp_corpus_append": (_int, [_vp, _vp, _vp, _u64]),
@@ -69,6 +85,8 @@ PROTOTYPES = {
     "ucfp_scan_jaccard": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "ucfp_scan_cosine": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "ucfp_ctx_last_scan_fallbacks": (_int, [_vp, C.POINTER(_u64)]),
+    "ucfp_scan_multihash": (_int, [_vp, _vp, _sz, _sz, _sz, C.POINTER(MultiHashConfig), _vp, _vp]),
+    "ucfp_multihash_compare": (_int, [_vp, _vp, _vp, _sz, C.POINTER(MultiHashConfig), _vp]),
     "ucfp_batcher_create": (_int, [_vp, _u32, _u32, C.POINTER(_vp)]),
     "ucfp_batcher_destroy": (None, [_vp]),
     "ucfp_batcher_query": (_int, [_vp, _vp, _sz, _vp, _vp]),

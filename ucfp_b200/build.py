@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 SO = os.path.join(HERE, "libucfp_cuda.so")
-SOURCES = ["api.cu", "corpus.cu", "batcher.cu", "group.cu", "hamming.cu", "jaccard.cu", "cosine.cu", "image.cu", "merge.cu"]
+SOURCES = ["api.cu", "corpus.cu", "batcher.cu", "group.cu", "multihash.cu", "jpeg.cu", "hamming.cu", "jaccard.cu", "cosine.cu", "image.cu", "merge.cu"]
 # Per-file extra flags.  image.cu must not contract a*b+c into FMA: the hash spec fixes
 # separately rounded mul and add (docs/HASH_SPEC.md section 2).
 EXTRA = {"image.cu": ["-fmad=false"], "cosine.cu": ["-fmad=false"]}

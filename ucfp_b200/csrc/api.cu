@@ -34,7 +34,7 @@ static void lane_destroy(ucfp_lane *ln) {
     if (!ln) return;
     cudaStreamSynchronize(ln->own_stream);
     DevBuf *bufs[] = {&ln->q_dev, &ln->out_ids_dev, &ln->out_keys_dev, &ln->cand, &ln->cand_count, &ln->qstate, &ln->flags, &ln->misc,
-                      &ln->img_desc_dev, &ln->img_out_dev, &ln->img_status_dev, &ln->img_tables_dev, &ln->img_stage_dev, &ln->stats};
+                      &ln->img_desc_dev, &ln->img_out_dev, &ln->img_status_dev, &ln->img_tables_dev, &ln->img_stage_dev, &ln->stats, &ln->mh_a, &ln->mh_b};
     for (DevBuf *b : bufs) b->release();
     ln->pin_a.release(); ln->pin_b.release();
     cudaStreamDestroy(ln->own_stream);
@@ -114,6 +114,7 @@ size_t row_bytes(const ucfp_corpus *c) {
         case UCFP_KIND_HAMMING64: return 8;
         case UCFP_KIND_MINHASH128: return 1024;
         case UCFP_KIND_COSINE: return 4 * (size_t)c->dim;
+        case UCFP_KIND_MULTIHASH: return sizeof(ucfp_image_hashes);
     }
     return 0;
 }
@@ -122,6 +123,7 @@ int after_append(ucfp_lane *ln, ucfp_corpus *c, uint64_t first, uint64_t n) {
     if (c->kind == UCFP_KIND_HAMMING64) return hamming_on_append(ln, c, first, n);
     if (c->kind == UCFP_KIND_MINHASH128) return jaccard_on_append(ln, c, first, n);
     if (c->kind == UCFP_KIND_COSINE) return cosine_on_append(ln, c, first, n);
+    if (c->kind == UCFP_KIND_MULTIHASH) return multihash_on_append(ln, c, first, n);
     return UCFP_OK;
 }
 
@@ -179,6 +181,7 @@ void ucfp_destroy(ucfp_ctx *ctx) {
         DeviceGuard dg(ctx->device);
         for (int i = 0; i < ctx->n_lanes; ++i) lane_destroy(ctx->lanes[i]);
         image_cache_destroy(ctx);
+        jpeg_destroy(ctx);
         for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
         delete ctx;
     } catch (...) {
@@ -276,6 +279,7 @@ int ucfp_ctx_profile_end(ucfp_ctx *ctx, int kernel_class, double *kernel_ms, dou
 // ---- corpus -------------------------------------------------------------------------------
 
 static void corpus_free_arrays(ucfp_corpus *c) {
+    if (c->coarse) { corpus_free_arrays(c->coarse); delete c->coarse; c->coarse = nullptr; }
     if (c->rows) cudaFree(c->rows);
     if (c->ids) cudaFree(c->ids);
     if (c->ham_ops) cudaFree(c->ham_ops);
@@ -291,8 +295,8 @@ int ucfp_corpus_create(ucfp_ctx *ctx, int kind, uint32_t dim, uint64_t capacity,
     *out = nullptr;
     UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
     UCFP_LEASE(ctx);
-    UCFP_REQUIRE(kind == UCFP_KIND_HAMMING64 || kind == UCFP_KIND_MINHASH128 || kind == UCFP_KIND_COSINE, UCFP_E_INVALID,
-                 "unknown corpus kind %d", kind);
+    UCFP_REQUIRE(kind == UCFP_KIND_HAMMING64 || kind == UCFP_KIND_MINHASH128 || kind == UCFP_KIND_COSINE || kind == UCFP_KIND_MULTIHASH,
+                 UCFP_E_INVALID, "unknown corpus kind %d", kind);
     UCFP_REQUIRE(capacity > 0, UCFP_E_INVALID, "capacity must be > 0");
     if (kind == UCFP_KIND_COSINE) UCFP_REQUIRE(dim > 0 && dim <= 4096, UCFP_E_INVALID, "cosine dim must be in 1..4096 (got %u)", dim);
     ucfp_corpus *c = new (std::nothrow) ucfp_corpus();
@@ -361,9 +365,10 @@ static int append_common(ucfp_corpus *c, const uint64_t *ids, const void *src, u
     if (n == 0) return UCFP_OK;
     UCFP_REQUIRE(src != nullptr, UCFP_E_INVALID, "rows is NULL");
     const size_t rb = row_bytes(c);
+    const bool bundles = strided && c->kind == UCFP_KIND_MULTIHASH;   // records are 536-byte MultiHashFingerprints starting at field_offset
     if (strided)
-        UCFP_REQUIRE(src_stride >= field_offset + rb, UCFP_E_INVALID, "record stride %llu cannot hold a %zu-byte field at offset %llu",
-                     (unsigned long long)src_stride, rb, (unsigned long long)field_offset);
+        UCFP_REQUIRE(src_stride >= field_offset + (bundles ? 536 : rb), UCFP_E_INVALID, "record stride %llu cannot hold a %zu-byte field at offset %llu",
+                     (unsigned long long)src_stride, bundles ? (size_t)536 : rb, (unsigned long long)field_offset);
     UCFP_REQUIRE(c->size + n <= c->capacity, UCFP_E_CAPACITY, "append of %llu rows exceeds capacity %llu (size %llu)",
                  (unsigned long long)n, (unsigned long long)c->capacity, (unsigned long long)c->size);
     const int mode = ids ? 1 : 2;
@@ -373,7 +378,10 @@ static int append_common(ucfp_corpus *c, const uint64_t *ids, const void *src, u
     const bool dev_src = classify(src) == Mem::Device;
     const cudaMemcpyKind kr = dev_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     char *dst = static_cast<char *>(c->rows) + rb * c->size;
-    if (strided)   // a pitched copy gathers the field of every record: source pitch = record stride, width = one row
+    if (bundles) {   // exact[32] | ahash:ImageFingerprint | phash | dhash, each ImageFingerprint = exact[32] | global | 16 blocks: three 136-byte runs
+        for (int a = 0; a < 3; ++a)
+            UCFP_CUDA_TRY(cudaMemcpy2DAsync(dst + 136 * a, rb, static_cast<const char *>(src) + field_offset + 64 + 168 * a, src_stride, 136, n, kr, st));
+    } else if (strided)   // a pitched copy gathers the field of every record: source pitch = record stride, width = one row
         UCFP_CUDA_TRY(cudaMemcpy2DAsync(dst, rb, static_cast<const char *>(src) + field_offset, src_stride, rb, n, kr, st));
     else
         UCFP_CUDA_TRY(cudaMemcpyAsync(dst, src, rb * n, kr, st));

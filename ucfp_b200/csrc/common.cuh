@@ -114,6 +114,7 @@ struct ucfp_lane {
     // scratch of the scans
     ucfp::DevBuf q_dev, out_ids_dev, out_keys_dev, cand, cand_count, qstate, flags, misc;
     ucfp::DevBuf img_desc_dev, img_out_dev, img_status_dev, img_tables_dev, img_stage_dev;
+    ucfp::DevBuf mh_a, mh_b;             // multi-hash re-rank: query codes + coarse candidates, scored + merged lists
     ucfp::PinnedBuf pin_a, pin_b;
     ucfp::DevBuf stats;                  // u64[4]: [0] queries recomputed by the exact fallback in this lane's last scan
     ucfp_exchange *xch = nullptr;        // non-null during a group scan with more than one rank
@@ -145,6 +146,9 @@ struct ucfp_ctx {
     // per-shape tap tables of image.cu (owned by it; freed by image_cache_destroy), shared by all lanes
     std::mutex image_mu;
     void *image_cache = nullptr;
+    // nvJPEG decoder of ucfp_image_hash_jpeg_batch (owned by jpeg.cu; one decode batch at a time)
+    std::mutex jpeg_mu;
+    void *jpeg = nullptr;
     // launch parameters that depend on the device only, computed once by the *_device_init functions at ucfp_init
     int ham_scan_occ = 1, jac_scan_occ = 1, ham_exact_occ = 1, jac_exact_occ = 1, cos_exact_occ = 1;
 };
@@ -167,6 +171,7 @@ struct ucfp_corpus {
     void *cos_bf16 = nullptr;      // COSINE: bf16[cap][dim_pad] rows scaled to unit norm, for the tensor-core pass
     float *cos_inv_norm = nullptr; // COSINE: 1/|v| in f32 (0 for zero rows)
     uint32_t dim_pad = 0;
+    ucfp_corpus *coarse = nullptr; // MULTIHASH: HAMMING64 side corpus of the PHash global hashes (word 17), same row order, implicit ids = rows
 };
 
 namespace ucfp {
@@ -214,6 +219,7 @@ int cosine_scan(ucfp_lane *ctx, ucfp_corpus *c, const float *q_dev, size_t nq, s
 int hamming_on_append(ucfp_lane *ctx, ucfp_corpus *c, uint64_t first_row, uint64_t n);
 int jaccard_on_append(ucfp_lane *ctx, ucfp_corpus *c, uint64_t first_row, uint64_t n);
 int cosine_on_append(ucfp_lane *ctx, ucfp_corpus *c, uint64_t first_row, uint64_t n);
+int multihash_on_append(ucfp_lane *ctx, ucfp_corpus *c, uint64_t first_row, uint64_t n);
 int merge_u32(ucfp_lane *ctx, const uint64_t *ids_in, const uint32_t *keys_in, size_t parts, size_t nq, size_t k,
               int descending, uint64_t *ids_out, uint32_t *keys_out);
 int merge_f32(ucfp_lane *ctx, const uint64_t *ids_in, const float *keys_in, size_t parts, size_t nq, size_t k,
@@ -231,6 +237,7 @@ int image_device_init(ucfp_ctx *ctx);
 int merge_device_init(ucfp_ctx *ctx);
 
 void image_cache_destroy(ucfp_ctx *ctx);
+void jpeg_destroy(ucfp_ctx *ctx);
 int stats_reset(ucfp_lane *ctx);
 int stats_add_flags(ucfp_lane *ctx, const uint32_t *flags_dev, uint32_t nq);
 

@@ -174,6 +174,13 @@ int corpus_alloc_arrays(ucfp_lane *ln, ucfp_corpus *c, uint64_t capacity) {
         c->rows = nullptr; c->mh_sketch = nullptr; c->cos_bf16 = nullptr; c->cos_inv_norm = nullptr; c->ham_ops = nullptr;
         return UCFP_E_OOM;
     }
+    if (kind == UCFP_KIND_MULTIHASH) {   // side corpus of the PHash global hashes, scanned by the coarse pass of a re-rank
+        c->coarse = new (std::nothrow) ucfp_corpus();
+        int rc = c->coarse ? UCFP_OK : UCFP_E_OOM;
+        if (rc == UCFP_OK) { c->coarse->ctx = c->ctx; c->coarse->kind = UCFP_KIND_HAMMING64; rc = corpus_alloc_arrays(ln, c->coarse, capacity); }
+        if (rc != UCFP_OK) { delete c->coarse; c->coarse = nullptr; cudaFree(c->rows); c->rows = nullptr; return rc; }
+        c->coarse->id_mode = 2;
+    }
     c->capacity = capacity;
     return UCFP_OK;
 }
@@ -182,7 +189,7 @@ int corpus_alloc_arrays(ucfp_lane *ln, ucfp_corpus *c, uint64_t capacity) {
 int corpus_grow(ucfp_lane *ln, ucfp_corpus *c, uint64_t capacity) {
     if (capacity <= c->capacity) return UCFP_OK;
     ucfp_corpus fresh;
-    fresh.kind = c->kind; fresh.dim = c->dim;
+    fresh.kind = c->kind; fresh.dim = c->dim; fresh.ctx = c->ctx;
     UCFP_TRY(corpus_alloc_arrays(ln, &fresh, capacity));
     const size_t rb = row_bytes(c);
     cudaError_t e = cudaSuccess;
@@ -195,12 +202,17 @@ int corpus_grow(ucfp_lane *ln, ucfp_corpus *c, uint64_t capacity) {
     if (e != cudaSuccess) {
         cudaGetLastError();
         set_error("growing the corpus to %llu rows failed: %s", (unsigned long long)capacity, cudaGetErrorString(e));
-        void *arrs[] = {fresh.rows, fresh.ids, fresh.ham_ops, fresh.mh_sketch, fresh.cos_bf16, fresh.cos_inv_norm};
+        void *arrs[] = {fresh.rows, fresh.ids, fresh.ham_ops, fresh.mh_sketch, fresh.cos_bf16, fresh.cos_inv_norm,
+                        fresh.coarse ? fresh.coarse->rows : nullptr, fresh.coarse ? (void *)fresh.coarse->ham_ops : nullptr};
         for (void *a : arrs) if (a) cudaFree(a);
+        delete fresh.coarse;
         return e == cudaErrorMemoryAllocation ? UCFP_E_OOM : UCFP_E_CUDA;
     }
-    void *old[] = {c->rows, c->ids, c->ham_ops, c->mh_sketch, c->cos_bf16, c->cos_inv_norm};
+    void *old[] = {c->rows, c->ids, c->ham_ops, c->mh_sketch, c->cos_bf16, c->cos_inv_norm,
+                   c->coarse ? c->coarse->rows : nullptr, c->coarse ? (void *)c->coarse->ham_ops : nullptr};
     for (void *a : old) if (a) cudaFree(a);
+    delete c->coarse;
+    c->coarse = fresh.coarse;
     c->rows = fresh.rows; c->ids = fresh.ids; c->ham_ops = fresh.ham_ops; c->mh_sketch = fresh.mh_sketch;
     c->cos_bf16 = fresh.cos_bf16; c->cos_inv_norm = fresh.cos_inv_norm; c->dim_pad = fresh.dim_pad; c->capacity = capacity;
     return after_append(ln, c, 0, c->size);

@@ -29,11 +29,26 @@ from . import _ffi
 from .core import Error, Modality, Record
 from .runtime import Context
 
-ALGORITHM = "imgfprint-multihash-v1"            # src/modality/image.rs:38
-ALGORITHM_MULTIHASH = "imgfprint-multihash-v1"  # :40
-ALGORITHM_PHASH = "imgfprint-phash-v1"          # :42
-ALGORITHM_DHASH = "imgfprint-dhash-v1"          # :44
-ALGORITHM_AHASH = "imgfprint-ahash-v1"          # :46
+# The reference's tags (src/modality/image.rs:38-46) name imgfprint's hash definitions.  Bit parity of this repo's hashes
+# with imgfprint 0.4.1 is UNPINNED (docs/HASH_SPEC.md, tests/test_imgfprint_parity.py), and an index keys its Hamming
+# corpora by algorithm tag: stamping spec-v1 hashes with imgfprint's tags would let records hashed here and records
+# hashed by the reference share one corpus and return meaningless distances.  Until the golden vectors exist and the
+# parity test passes, records produced here carry their own tags; flip the flag below (and only then) to become a
+# byte-for-byte drop-in.  Records hydrated from the reference's store keep the tags they were written with.
+IMGFPRINT_PARITY_VERIFIED = False
+REFERENCE_ALGORITHM_MULTIHASH = "imgfprint-multihash-v1"  # src/modality/image.rs:38, :40
+REFERENCE_ALGORITHM_PHASH = "imgfprint-phash-v1"          # :42
+REFERENCE_ALGORITHM_DHASH = "imgfprint-dhash-v1"          # :44
+REFERENCE_ALGORITHM_AHASH = "imgfprint-ahash-v1"          # :46
+_PREFIX = "imgfprint" if IMGFPRINT_PARITY_VERIFIED else "ucfp-b200"
+ALGORITHM = f"{_PREFIX}-multihash-v1"
+ALGORITHM_MULTIHASH = f"{_PREFIX}-multihash-v1"
+ALGORITHM_PHASH = f"{_PREFIX}-phash-v1"
+ALGORITHM_DHASH = f"{_PREFIX}-dhash-v1"
+ALGORITHM_AHASH = f"{_PREFIX}-ahash-v1"
+MULTIHASH_TAGS = (ALGORITHM_MULTIHASH, REFERENCE_ALGORITHM_MULTIHASH)   # 536-byte bundles
+SINGLE_HASH_TAGS = (ALGORITHM_PHASH, ALGORITHM_DHASH, ALGORITHM_AHASH, REFERENCE_ALGORITHM_PHASH, REFERENCE_ALGORITHM_DHASH,
+                    REFERENCE_ALGORITHM_AHASH)                            # 168-byte ImageFingerprints
 FORMAT_VERSION = 1                               # imgfprint::FORMAT_VERSION (web/src/lib/docs/api-reference-image.md:103)
 
 _TAG = {_ffi.ALGO_MULTI: ALGORITHM_MULTIHASH, _ffi.ALGO_PHASH: ALGORITHM_PHASH, _ffi.ALGO_DHASH: ALGORITHM_DHASH,
@@ -177,7 +192,7 @@ def fingerprint_ahash(data: bytes, preprocess: PreprocessConfig, tenant_id: int,
 def global_hash_of(fingerprint: bytes, algorithm: str) -> int:
     """The u64 the Hamming scan indexes: global_hash @32 of a 168-byte ImageFingerprint, or the PHash
     global hash @232 of a 536-byte multi bundle."""
-    if algorithm == ALGORITHM_MULTIHASH:
+    if algorithm in MULTIHASH_TAGS:
         if len(fingerprint) != 536:
             raise Error("Incompatible", f"multihash bundle must be 536 bytes, got {len(fingerprint)}")
         return struct.unpack_from("<Q", fingerprint, 232)[0]
@@ -194,3 +209,10 @@ def minhash_payload_of(fingerprint: bytes) -> np.ndarray:
     if fingerprint[:8] != b"\x01\x00\x00\x00\x00\x00\x00\x00":
         raise Error("Incompatible", "unsupported MinHashSig schema header")
     return np.frombuffer(fingerprint, dtype="<u8", count=128, offset=8).copy()
+
+
+def bundle_words_of(fingerprint: bytes) -> np.ndarray:
+    """The 51 hash words (ahash[17] | phash[17] | dhash[17]) of a 536-byte multi bundle: what a MULTIHASH corpus row holds."""
+    if len(fingerprint) != 536:
+        raise Error("Incompatible", f"multihash bundle must be 536 bytes, got {len(fingerprint)}")
+    return np.concatenate([np.frombuffer(fingerprint, dtype="<u8", count=17, offset=64 + 168 * a) for a in range(3)])

@@ -1,122 +1,153 @@
 """GPU index backend -- mirror of the reference's `trait IndexBackend` (src/index/mod.rs:17-78) for the scan
-path, plus the two entry points the reference lacks (Hamming / Jaccard k-NN).
+path, plus the entry points the reference lacks (Hamming / Jaccard k-NN and the block-hash re-rank).
 
 `GpuIndexBackend.knn` has the semantics of EmbeddedBackend::knn (src/index/embedded/mod.rs:268-360):
 per-tenant brute-force cosine, `k == 0` or an empty / zero-norm query -> [], rows whose dimension differs
-from the query's are invisible (:307), hits are Vector-sourced and sorted by score descending.  Storage
-(redb), BM25 and metadata stay on the host and are out of scope here; `upsert` only mirrors the fields the
-scans need into HBM (the corpus is a cache of what redb holds).
+from the query's are invisible (:307), hits are Vector-sourced and sorted by score descending, at most min(k, N) hits.
+Storage (redb), BM25 and metadata stay on the host and are out of scope here: the corpora are the HBM mirror of what
+redb holds.  `upsert` / `delete` go straight to ucfp_corpus_upsert / ucfp_corpus_delete (insert-or-replace and
+idempotent delete by record id on the device): nothing is rebuilt, no host copy of the rows is kept.
 """
 from __future__ import annotations
 
+from collections import defaultdict
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
 from . import _ffi
 from .core import Error, Hit, HitSource, Record
-from .image import ALGORITHM_MULTIHASH, global_hash_of, minhash_payload_of
+from .image import MULTIHASH_TAGS, SINGLE_HASH_TAGS, bundle_words_of, global_hash_of, minhash_payload_of
 from .runtime import Context, Corpus
 
-_GROW = 2.0
+K_LIMIT = {_ffi.KIND_COSINE: 1024, _ffi.KIND_HAMMING64: 2048, _ffi.KIND_MINHASH128: 2048, _ffi.KIND_MULTIHASH: 2048}   # include/ucfp_cuda.h
+_FIRST_CAPACITY = 1024
 
 
 class _Shelf:
-    """One (tenant, kind, dim) corpus with amortised growth (HBM rows are append-only; delete rebuilds)."""
+    """One (tenant, kind, dim) corpus.  It grows by itself (ucfp_corpus_upsert reallocates a full corpus)."""
 
     def __init__(self, ctx: Context, kind: int, dim: int, np_dtype, width: int):
         self.ctx, self.kind, self.dim, self.np_dtype, self.width = ctx, kind, dim, np_dtype, width
-        self.rows: Dict[int, np.ndarray] = {}     # record_id -> host copy (source of truth for rebuilds)
         self.corpus: Optional[Corpus] = None
-        self.dirty = True
 
-    def put(self, rid: int, row: np.ndarray) -> None:
-        self.rows[rid] = np.ascontiguousarray(row, dtype=self.np_dtype).reshape(self.width)
-        self.dirty = True
+    def _ensure(self, rows_hint: int) -> Corpus:
+        if self.corpus is None:
+            self.corpus = Corpus(self.ctx, self.kind, max(_FIRST_CAPACITY, rows_hint), dim=self.dim)
+        return self.corpus
 
-    def drop(self, rid: int) -> None:
-        if self.rows.pop(rid, None) is not None:
-            self.dirty = True
+    def upsert(self, ids: np.ndarray, rows: np.ndarray) -> None:
+        self._ensure(len(ids)).upsert(np.ascontiguousarray(ids, dtype=np.uint64),
+                                      np.ascontiguousarray(rows, dtype=self.np_dtype).reshape(len(ids), self.width))
+
+    def delete(self, ids: np.ndarray) -> None:
+        if self.corpus is not None and len(self.corpus):
+            self.corpus.delete(ids)
 
     def resident(self) -> Optional[Corpus]:
-        if not self.rows:
-            return None
-        if self.dirty:
-            if self.corpus is not None:
-                self.corpus.close()
-            ids = np.fromiter(self.rows.keys(), dtype=np.uint64, count=len(self.rows))
-            mat = np.stack([self.rows[int(i)] for i in ids]) if self.width > 1 else \
-                np.array([self.rows[int(i)][0] for i in ids], dtype=self.np_dtype)
-            self.corpus = Corpus(self.ctx, self.kind, max(int(len(ids) * _GROW), 1024), dim=self.dim)
-            self.corpus.append(mat, ids)
-            self.dirty = False
-        return self.corpus
+        return self.corpus if self.corpus is not None and len(self.corpus) else None
+
+    def clamp_k(self, k: int) -> int:
+        """EmbeddedBackend::knn returns min(k, N) hits; the scan kernels cap k per call (include/ucfp_cuda.h)."""
+        k = min(int(k), len(self.corpus))
+        if k > K_LIMIT[self.kind]:
+            raise Error("Unsupported", f"k = {k} exceeds the scan limit of {K_LIMIT[self.kind]} results per query")
+        return k
 
 
 class GpuIndexBackend:
     def __init__(self, ctx: Optional[Context] = None, device: int = 0):
         self.ctx = ctx or Context(device)
         self._vec: Dict[Tuple[int, int], _Shelf] = {}     # (tenant, dim)
-        self._ham: Dict[Tuple[int, str], _Shelf] = {}     # (tenant, algorithm)
+        self._ham: Dict[Tuple[int, str], _Shelf] = {}     # (tenant, algorithm): one u64 code per record
+        self._multi: Dict[Tuple[int, str], _Shelf] = {}   # (tenant, algorithm): 51-word bundles, for the block-hash re-rank
         self._mh: Dict[int, _Shelf] = {}                  # tenant
+
+    def _shelves_of(self, tenant_id: int):
+        for table in (self._vec, self._ham, self._multi):
+            for (t, _), shelf in table.items():
+                if t == tenant_id:
+                    yield shelf
+        if tenant_id in self._mh:
+            yield self._mh[tenant_id]
 
     # ---- IndexBackend::upsert / delete (src/index/mod.rs:20-25) ------------------------------------
     def upsert(self, batch: Sequence[Record]) -> None:
+        """Insert-or-replace by (tenant_id, record_id).  A record that changes shape (e.g. gets a new embedding dimension
+        or algorithm) leaves its old shelves first, as the redb row it replaces would."""
+        by_tenant = defaultdict(list)
         for r in batch:
-            self.delete(r.tenant_id, [r.record_id])  # insert-or-replace by (tenant_id, record_id)
+            by_tenant[r.tenant_id].append(r.record_id)
+        groups = defaultdict(lambda: ([], []))             # shelf -> (ids, rows)
+        for r in batch:
             if r.embedding is not None and len(r.embedding) > 0:
                 dim = len(r.embedding)
                 shelf = self._vec.setdefault((r.tenant_id, dim), _Shelf(self.ctx, _ffi.KIND_COSINE, dim, np.float32, dim))
-                shelf.put(r.record_id, np.asarray(r.embedding, dtype=np.float32))
-            if r.algorithm.startswith("imgfprint-") and len(r.fingerprint) in (168, 536):
+                groups[shelf][0].append(r.record_id); groups[shelf][1].append(np.asarray(r.embedding, dtype=np.float32))
+            if r.algorithm in MULTIHASH_TAGS and len(r.fingerprint) == 536 or r.algorithm in SINGLE_HASH_TAGS and len(r.fingerprint) == 168:
                 shelf = self._ham.setdefault((r.tenant_id, r.algorithm), _Shelf(self.ctx, _ffi.KIND_HAMMING64, 0, np.uint64, 1))
-                shelf.put(r.record_id, np.array([global_hash_of(r.fingerprint, r.algorithm)], dtype=np.uint64))
+                groups[shelf][0].append(r.record_id); groups[shelf][1].append(np.array([global_hash_of(r.fingerprint, r.algorithm)], dtype=np.uint64))
+            if r.algorithm in MULTIHASH_TAGS and len(r.fingerprint) == 536:
+                shelf = self._multi.setdefault((r.tenant_id, r.algorithm), _Shelf(self.ctx, _ffi.KIND_MULTIHASH, 0, np.uint64, 51))
+                groups[shelf][0].append(r.record_id); groups[shelf][1].append(bundle_words_of(r.fingerprint))
             if r.algorithm == "minhash-h128" and len(r.fingerprint) == 1032:
                 shelf = self._mh.setdefault(r.tenant_id, _Shelf(self.ctx, _ffi.KIND_MINHASH128, 0, np.uint64, 128))
-                shelf.put(r.record_id, minhash_payload_of(r.fingerprint))
+                groups[shelf][0].append(r.record_id); groups[shelf][1].append(minhash_payload_of(r.fingerprint))
+        for tenant_id, ids in by_tenant.items():            # replaced records leave the shelves they no longer belong to
+            ids = np.asarray(ids, dtype=np.uint64)
+            for shelf in self._shelves_of(tenant_id):
+                if shelf not in groups:
+                    shelf.delete(ids)
+                else:
+                    stay = np.asarray(groups[shelf][0], dtype=np.uint64)
+                    gone = np.setdiff1d(ids, stay)
+                    if len(gone):
+                        shelf.delete(gone)
+        for shelf, (ids, rows) in groups.items():
+            shelf.upsert(np.asarray(ids, dtype=np.uint64), np.stack(rows))
 
     def delete(self, tenant_id: int, ids: Sequence[int]) -> None:
         """Idempotent: missing ids are ignored (src/index/mod.rs:23-25)."""
-        for (t, _), shelf in list(self._vec.items()) + list(self._ham.items()):
-            if t == tenant_id:
-                for i in ids:
-                    shelf.drop(i)
-        if tenant_id in self._mh:
-            for i in ids:
-                self._mh[tenant_id].drop(i)
+        ids = np.asarray(list(ids), dtype=np.uint64)
+        if len(ids):
+            for shelf in self._shelves_of(tenant_id):
+                shelf.delete(ids)
 
     def hydrate_fingerprints(self, tenant_id: int, algorithm: str, record_ids, blobs: bytes) -> None:
         """Bulk load: `blobs` = equally sized fingerprint blobs back to back, as a range scan of the
-        redb fingerprints table yields them (src/index/embedded/mod.rs:37-43).  One strided copy per call instead of
-        one upsert per record."""
+        redb fingerprints table yields them (src/index/embedded/mod.rs:37-43).  One strided copy per corpus, no per-record
+        work; into a shelf that already holds rows the fields are extracted on the host and upserted."""
         ids = np.ascontiguousarray(record_ids, dtype=np.uint64)
         n = len(ids)
         if n == 0:
             return
         size = len(blobs) // n
         buf = np.frombuffer(blobs, dtype=np.uint8)
+        plans = []                                           # (shelf, field offset, host view for the upsert path)
         if algorithm == "minhash-h128":
             if size != 1032:
                 raise Error("Incompatible", f"MinHashSig<128> blobs must be 1032 bytes, got {size}")
             shelf = self._mh.setdefault(tenant_id, _Shelf(self.ctx, _ffi.KIND_MINHASH128, 0, np.uint64, 128))
-            off, view = 8, buf.reshape(n, size)[:, 8:].copy().view(np.uint64)
-        else:
-            off = 232 if algorithm == ALGORITHM_MULTIHASH else 32
-            if size != (536 if algorithm == ALGORITHM_MULTIHASH else 168):
+            plans.append((shelf, 8, lambda: buf.reshape(n, size)[:, 8:].copy().view(np.uint64)))
+        elif algorithm in MULTIHASH_TAGS or algorithm in SINGLE_HASH_TAGS:
+            multi = algorithm in MULTIHASH_TAGS
+            off = 232 if multi else 32
+            if size != (536 if multi else 168):
                 raise Error("Incompatible", f"{algorithm} blobs have the wrong size {size}")
             shelf = self._ham.setdefault((tenant_id, algorithm), _Shelf(self.ctx, _ffi.KIND_HAMMING64, 0, np.uint64, 1))
-            view = buf.reshape(n, size)[:, off:off + 8].copy().view(np.uint64)
-        for rid, row in zip(ids, view):          # host copy stays the source of truth for deletes/rebuilds
-            shelf.rows[int(rid)] = np.ascontiguousarray(row).reshape(shelf.width)
-        # the HBM mirror itself is filled by one strided copy straight from the blob run
-        if shelf.corpus is not None:
-            shelf.corpus.close()
-        shelf.corpus = Corpus(self.ctx, shelf.kind, max(int(len(shelf.rows) * _GROW), 1024), dim=shelf.dim)
-        if len(shelf.rows) == n:
-            shelf.corpus.append_strided(buf, size, off, n, ids)
-            shelf.dirty = False
+            plans.append((shelf, off, lambda: buf.reshape(n, size)[:, off:off + 8].copy().view(np.uint64)))
+            if multi:
+                shelf = self._multi.setdefault((tenant_id, algorithm), _Shelf(self.ctx, _ffi.KIND_MULTIHASH, 0, np.uint64, 51))
+                plans.append((shelf, 0, lambda: np.concatenate([buf.reshape(n, size)[:, 64 + 168 * a: 200 + 168 * a] for a in range(3)], axis=1).copy().view(np.uint64)))
         else:
-            shelf.dirty = True
+            raise Error("Unsupported", f"no scan corpus for algorithm {algorithm!r}")
+        for shelf, off, host_rows in plans:
+            if shelf.resident() is None:
+                corpus = shelf._ensure(n)
+                corpus.reserve(n)
+                corpus.append_strided(buf, size, off, n, ids)
+            else:
+                shelf.upsert(ids, host_rows())
 
     def flush(self) -> None:
         self.ctx.synchronize()
@@ -133,7 +164,7 @@ class GpuIndexBackend:
         corpus = shelf.resident() if shelf else None
         if corpus is None:
             return [[] for _ in range(len(q))]
-        ids, scores = corpus.scan_cosine(q, k)
+        ids, scores = corpus.scan_cosine(q, shelf.clamp_k(k))
         return [[Hit(tenant_id, int(i), float(s), HitSource.VECTOR) for i, s in zip(ri, rs) if i != _ffi.ID_NONE]
                 for ri, rs in zip(ids, scores)]
 
@@ -144,7 +175,7 @@ class GpuIndexBackend:
         corpus = shelf.resident() if shelf else None
         if corpus is None or k == 0:
             return []
-        ids, dist = corpus.scan_hamming(np.array([code], dtype=np.uint64), k)
+        ids, dist = corpus.scan_hamming(np.array([code], dtype=np.uint64), shelf.clamp_k(k))
         return [Hit(tenant_id, int(i), 1.0 - float(d) / 64.0, HitSource.VECTOR) for i, d in zip(ids[0], dist[0]) if i != _ffi.ID_NONE]
 
     def jaccard_knn(self, tenant_id: int, signature, k: int) -> List[Hit]:
@@ -154,8 +185,22 @@ class GpuIndexBackend:
         if corpus is None or k == 0:
             return []
         sig = np.ascontiguousarray(signature, dtype=np.uint64).reshape(1, 128)
-        ids, m = corpus.scan_jaccard(sig, k)
+        ids, m = corpus.scan_jaccard(sig, shelf.clamp_k(k))
         return [Hit(tenant_id, int(i), float(x) / 128.0, HitSource.VECTOR) for i, x in zip(ids[0], m[0]) if i != _ffi.ID_NONE]
+
+    def multihash_knn(self, tenant_id: int, algorithm: str, bundle: bytes, k: int, k_prime: Optional[int] = None, config=None) -> List[Hit]:
+        """Block-hash-aware search (docs/HASH_SPEC.md section 10): the k' nearest PHash global hashes re-ranked by
+        the blended global + block similarity of the whole 536-byte bundle.  Hit.score = that similarity; `config` = the
+        reference's MultiHashConfigDto fields (src/server/dto.rs:462-480), kebab- or snake-case."""
+        shelf = self._multi.get((tenant_id, algorithm))
+        corpus = shelf.resident() if shelf else None
+        if corpus is None or k == 0:
+            return []
+        k = shelf.clamp_k(k)
+        kp = min(max(k_prime or 8 * k, k), len(corpus), 2048)
+        cfg = {key.replace("-", "_"): v for key, v in (config or {}).items() if v is not None}
+        ids, sc = corpus.scan_multihash(bundle_words_of(bundle).reshape(1, 51), kp, k, cfg)
+        return [Hit(tenant_id, int(i), float(s), HitSource.VECTOR) for i, s in zip(ids[0], sc[0]) if i != _ffi.ID_NONE]
 
     def bm25(self, tenant_id: int, terms, k: int, _filter=None) -> List[Hit]:
         raise Error("Unsupported", "bm25 stays on the host backend (out of scope for the GPU hot path)")

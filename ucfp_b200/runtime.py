@@ -38,6 +38,21 @@ def _is_device(buf) -> bool:
     return torch is not None and isinstance(buf, torch.Tensor) and buf.is_cuda
 
 
+def _jpeg_pixels_upper_bound(blob: np.ndarray) -> int:
+    """3 * w * h from the first SOFn marker of a JPEG (0 when none is found)."""
+    b = blob.tobytes()
+    i = 2
+    while i + 9 < len(b) and b[i] == 0xFF:
+        m = b[i + 1]
+        if m in (0xC0, 0xC1, 0xC2, 0xC3, 0xC5, 0xC6, 0xC7, 0xC9, 0xCA, 0xCB, 0xCD, 0xCE, 0xCF):
+            return 3 * ((b[i + 5] << 8) | b[i + 6]) * ((b[i + 7] << 8) | b[i + 8])
+        if m == 0xD8 or 0xD0 <= m <= 0xD7 or m == 0x01:
+            i += 2
+            continue
+        i += 2 + ((b[i + 2] << 8) | b[i + 3])
+    return 0
+
+
 class Context:
     """ucfp_ctx: binds one CUDA device.  Raises UcfpError(UCFP_E_CUDA) without an sm_100 GPU."""
 
@@ -135,6 +150,43 @@ class Context:
         check(self._L.ucfp_image_hash_batch(self._h, descs, n, algo_mask, _ptr(out), _ptr(status)))
         return out, status
 
+    def image_hash_jpeg_batch(self, blobs, algo_mask: int = _ffi.ALGO_MULTI, want_pixels: bool = False):
+        """Encoded JPEG bytes -> hashes, decoded on the device by nvJPEG.  Returns ((n, 51) u64, (n,) i32 status,
+        (n, 2) u32 {w, h}[, list of decoded (h, w, 3) u8 arrays or None])."""
+        n = len(blobs)
+        keep = [np.frombuffer(b, dtype=np.uint8) for b in blobs]
+        ptrs = (C.c_void_p * max(n, 1))(*[k.ctypes.data if len(k) else None for k in keep])
+        lens = (C.c_size_t * max(n, 1))(*[len(k) for k in keep])
+        out = np.zeros((n, 51), dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        dims = np.zeros((n, 2), dtype=np.uint32)
+        if not want_pixels:
+            check(self._L.ucfp_image_hash_jpeg_batch(self._h, ptrs, lens, n, algo_mask, _ptr(out), _ptr(status), _ptr(dims), None, 0))
+            return out, status, dims
+        # a first pass for the dimensions would decode twice; size the pixel buffer from the JPEG headers instead
+        cap = 0
+        for k in keep:
+            cap += _jpeg_pixels_upper_bound(k)
+        px = np.zeros(max(cap, 1), dtype=np.uint8)
+        check(self._L.ucfp_image_hash_jpeg_batch(self._h, ptrs, lens, n, algo_mask, _ptr(out), _ptr(status), _ptr(dims), _ptr(px), cap))
+        images, at = [], 0
+        for i in range(n):
+            if status[i] != 0:
+                images.append(None)
+                continue
+            w, h = int(dims[i, 0]), int(dims[i, 1])
+            images.append(px[at: at + 3 * w * h].reshape(h, w, 3).copy())
+            at += 3 * w * h
+        return out, status, dims, images
+
+    def multihash_compare(self, a, b, cfg=None):
+        """Blended global + block similarity of bundle pairs (docs/HASH_SPEC.md section 10).  a, b: (n, 51) u64."""
+        n = a.shape[0]
+        out = (torch.empty(n, dtype=torch.float32, device=a.device) if _is_device(a) else np.empty(n, dtype=np.float32))
+        c = _ffi.MultiHashConfig.of(cfg)
+        check(self._L.ucfp_multihash_compare(self._h, _ptr(a), _ptr(b), n, C.byref(c), _ptr(out)))
+        return out
+
     # ---- merges ---------------------------------------------------------------------------
     def merge_topk_u32(self, ids_in, keys_in, parts: int, nq: int, k: int, descending: bool, ids_out, keys_out):
         check(self._L.ucfp_merge_topk_u32(self._h, _ptr(ids_in), _ptr(keys_in), parts, nq, k, int(descending),
@@ -228,6 +280,15 @@ class Corpus:
         nq = queries.shape[0]
         ids_out, score_out = self._outs(queries, nq, k, np.float32, torch.float32 if torch else None, ids_out, score_out)
         check(self._L.ucfp_scan_cosine(self._h, _ptr(queries), nq, k, _ptr(ids_out), _ptr(score_out)))
+        return ids_out, score_out
+
+    def scan_multihash(self, queries, k_prime: int, k: int, cfg=None, ids_out=None, score_out=None):
+        """Re-rank (spec section 10): Hamming top-k' on the PHash global hash, blended global + block score, best k.
+        queries: (nq, 51) u64 bundles.  MULTIHASH corpora only."""
+        nq = queries.shape[0]
+        ids_out, score_out = self._outs(queries, nq, k, np.float32, torch.float32 if torch else None, ids_out, score_out)
+        c = _ffi.MultiHashConfig.of(cfg)
+        check(self._L.ucfp_scan_multihash(self._h, _ptr(queries), nq, k_prime, k, C.byref(c), _ptr(ids_out), _ptr(score_out)))
         return ids_out, score_out
 
     def close(self) -> None:

@@ -20,7 +20,7 @@ from .matcher import Matcher
 
 DEFAULT_K = 10                                    # dto.rs:86 default_k
 _MODALITY = {"Audio": Modality.AUDIO, "Image": Modality.IMAGE, "Text": Modality.TEXT}   # serde: variant names, core/mod.rs:17-25
-DEFAULT_HASH_ALGORITHM = "imgfprint-multihash-v1"  # ALGORITHM_MULTIHASH, image.rs:38
+from .image import ALGORITHM_MULTIHASH as DEFAULT_HASH_ALGORITHM  # the multi bundle (image.rs:38), under the tag this build stamps
 
 
 def parse_explain(value: Optional[str]) -> bool:
