@@ -314,6 +314,10 @@ UCFP_API int ucfp_group_scan_cosine(ucfp_group *g, ucfp_corpus *const *corpora, 
 /* Diagnostics of the most recent scan on this context (synchronises the stream): how many of its queries
  * overflowed their candidate list and were recomputed by the exact multi-pass selection.  0 on the fast path. */
 UCFP_API int ucfp_ctx_last_scan_fallbacks(ucfp_ctx *ctx, uint64_t *queries_recomputed);
+/* Same, plus the longest candidate list any query of that scan (Hamming / Jaccard) accumulated between two compactions; the
+ * lists hold 4096 entries (more for k > 1024), a longer one overflows into the exact multi-pass selection.  A robustness
+ * gauge for skewed corpora: clustered near-duplicates, floods of identical codes. */
+UCFP_API int ucfp_ctx_last_scan_stats(ucfp_ctx *ctx, uint64_t *queries_recomputed, uint64_t *max_list_fill);
 
 /* Merges `parts` per-shard result lists (each nq x k, best first, as written by a scan) into one
  * nq x k list under the same total order: the step after the NCCL all-gather of per-rank candidates.

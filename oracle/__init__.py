@@ -251,8 +251,11 @@ def multihash_rerank(bundles: np.ndarray, queries: np.ndarray, k_prime: int, k: 
     bundles = np.ascontiguousarray(bundles, dtype=np.uint64).reshape(-1, 51)
     queries = np.ascontiguousarray(queries, dtype=np.uint64).reshape(-1, 51)
     n, nq = len(bundles), len(queries)
-    rows, _ = hamming_topk(np.ascontiguousarray(bundles[:, 17]), np.ascontiguousarray(queries[:, 17]), k_prime, threads=threads)
     rid = np.arange(n, dtype=np.uint64) if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
+    # coarse pass: ranked by (distance, RECORD id) -- the candidate set must not depend on the row order
+    cand_ids, _ = hamming_topk(np.ascontiguousarray(bundles[:, 17]), np.ascontiguousarray(queries[:, 17]), k_prime, ids=rid, threads=threads)
+    row_of = {int(i): r for r, i in enumerate(rid)}
+    rows = np.array([[row_of.get(int(i), 2**64 - 1) for i in cq] for cq in cand_ids], dtype=np.uint64).reshape(nq, -1)
     out_i = np.full((nq, k), np.uint64(2**64 - 1), dtype=np.uint64)
     out_s = np.full((nq, k), -np.inf, dtype=np.float32)
     for q in range(nq):

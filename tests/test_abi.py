@@ -36,17 +36,14 @@ def test_header_is_plain_c():
     assert subprocess.call([exe]) == 0
 
 
-def test_host_mirror_compiles_against_the_abi():
-    """include/ucfp/host.hpp (the C++ mirror of the reference's Rust interface) builds and links against the .so."""
-    hpp = os.path.join(ROOT, "include", "ucfp", "host.hpp")
-    if not os.path.exists(hpp):
-        pytest.skip("C++ host mirror not written yet")
-    src = '#include "ucfp/host.hpp"\nint main(){ ucfp::Query q; return q.k == 10 && q.rrf_k == 60 ? 0 : 1; }\n'
-    exe = "/tmp/ucfp_host_check"
-    subprocess.run(["g++", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-x", "c++", "-", "-o", exe,
-                           "-L", os.path.dirname(_ffi.LIB_PATH), "-lucfp_cuda", "-Wl,-rpath," + os.path.dirname(_ffi.LIB_PATH)],
-                   input=src.encode(), check=True)
-    assert subprocess.call([exe]) == 0
+def test_plain_c_client_compiles_and_links_against_the_abi():
+    """tests/c/abi_client.c -- a C11 program written against nothing but include/ucfp_cuda.h -- builds with -Wall -Werror
+    and links against the .so (it RUNS on the GPU box: tests/test_host_layer_gpu.py)."""
+    exe = "/tmp/ucfp_abi_client"
+    libdir = os.path.dirname(_ffi.LIB_PATH)
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_client.c"),
+                    "-o", exe, "-L", libdir, "-lucfp_cuda", "-Wl,-rpath," + libdir], check=True)
+    assert os.path.exists(exe)
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -146,18 +146,19 @@ def test_bulk_hydration_from_stored_blobs(ctx):
     c.close()
 
 
-def test_cpp_host_mirror_runs_on_the_gpu(tmp_path):
-    """include/ucfp/host.hpp end to end: the reference's index tests and one image bundle, from C++."""
+def test_plain_c_client_runs_on_the_gpu(tmp_path):
+    """tests/c/abi_client.c end to end: the reference's index known-answer tests, insert-or-replace / delete, the batcher and one
+    image bundle, from plain C through include/ucfp_cuda.h -- the path a Rust / cgo / JNI host takes."""
     import os
     import subprocess
     from ucfp_b200 import _ffi
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = str(tmp_path / "host_mirror_test")
+    exe = str(tmp_path / "abi_client")
     libdir = os.path.dirname(_ffi.LIB_PATH)
-    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "host_mirror_test.cpp"),
+    subprocess.run(["gcc", "-std=c11", "-O1", "-Wall", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c", "abi_client.c"),
                     "-o", exe, "-L", libdir, "-lucfp_cuda", "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
-    bundle = bytes.fromhex([l for l in out.stdout.splitlines() if l.startswith("BUNDLE ")][0].split()[1])
+    words = [int(x, 16) for x in [l for l in out.stdout.splitlines() if l.startswith("WORDS")][0].split()[1:]]
     _, arr = synthetic_png(64, 64)
-    assert bundle == image.pack_multihash(bytes([0xAB]) * 32, oracle.image_multihash(arr))
+    assert words == [int(x) for x in oracle.image_multihash(arr)]

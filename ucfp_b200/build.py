@@ -40,15 +40,18 @@ def _deps_mtime() -> float:
     return max(m, os.path.getmtime(__file__))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(SO) and os.path.getmtime(SO) >= _deps_mtime():
+def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
+    """experiments=True also compiles csrc/hamming_experiments.cuh (round-2 tensor-scan schedules that were measured and not
+    adopted; selected with UCFP_HAMMING_MMA_V / UCFP_HAMMING_EPI_WARPS)."""
+    if not force and not experiments and os.path.exists(SO) and os.path.getmtime(SO) >= _deps_mtime():
         return SO
     os.makedirs(OBJ, exist_ok=True)
     cc = nvcc()
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [cc, *NVCC_FLAGS, *EXTRA.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [cc, *NVCC_FLAGS, *EXTRA.get(src, []), *(["-DUCFP_HAMMING_EXPERIMENTS"] if experiments and src == "hamming.cu" else []),
+               "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -70,4 +73,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, experiments="--experiments" in sys.argv))

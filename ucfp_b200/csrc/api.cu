@@ -279,7 +279,7 @@ int ucfp_ctx_profile_end(ucfp_ctx *ctx, int kernel_class, double *kernel_ms, dou
 // ---- corpus -------------------------------------------------------------------------------
 
 static void corpus_free_arrays(ucfp_corpus *c) {
-    if (c->coarse) { corpus_free_arrays(c->coarse); delete c->coarse; c->coarse = nullptr; }
+    if (c->coarse) { c->coarse->ids = nullptr; /* borrowed from c */ corpus_free_arrays(c->coarse); delete c->coarse; c->coarse = nullptr; }
     if (c->rows) cudaFree(c->rows);
     if (c->ids) cudaFree(c->ids);
     if (c->ham_ops) cudaFree(c->ham_ops);
@@ -524,6 +524,27 @@ int ucfp_scan_jaccard(ucfp_corpus *c, const uint64_t *queries, size_t nq, size_t
 int ucfp_scan_cosine(ucfp_corpus *c, const float *queries, size_t nq, size_t k, uint64_t *ids_out, float *score_out) {
     UCFP_API_BEGIN
     return run_scan_any(c, UCFP_KIND_COSINE, queries, nq, k, ids_out, score_out);
+    UCFP_API_END
+}
+
+int ucfp_ctx_last_scan_stats(ucfp_ctx *ctx, uint64_t *queries_recomputed, uint64_t *max_list_fill) {
+    UCFP_API_BEGIN
+    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    if (queries_recomputed) *queries_recomputed = 0;
+    if (max_list_fill) *max_list_fill = 0;
+    UCFP_TRY(ucfp_ctx_synchronize(ctx));
+    DeviceGuard dg(ctx->device);
+    void *stats = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        stats = ctx->lanes[ctx->last_scan_lane]->stats.ptr;
+    }
+    if (!stats) return UCFP_OK;
+    uint64_t h[2] = {0, 0};
+    UCFP_CUDA_TRY(cudaMemcpy(h, stats, 16, cudaMemcpyDeviceToHost));
+    if (queries_recomputed) *queries_recomputed = h[0];
+    if (max_list_fill) *max_list_fill = h[1];
+    return UCFP_OK;
     UCFP_API_END
 }
 

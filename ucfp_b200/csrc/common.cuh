@@ -213,7 +213,8 @@ inline int check_launch(const char *what) {
 
 // ---- kernels-side entry points implemented in the per-path .cu files -------
 // `ctx` is the lane the call has leased: its stream, its scratch.
-int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, uint32_t *dist_out_dev);
+int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, uint32_t *dist_out_dev,
+                 bool emit_rows = false);   // emit_rows: report row indices (ties still by record id)
 int jaccard_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, uint32_t *m_out_dev);
 int cosine_scan(ucfp_lane *ctx, ucfp_corpus *c, const float *q_dev, size_t nq, size_t k, uint64_t *ids_out_dev, float *score_out_dev);
 int hamming_on_append(ucfp_lane *ctx, ucfp_corpus *c, uint64_t first_row, uint64_t n);

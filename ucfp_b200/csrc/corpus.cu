@@ -48,9 +48,9 @@ __global__ void fill_ids_kernel(uint64_t *ids, uint64_t id_base, uint64_t n) {
 
 // One CTA per job: corpus row dst[j] <- row src[j] of `from` (words of 8 bytes); ids likewise when id_from is given,
 // else ids[dst[j]] = new_ids[j].
-__global__ void __launch_bounds__(128) copy_rows_kernel(uint64_t *rows, uint64_t *ids, const uint64_t *__restrict__ from, const uint64_t *id_from,
+__global__ void __launch_bounds__(128) copy_rows_kernel(uint32_t *rows, uint64_t *ids, const uint32_t *__restrict__ from, const uint64_t *id_from,
                                                          const uint64_t *new_ids, const uint64_t *__restrict__ dst, const uint64_t *__restrict__ src,
-                                                         uint32_t words_per_row) {
+                                                         uint32_t words_per_row) {   // 32-bit words: every row size is a multiple of 4 (cosine rows are 4 x dim bytes)
     const uint64_t d = dst[blockIdx.x], s = src[blockIdx.x];
     for (uint32_t w = threadIdx.x; w < words_per_row; w += blockDim.x) rows[d * words_per_row + w] = from[s * words_per_row + w];
     if (threadIdx.x == 0 && ids) ids[d] = id_from ? id_from[s] : new_ids[blockIdx.x];
@@ -131,8 +131,8 @@ int launch_copy_rows(ucfp_lane *ln, ucfp_corpus *c, const void *from, const uint
     if (i_dev) UCFP_CUDA_TRY(cudaMemcpyAsync(i_dev, new_ids.data(), 8 * n, cudaMemcpyHostToDevice, ln->stream));
     for (size_t lo = 0; lo < n; lo += 65535) {   // grid.x limit is far away, but keep launches modest
         const unsigned m = (unsigned)std::min<size_t>(65535, n - lo);
-        copy_rows_kernel<<<m, 128, 0, ln->stream>>>(static_cast<uint64_t *>(c->rows), c->ids, static_cast<const uint64_t *>(from), id_from,
-                                                    i_dev ? i_dev + lo : nullptr, d_dev + lo, s_dev + lo, (uint32_t)(row_bytes(c) / 8));
+        copy_rows_kernel<<<m, 128, 0, ln->stream>>>(static_cast<uint32_t *>(c->rows), c->ids, static_cast<const uint32_t *>(from), id_from,
+                                                    i_dev ? i_dev + lo : nullptr, d_dev + lo, s_dev + lo, (uint32_t)(row_bytes(c) / 4));
         count_launch(ln);
     }
     UCFP_TRY(check_launch("copy_rows"));

@@ -239,6 +239,8 @@ int jaccard_on_append(ucfp_lane *ctx, ucfp_corpus *c, uint64_t first_row, uint64
     return check_launch("sketch_build");
 }
 
+constexpr uint64_t kJaccardExchangeRows[kBoundExchanges] = {1ULL << 12, 1ULL << 14, 1ULL << 16, 1ULL << 19};   // rows seen per rank before exchange e
+
 constexpr size_t kJaccardScanSmemMax = (size_t)kMaxQueriesPerPass * (2 * kSketchWords + 1 + 2) * 4 + 8;
 
 int jaccard_device_init(ucfp_ctx *ctx) {
@@ -261,7 +263,8 @@ int jaccard_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
         size_t tot = nq * k;
         fill_sentinel_u32_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ids_out_dev, m_out_dev, tot);
         count_launch(ctx);
-        return check_launch("fill_sentinel");
+        UCFP_TRY(check_launch("fill_sentinel"));
+        if (!ctx->xch) return UCFP_OK;   // an empty shard of a group scan still takes part in the bound exchanges below
     }
     uint32_t cap = 4096;
     while (cap < 4 * k) cap <<= 1;
@@ -286,9 +289,15 @@ int jaccard_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
         const uint64_t *qp = q_dev + q0 * kSlots;
         uint64_t *ids_out = ids_out_dev + q0 * k;
         uint32_t *m_out = m_out_dev + q0 * k;
-        SelectState sel{cand, count, thr, 1, kth, flags, cap, flags + nqp};
+        SelectState sel{cand, count, thr, 1, kth, flags, cap, flags + nqp, ctx->stats.as<unsigned long long>() + 1};
 
         jaccard_init_kernel<<<(nqp * kSketchWords + 255) / 256, 256, 0, st>>>(qp, nqp, qsk, thr, kth, count, flags);
+        if (N == 0) {   // group scan, empty shard: contribute the trivial bound to every exchange
+            count_launch(ctx);
+            while (ctx->xch->done < kBoundExchanges) UCFP_TRY(exchange_bounds(ctx, sel, nqp));
+            ctx->xch->done = 0;
+            continue;
+        }
         const uint32_t seed = (uint32_t)(N < kSeedRows ? N : kSeedRows);
         jaccard_seed_kernel<<<dim3((seed + 7) / 8, nqp), 256, 0, st>>>(sigs, seed, qp, cand, count, cap);
         count_launch(ctx, 2);
@@ -322,7 +331,15 @@ int jaccard_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
             count_launch(ctx);
             pos += n;
             compact(pos == N);
+            // group scan: the loose-bound phase is where a small shard loses its time (no early exit, every chance collision is
+            // verified); the other shards' bounds end it after a few thousand rows per rank instead of a few hundred thousand
+            if (ctx->xch && pos < N)
+                while (ctx->xch->done < kBoundExchanges && pos >= kJaccardExchangeRows[ctx->xch->done]) UCFP_TRY(exchange_bounds(ctx, sel, nqp));
             chunk = chunk * growth < kMaxChunkRows ? chunk * growth : kMaxChunkRows;
+        }
+        if (ctx->xch) {
+            while (ctx->xch->done < kBoundExchanges) UCFP_TRY(exchange_bounds(ctx, sel, nqp));
+            ctx->xch->done = 0;
         }
         UCFP_TRY(check_launch("jaccard scan"));
         UCFP_TRY(stats_add_flags(ctx, flags, nqp));

@@ -6,8 +6,9 @@
 // and the bundle stores are used here and nowhere else.
 //
 // A MULTIHASH corpus row is the 51-word hash part of a bundle (ahash[17] | phash[17] | dhash[17]).  Beside the rows the
-// corpus keeps a HAMMING64 side corpus of the PHash global hashes (word 17) in the same row order with implicit ids, so
-// the coarse pass of a re-rank scan is the ordinary Hamming scan (tensor-core path for batches >= 64) returning ROWS.
+// corpus keeps a HAMMING64 side corpus of the PHash global hashes (word 17) in the same row order (it borrows the bundle corpus's
+// id column), so the coarse pass of a re-rank scan is the ordinary Hamming scan (tensor-core path for batches >= 64), ranking by
+// (distance, record id) and reporting ROWS.
 #include <math.h>
 
 #include "api_util.cuh"
@@ -103,8 +104,6 @@ int multihash_on_append(ucfp_lane *ctx, ucfp_corpus *c, uint64_t first, uint64_t
     count_launch(ctx);
     UCFP_TRY(check_launch("gather_word"));
     c->coarse->size = c->size;   // rows that exist before this call; hamming_on_append extends to first + n itself
-    c->coarse->id_mode = 2;
-    c->coarse->id_base = 0;
     return hamming_on_append(ctx, c->coarse, first, n);
 }
 
@@ -141,8 +140,10 @@ int ucfp_scan_multihash(ucfp_corpus *c, const ucfp_image_hashes *queries, size_t
     UCFP_CUDA_TRY(cudaMemcpy2DAsync(q_codes, 8, static_cast<const uint64_t *>(q_dev) + kPhashGlobal, sizeof(ucfp_image_hashes), 8, nq,
                                     cudaMemcpyDeviceToDevice, st));
     UCFP_TRY(stats_reset(lane));
-    c->coarse->size = c->size; c->coarse->id_mode = 2; c->coarse->id_base = 0;   // coarse "ids" are rows
-    UCFP_TRY(hamming_scan(lane, c->coarse, q_codes, nq, k_prime, cand_rows, cand_dist));
+    // the coarse pass ranks by (distance, RECORD id) -- the candidate set must not depend on where delete / upsert moved a row --
+    // but reports rows: it borrows the bundle corpus's id column
+    c->coarse->size = c->size; c->coarse->id_mode = c->id_mode; c->coarse->id_base = c->id_base; c->coarse->ids = c->ids;
+    UCFP_TRY(hamming_scan(lane, c->coarse, q_codes, nq, k_prime, cand_rows, cand_dist, /*emit_rows=*/true));
     rerank_score_kernel<<<(unsigned)((n_cand * 32 + 255) / 256), 256, 0, st>>>(static_cast<const uint64_t *>(c->rows), c->id_mode == 1 ? c->ids : nullptr, c->id_base,
                                                                               static_cast<const uint64_t *>(q_dev), cand_rows, (uint32_t)nq, (uint32_t)k_prime, mc, scored);
     count_launch(lane);

@@ -20,6 +20,9 @@ struct SelectState {      // per query pass, all device pointers
     uint32_t *flags;      // [nq] 1 = list overflowed, needs exact_select
     uint32_t cap;
     uint32_t *big;        // [nq] list too long for the small compaction launch
+    unsigned long long *max_fill = nullptr;   // diagnostics (may be null): longest list any compaction of this scan has seen
+    int emit_rows = 0;    // the final pass reports ROW indices instead of record ids (ties are still broken by record id): the coarse
+                          // pass of the multi-hash re-rank needs the rows, and its candidate set must not depend on the row order
 };
 
 constexpr uint32_t kSmallList = 1024;   // entries the small compaction launch sorts (16 KiB of shared memory)
@@ -39,6 +42,7 @@ __global__ void compact_kernel(SelectState S, uint32_t k, const uint64_t *__rest
     const uint32_t q = blockIdx.x;
     const uint32_t n_raw = S.count[q];
     const uint32_t n = min(n_raw, S.cap);
+    if (!second_launch && threadIdx.x == 0 && S.max_fill && n_raw > 64) atomicMax(S.max_fill, (unsigned long long)n_raw);   // short lists: not worth an atomic
     if (!second_launch) {
         const bool big = n > smem_entries;
         if (threadIdx.x == 0) S.big[q] = big ? 1u : 0u;
@@ -73,7 +77,7 @@ __global__ void compact_kernel(SelectState S, uint32_t k, const uint64_t *__rest
         for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
             bool ok = i < m;
             uint32_t key = ok ? (uint32_t)(s_dr[i] >> 40) : 0;
-            ids_out[(size_t)q * k + i] = ok ? s_id[i] : UINT64_MAX;
+            ids_out[(size_t)q * k + i] = ok ? (S.emit_rows ? (s_dr[i] & kRowMask) : s_id[i]) : UINT64_MAX;
             keys_out[(size_t)q * k + i] = ok ? (key_flip ? key_flip - key : key) : UINT32_MAX;
         }
     }
@@ -156,7 +160,7 @@ template <typename KeyFn>
 __global__ void __launch_bounds__(256)
 exact_select_kernel(KeyFn fn, const uint64_t *__restrict__ ids, uint64_t id_base, uint64_t N,
                     const uint32_t *__restrict__ flags, uint32_t nq, uint32_t k, uint32_t key_flip, ExactScratch *scr,
-                    uint64_t *out_id, uint32_t *out_key, uint64_t *ids_out, uint32_t *keys_out) {
+                    uint64_t *out_id, uint32_t *out_key, uint64_t *out_row, int emit_rows, uint64_t *ids_out, uint32_t *keys_out) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned int s_any;
@@ -238,7 +242,7 @@ exact_select_kernel(KeyFn fn, const uint64_t *__restrict__ ids, uint64_t id_base
             uint64_t id = ids ? ids[r] : id_base + r;
             if (d == kstar && id > idstar) continue;
             unsigned int pos = atomicAdd(&scr->out_count, 1u);
-            if (pos < k) { out_id[pos] = id; out_key[pos] = d; }
+            if (pos < k) { out_id[pos] = id; out_key[pos] = d; out_row[pos] = r; }
         }
         grid.sync();
         // ---- 4. CTA 0 orders the winners (k <= 2048: rank by counting, O(k^2) on a tiny set)
@@ -253,7 +257,7 @@ exact_select_kernel(KeyFn fn, const uint64_t *__restrict__ ids, uint64_t id_base
                     uint64_t idj = out_id[j]; uint32_t dj = out_key[j];
                     rank += (dj < d || (dj == d && (idj < id || (idj == id && j < i))));
                 }
-                ids_out[(size_t)q * k + rank] = id;
+                ids_out[(size_t)q * k + rank] = emit_rows ? out_row[i] : id;
                 keys_out[(size_t)q * k + rank] = KeyFn::report(d, key_flip);
             }
         }
@@ -263,16 +267,17 @@ exact_select_kernel(KeyFn fn, const uint64_t *__restrict__ ids, uint64_t id_base
 
 template <typename KeyFn>
 static int exact_select_fallback(ucfp_lane *ctx, ucfp_corpus *c, int occ, KeyFn fn, const uint32_t *flags, uint32_t nq, uint32_t k,
-                                 uint32_t key_flip, uint64_t *ids_out, uint32_t *keys_out) {
-    size_t scratch = sizeof(ExactScratch) + (sizeof(uint64_t) + sizeof(uint32_t)) * (size_t)k + 64;
+                                 uint32_t key_flip, uint64_t *ids_out, uint32_t *keys_out, int emit_rows = 0) {
+    size_t scratch = sizeof(ExactScratch) + (2 * sizeof(uint64_t) + sizeof(uint32_t)) * (size_t)k + 64;
     UCFP_TRY(ctx->misc.reserve(scratch));
     ExactScratch *scr = ctx->misc.as<ExactScratch>();
     uint64_t *out_id = reinterpret_cast<uint64_t *>(scr + 1);
-    uint32_t *out_key = reinterpret_cast<uint32_t *>(out_id + k);
+    uint64_t *out_row = out_id + k;
+    uint32_t *out_key = reinterpret_cast<uint32_t *>(out_row + k);
     if (occ < 1) occ = 1;   // measured once per context by the *_device_init functions
     const uint64_t *ids = c->id_mode == 1 ? c->ids : nullptr;
     uint64_t id_base = c->id_base, N = c->size;
-    void *args[] = {&fn, &ids, &id_base, &N, &flags, &nq, &k, &key_flip, &scr, &out_id, &out_key, &ids_out, &keys_out};
+    void *args[] = {&fn, &ids, &id_base, &N, &flags, &nq, &k, &key_flip, &scr, &out_id, &out_key, &out_row, &emit_rows, &ids_out, &keys_out};
     UCFP_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)exact_select_kernel<KeyFn>, dim3(ctx->sm_count * occ), dim3(256), args,
                                               0, ctx->stream));
     count_launch(ctx);

@@ -92,6 +92,12 @@ class Context:
         check(self._L.ucfp_ctx_last_scan_fallbacks(self._h, C.byref(n)))
         return int(n.value)
 
+    def last_scan_stats(self):
+        """-> (queries recomputed by the exact fallback, longest candidate list between two compactions) of the most recent scan."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(self._L.ucfp_ctx_last_scan_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def profile_begin(self) -> None:
         check(self._L.ucfp_ctx_profile_begin(self._h))
 
