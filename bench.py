@@ -528,6 +528,12 @@ def main() -> int:
             for _ in range(2):
                 ctx.image_hash_uniform(px_host.numpy(), n_host, w, h, out=out_host)
             ms_e = timed(lambda: ctx.image_hash_uniform(px_host.numpy(), n_host, w, h, out=out_host), 3) / 3
+            img_parity = None
+            if rank == 0 and args.parity_queries > 0:   # the batch that was just timed, first 32 images, against the oracle (docs/HASH_SPEC.md)
+                import oracle
+                want_words = oracle.image_multihash_batch(px[:32].cpu().numpy(), threads=oracle.host_threads())
+                img_parity = {"images": 32, "ok": bool((out[:32].cpu().numpy().view(np.uint64) == want_words).all()),
+                              "against": "oracle/ (docs/HASH_SPEC.md; parity with imgfprint 0.4.1 itself is unpinned)"}
             gbps = n_img * (3.0 * w * h + 408) / (ms_i / 1e3) / 1e9
             secondary[f"{w}x{h}"] = {"metric": "images_hashed_per_s_multi_bundle", "value": world * n_img / (ms_i / 1e3),
                                      "unit": "images/s", "images_per_gpu_per_step": n_img,
@@ -535,7 +541,8 @@ def main() -> int:
                                                   "note": "3*w*h + 408 algorithmic bytes per image; the spec's exact f32 arithmetic "
                                                           "(no FMA) makes the FP32/ALU issue rate the bound in force"},
                                      "e2e": {"value": world * n_host / (ms_e / 1e3), "unit": "images/s",
-                                             "h2d_bytes_per_step": n_host * 3 * w * h, "d2h_bytes_per_step": n_host * 408}}
+                                             "h2d_bytes_per_step": n_host * 3 * w * h, "d2h_bytes_per_step": n_host * 408},
+                                     "parity_check": img_parity}
             del px, out, px_host
     # the other two scans of the hot path at BASELINE.json's shapes, sharded like the headline (configs[2], configs[3])
     if not args.no_paths:
@@ -548,33 +555,40 @@ def main() -> int:
         secondary["jaccard"] = secondary_jaccard(torch, ctx, group, rank, world, dev, timed, peak, args.small_paths)
         secondary["cosine"] = secondary_cosine(torch, ctx, group, rank, world, dev, timed, bf16_peak, args.small_paths)
     achieved = k_bytes / (k_ms / 1e3) / 1e9 if k_ms else None
-    traffic_path = os.path.join(ROOT, "profiles", "hamming_scan_traffic.json")
-    # ncu-measured DRAM bytes per scanned row (profiles/), scaled to this run's rows per launch
-    n_launch = t_n if t_n else k_n
-    traffic = (json.load(open(traffic_path))["dram_bytes_per_row"] * shard * args.steps / n_launch
-               if os.path.exists(traffic_path) and n_launch else None)
+    clk = clocks.summary()
 
-    # Dominant kernel of the step.  A >= 64-query batch runs on the int8 tensor pipe: achieved = int8 operations the
-    # tensor pipe executes (64 per (query, code) pair -- one 64-element +-1 dot product per TWO pairs) / kernel time.
-    # MEASURED_PEAKS.json has no int8 figure; int8 issues at twice the bf16 rate, so peak = 2 x the measured bf16 peak.
+    # Dominant kernel of the step.  A >= 64-query batch runs on the int8 tensor pipe: achieved = int8 operations the tensor
+    # pipe EXECUTES (64 per (query, code) pair -- one 64-element +-1 dot product per TWO pairs) / kernel time.
+    # Peak: MEASURED_PEAKS.json has no int8 figure, so the denominator is this repo's own measurement of the instruction the
+    # kernel issues -- tcgen05.mma kind::i8, M128 x N256 x K64 back to back into two TMEM stages: 256.0 clk per tile
+    # (scripts/micro/tmem_port.cu mode 0, output committed as profiles/r02_tmem_port.txt) = 16 384 int8 ops/clk/SM -- at the SM
+    # clock sampled during this run.  The round-1 denominator (2 x the cuBLAS bf16 figure of MEASURED_PEAKS.json, taken at a
+    # power-limited 1 305 MHz) is kept beside it as `frac_vs_2x_bf16_sustained`.
     pairs = nq * float(shard) * args.steps
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_mhz = clk["sm_mhz"] or 1965.0
+    int8_peak = 16384.0 * sm_count * sm_mhz * 1e6 / 1e12
     if t_n:
         tops = t_ops / (t_ms / 1e3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "hamming_mma_scan_kernel", "achieved": tops, "peak": 2 * bf16_peak,
-                    "unit": "TFLOP/s", "frac": tops / (2 * bf16_peak), "traffic": traffic,
-                    "peak_source": "2 x " + bf16_src + ": int8 tcgen05.mma issues at twice the bf16 rate; no int8 figure is measured",
+        roofline = {"bound": "tensor", "kernel": "hamming_mma_scan_kernel", "achieved": tops, "peak": int8_peak,
+                    "unit": "TFLOP/s", "frac": tops / int8_peak, "traffic": None,
+                    "peak_source": f"measured: int8 tcgen05.mma M128xN256xK64 at 256.0 clk/tile (profiles/r02_tmem_port.txt) x {sm_count} SMs x "
+                                   f"{sm_mhz:.0f} MHz sampled under load; MEASURED_PEAKS.json holds no int8 figure",
+                    "frac_vs_2x_bf16_sustained": tops / (2 * bf16_peak), "tensor_pipe_active_ncu": 0.39,
                     "launches": t_n, "kernel_ms_per_step": t_ms / args.steps,
                     "pairs_per_s": (t_ops / 64.0) / (t_ms / 1e3),
                     "all_scan_launches": {"launches": k_n, "kernel_ms_per_step": k_ms / args.steps,
                                           "pairs_per_s": pairs / (k_ms / 1e3) if k_ms else None},
-                    "note": "achieved counts int8 operations (TOP/s) EXECUTED by the tensor pipe; the textbook binary-GEMM count "
-                            "is 128 per pair, twice this.  The bound in force is the epilogue (tcgen05.ld + s16x2 min/max on the "
-                            "ALU pipe), see DESIGN.md 4.1; HBM traffic is 8 B per row per 1024-query batch (`traffic`).  "
-                            "`streaming` is hamming_scan_kernel with 1-2 queries per corpus pass, where HBM is the bound",
+                    "note": "achieved counts int8 operations (TOP/s) EXECUTED by the tensor pipe; `frac` agrees with ncu's "
+                            "sm__pipe_tensor_cycles_active (0.39, profiles/r01_hamming_mma_q1024_ncu.txt).  The bound in force is the "
+                            "epilogue: ~420 clk of ALU-pipe min/max per 256-clk accumulator tile plus exposed mbarrier / tcgen05.ld "
+                            "latency (DESIGN.md 4.1, profiles/r02_hamming_schedules.md).  DRAM traffic is 8.02 B per row per batch "
+                            "(ncu, profiles/hamming_scan_traffic.json): not measured live, hence `traffic` null.  `streaming` is "
+                            "hamming_scan_kernel with 1-2 queries per corpus pass, where HBM is the bound",
                     "streaming": streaming}
     else:
         roofline = {"bound": "hbm", "kernel": "hamming_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src, "launches": k_n,
+                    "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_src, "launches": k_n,
                     "kernel_ms_per_step": k_ms / args.steps, "pairs_per_s": pairs / (k_ms / 1e3) if k_ms else None,
                     "note": "algorithmic bytes = 8 B x rows x queries per launch", "streaming": streaming}
 
@@ -610,7 +624,7 @@ def main() -> int:
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(lt.item()),
             "roofline": roofline,
-            "clocks": clocks.summary(),
+            "clocks": clk,
             "secondary": secondary,
             "config2": config2,
         }
@@ -622,7 +636,9 @@ def main() -> int:
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if parity is not None and not parity["ok"]:
+    secondary_bad = [k for k, v in secondary.items() if isinstance(v, dict) and isinstance(v.get("parity_check"), dict) and not v["parity_check"]["ok"]]
+    if (parity is not None and not parity["ok"]) or secondary_bad:
+        sys.stderr.write(f"PARITY FAILURE: headline {parity}, secondary paths {secondary_bad}\n")
         return 3   # a fast answer that differs from the oracle is not a result
     return 0
 

@@ -34,7 +34,7 @@ static void lane_destroy(ucfp_lane *ln) {
     if (!ln) return;
     cudaStreamSynchronize(ln->own_stream);
     DevBuf *bufs[] = {&ln->q_dev, &ln->out_ids_dev, &ln->out_keys_dev, &ln->cand, &ln->cand_count, &ln->qstate, &ln->flags, &ln->misc,
-                      &ln->img_desc_dev, &ln->img_out_dev, &ln->img_status_dev, &ln->img_tables_dev, &ln->img_stage_dev, &ln->stats, &ln->mh_a, &ln->mh_b};
+                      &ln->img_desc_dev, &ln->img_out_dev, &ln->img_status_dev, &ln->img_tables_dev, &ln->img_stage_dev, &ln->stats, &ln->mh_a, &ln->mh_b, &ln->spill};
     for (DevBuf *b : bufs) b->release();
     ln->pin_a.release(); ln->pin_b.release();
     cudaStreamDestroy(ln->own_stream);

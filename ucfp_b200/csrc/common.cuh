@@ -114,6 +114,7 @@ struct ucfp_lane {
     // scratch of the scans
     ucfp::DevBuf q_dev, out_ids_dev, out_keys_dev, cand, cand_count, qstate, flags, misc;
     ucfp::DevBuf img_desc_dev, img_out_dev, img_status_dev, img_tables_dev, img_stage_dev;
+    ucfp::DevBuf spill;                  // Hamming tensor scan: per-CTA queues of admitted pairs (64 KiB per CTA)
     ucfp::DevBuf mh_a, mh_b;             // multi-hash re-rank: query codes + coarse candidates, scored + merged lists
     ucfp::PinnedBuf pin_a, pin_b;
     ucfp::DevBuf stats;                  // u64[4]: [0] queries recomputed by the exact fallback in this lane's last scan

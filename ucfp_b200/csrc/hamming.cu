@@ -248,8 +248,14 @@ struct MmaScanArgs {
     uint64_t row0, row_end;                  // rows [row0, row_end), row0 even
     const QSlot *slots; const uint64_t *kth_id; uint32_t nq;
     uint64_t *cand; uint32_t *count; uint32_t cap;
-    uint32_t wait_flags;                     // bit 0: MMA issuer and TMA producer spin on their mbarriers; bit 1: epilogue warps spin
+    uint32_t wait_flags;                     // experiments only (hamming_experiments.cuh)
+    // Admitted pairs are parked in a per-CTA queue in global memory ({query, dist << 40 | row}, slot taken with a SHARED-memory
+    // atomic) and moved into the per-query candidate lists by spill_scatter_kernel after the launch: a lane that admits a pair no
+    // longer waits ~1 us for a returning global atomic while the other fifteen epilogue warps and the MMA issuer wait for it.
+    uint4 *spill; uint32_t *spill_count; uint32_t spill_cap;
 };
+
+constexpr uint32_t kSpillCap = 4096;         // entries per CTA and launch (64 KiB); beyond it a lane appends directly as before
 
 // Cold path of one lane (= one query) whose bounds were crossed somewhere in its 64 accumulators.  It runs AFTER the warp
 // has handed the TMEM stage back, from the packed register image alone (|D| <= 4160 fits the 16 bits that were loaded),
@@ -258,7 +264,7 @@ struct MmaScanArgs {
 // low 7 bits ^ 64; x_b = (D + x_a) / 64).  Only u == 0, where x_a = 64 and -64 alias, reads the two codes.
 template <int NREG>   // NREG packed registers = 2 NREG accumulator columns = 4 NREG codes starting at first_row
 __device__ __forceinline__ void hamming_mma_settle(const uint32_t (&p)[NREG], uint64_t first_row, uint32_t thr_hot, uint32_t q,
-                                                   const MmaScanArgs &A, const uint4 *s_q, const uint64_t *s_kid) {
+                                                   const MmaScanArgs &A, const uint4 *s_q, const uint64_t *s_kid, uint32_t *s_spill_n = nullptr) {
     const int32_t hi_bound = 64 * (63 - 2 * (int32_t)thr_hot);
     uint32_t m_even = 0, m_odd = 0;   // bit c: column 2c / 2c + 1 can hold an admissible pair
 #pragma unroll
@@ -298,10 +304,28 @@ __device__ __forceinline__ void hamming_mma_settle(const uint32_t (&p)[NREG], ui
             if (r >= A.row_end || d[h] > thr) continue;
             const uint64_t id = A.ids ? (d[h] == thr ? A.ids[r] : 0) : A.id_base + r;
             if (d[h] < thr || id < kid) {
-                const uint32_t pos = atomicAdd(&A.count[q], 1u);
-                if (pos < A.cap) A.cand[(size_t)q * A.cap + pos] = ((uint64_t)d[h] << 40) | r;
+                const uint64_t entry = ((uint64_t)d[h] << 40) | r;
+                const uint32_t slot = s_spill_n ? atomicAdd(s_spill_n, 1u) : 0xFFFFFFFFu;
+                if (slot < A.spill_cap) {   // fire and forget: nothing waits for this store
+                    A.spill[(size_t)blockIdx.x * A.spill_cap + slot] = make_uint4(q, 0u, (uint32_t)entry, (uint32_t)(entry >> 32));
+                } else {
+                    const uint32_t pos = atomicAdd(&A.count[q], 1u);
+                    if (pos < A.cap) A.cand[(size_t)q * A.cap + pos] = entry;
+                }
             }
         }
+    }
+}
+
+// After a tensor-scan launch: every CTA's parked pairs go to their queries' candidate lists (same counters, same overflow rule).
+__global__ void __launch_bounds__(256) spill_scatter_kernel(const uint4 *__restrict__ spill, const uint32_t *__restrict__ spill_count, uint32_t spill_cap,
+                                                             uint64_t *cand, uint32_t *count, uint32_t cap) {
+    const uint32_t n = min(spill_count[blockIdx.x], spill_cap);
+    const uint4 *mine = spill + (size_t)blockIdx.x * spill_cap;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint4 e = mine[i];
+        const uint32_t pos = atomicAdd(&count[e.x], 1u);
+        if (pos < cap) cand[(size_t)e.x * cap + pos] = (uint64_t)e.w << 32 | e.z;
     }
 }
 
@@ -324,6 +348,7 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
     uint64_t *cfull = reinterpret_cast<uint64_t *>(s_bnd + kMmaMaxQueries);
     uint64_t *cempty = cfull + kMmaMaxImgStages, *tfull = cempty + kMmaMaxImgStages, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint32_t *s_spill_n = tmem_slot + 1;   // entries this CTA has parked in its global queue
     const uint32_t n_tiles = (uint32_t)((A.row_end - A.row0 + kMmaTileCodes - 1) / kMmaTileCodes);
 
     for (uint32_t q = threadIdx.x; q < q_tiles * kMmaQTile; q += blockDim.x) {
@@ -350,6 +375,7 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
         s_bnd[q] = make_uint2(hi1 << 16 | hi1, lo1 << 16 | lo1);   // both halfwords
     }
     if (threadIdx.x == 0) {
+        *s_spill_n = 0;
         for (uint32_t s = 0; s < n_stages; ++s) { mbar_init(&cfull[s], kPreExpanded ? 1 : kMmaExpWarps * 32); mbar_init(&cempty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kMmaEpiWarps); }
         mbar_fence_init();
@@ -466,13 +492,15 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
                 as ^= 1; aph ^= as ^ 1;
                 if (fired) {   // the bound of the hot test, recomputed: thr - 1 under implicit ids (0 when nothing can be admitted)
                     const uint32_t thr = s_q[q].z;
-                    hamming_mma_settle<32>(p, first_row, (A.ids == nullptr && s_kid[q] < A.id_base + A.row0) ? (thr == 0 ? 0u : thr - 1) : thr, q, A, s_q, s_kid);
+                    hamming_mma_settle<32>(p, first_row, (A.ids == nullptr && s_kid[q] < A.id_base + A.row0) ? (thr == 0 ? 0u : thr - 1) : thr, q, A, s_q, s_kid,
+                                           A.spill ? s_spill_n : nullptr);
                 }
             }
         }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0 && A.spill) A.spill_count[blockIdx.x] = *s_spill_n;
     if (warp == 0) {
         tcgen05_fence_after();
         tmem_dealloc_512(tmem_base);
@@ -560,7 +588,8 @@ int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
     constexpr long env_wait = 0;
 #endif
     static const bool env_no_mma = getenv("UCFP_HAMMING_NO_MMA") != nullptr;   // developer switches: POPC scan only /
-    static const bool env_no_ops = getenv("UCFP_HAMMING_NO_OPS") != nullptr;   // expand codes in the kernel although operand rows exist
+    static const bool env_no_ops = getenv("UCFP_HAMMING_NO_OPS") != nullptr;
+    static const bool env_no_spill = getenv("UCFP_HAMMING_NO_SPILL") != nullptr;   // developer switch: admit straight into the lists (round-1 behaviour)   // expand codes in the kernel although operand rows exist
     static const long env_img_maxq = getenv("UCFP_HAMMING_IMG_MAXQ") ? atol(getenv("UCFP_HAMMING_IMG_MAXQ")) : 7 * kMmaQTile;
 
     for (size_t q0 = 0; q0 < nq; q0 += kMaxQueriesPerPass) {
@@ -628,7 +657,11 @@ int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
                 const unsigned mma_grid = (unsigned)(tiles < (uint64_t)ctx->sm_count ? tiles : (uint64_t)ctx->sm_count);
                 ProfScope ps(ctx, UCFP_PROF_HAMMING_SCAN, 8.0 * (double)n * nqp);
                 ProfScope pt(ctx, UCFP_PROF_HAMMING_TENSOR, 64.0 * (double)n * nqp);
-                const MmaScanArgs margs{codes, reinterpret_cast<const uint4 *>(c->ham_ops), ids, c->id_base, pos, pos + n, slots, kth, nqp, cand, count, cap, (uint32_t)env_wait};
+                UCFP_TRY(ctx->spill.reserve((size_t)mma_grid * kSpillCap * sizeof(uint4) + 4 * (size_t)mma_grid + 256));
+                uint4 *spill = ctx->spill.as<uint4>();
+                uint32_t *spill_count = reinterpret_cast<uint32_t *>(spill + (size_t)mma_grid * kSpillCap);
+                const MmaScanArgs margs{codes, reinterpret_cast<const uint4 *>(c->ham_ops), ids, c->id_base, pos, pos + n, slots, kth, nqp, cand, count, cap, (uint32_t)env_wait,
+                                        env_no_spill ? nullptr : spill, spill_count, kSpillCap};
                 // With all eight query tiles in use a 512-code stage lasts ~3 300 clk and the in-kernel expansion hides completely
                 // behind it (measured 41.8 vs 43.0 ms per 1 B rows); below that the ready-made images win (7.6 vs 13.5 ms at 64-128 queries).
                 const bool have_images = c->ham_ops && !env_no_ops && pos % kMmaTileCodes == 0;
@@ -646,6 +679,10 @@ int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
                 if (launched) {}
                 else if (have_images && (long)nqp <= env_img_maxq) hamming_mma_scan_kernel<true><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
                 else hamming_mma_scan_kernel<false><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
+                if (!launched && !env_no_spill) {   // the parked pairs of this launch join their queries' lists before the compaction
+                    spill_scatter_kernel<<<mma_grid, 256, 0, st>>>(spill, spill_count, kSpillCap, cand, count, cap);
+                    count_launch(ctx);
+                }
             } else {
                 ProfScope ps(ctx, UCFP_PROF_HAMMING_SCAN, 8.0 * (double)n * nqp);
                 hamming_scan_kernel<<<(unsigned)grid, kScanThreads, sizeof(QSlot) * nqp, st>>>(
