@@ -249,13 +249,16 @@ struct MmaScanArgs {
     const QSlot *slots; const uint64_t *kth_id; uint32_t nq;
     uint64_t *cand; uint32_t *count; uint32_t cap;
     uint32_t wait_flags;                     // experiments only (hamming_experiments.cuh)
-    // Admitted pairs are parked in a per-CTA queue in global memory ({query, dist << 40 | row}, slot taken with a SHARED-memory
-    // atomic) and moved into the per-query candidate lists by spill_scatter_kernel after the launch: a lane that admits a pair no
-    // longer waits ~1 us for a returning global atomic while the other fifteen epilogue warps and the MMA issuer wait for it.
+    // A lane whose hot test fired does not settle its 128 rows inside the scan: it parks {query, first row} in a per-CTA queue in
+    // global memory (slot taken with a SHARED-memory atomic, store fire-and-forget) and recheck_parked_kernel settles the
+    // parked strips after the launch with ordinary popcounts.  Settling in place costs a lone lane ~500 instructions while the
+    // other fifteen epilogue warps and the MMA issuer wait two accumulator stages later: in a 125M-row shard that was 0.74 ms
+    // of 5.4 ms (ncu launch list, profiles/r02_launches_125m.md).
     uint4 *spill; uint32_t *spill_count; uint32_t spill_cap;
 };
 
-constexpr uint32_t kSpillCap = 4096;         // entries per CTA and launch (64 KiB); beyond it a lane appends directly as before
+constexpr uint32_t kRecheckSlices = 8;       // CTAs of recheck_parked_kernel per queue
+constexpr uint32_t kSpillCap = 4096;         // strips per CTA and launch (64 KiB); beyond it a lane settles in place as before
 
 // Cold path of one lane (= one query) whose bounds were crossed somewhere in its 64 accumulators.  It runs AFTER the warp
 // has handed the TMEM stage back, from the packed register image alone (|D| <= 4160 fits the 16 bits that were loaded),
@@ -264,7 +267,7 @@ constexpr uint32_t kSpillCap = 4096;         // entries per CTA and launch (64 K
 // low 7 bits ^ 64; x_b = (D + x_a) / 64).  Only u == 0, where x_a = 64 and -64 alias, reads the two codes.
 template <int NREG>   // NREG packed registers = 2 NREG accumulator columns = 4 NREG codes starting at first_row
 __device__ __forceinline__ void hamming_mma_settle(const uint32_t (&p)[NREG], uint64_t first_row, uint32_t thr_hot, uint32_t q,
-                                                   const MmaScanArgs &A, const uint4 *s_q, const uint64_t *s_kid, uint32_t *s_spill_n = nullptr) {
+                                                   const MmaScanArgs &A, const uint4 *s_q, const uint64_t *s_kid) {
     const int32_t hi_bound = 64 * (63 - 2 * (int32_t)thr_hot);
     uint32_t m_even = 0, m_odd = 0;   // bit c: column 2c / 2c + 1 can hold an admissible pair
 #pragma unroll
@@ -304,28 +307,51 @@ __device__ __forceinline__ void hamming_mma_settle(const uint32_t (&p)[NREG], ui
             if (r >= A.row_end || d[h] > thr) continue;
             const uint64_t id = A.ids ? (d[h] == thr ? A.ids[r] : 0) : A.id_base + r;
             if (d[h] < thr || id < kid) {
-                const uint64_t entry = ((uint64_t)d[h] << 40) | r;
-                const uint32_t slot = s_spill_n ? atomicAdd(s_spill_n, 1u) : 0xFFFFFFFFu;
-                if (slot < A.spill_cap) {   // fire and forget: nothing waits for this store
-                    A.spill[(size_t)blockIdx.x * A.spill_cap + slot] = make_uint4(q, 0u, (uint32_t)entry, (uint32_t)(entry >> 32));
-                } else {
-                    const uint32_t pos = atomicAdd(&A.count[q], 1u);
-                    if (pos < A.cap) A.cand[(size_t)q * A.cap + pos] = entry;
-                }
+                const uint32_t pos = atomicAdd(&A.count[q], 1u);
+                if (pos < A.cap) A.cand[(size_t)q * A.cap + pos] = ((uint64_t)d[h] << 40) | r;
             }
         }
     }
 }
 
-// After a tensor-scan launch: every CTA's parked pairs go to their queries' candidate lists (same counters, same overflow rule).
-__global__ void __launch_bounds__(256) spill_scatter_kernel(const uint4 *__restrict__ spill, const uint32_t *__restrict__ spill_count, uint32_t spill_cap,
-                                                             uint64_t *cand, uint32_t *count, uint32_t cap) {
+// After a tensor-scan launch: one warp per parked strip {query, first row} settles its 128 rows (lane l: rows 4l .. 4l + 3) under
+// the same admission rule as hamming_mma_settle -- d < thr, or d == thr and id below the k-th result's -- and appends to the
+// query's candidate list (same counters, same overflow rule).  The bounds are the ones the scan launch itself used: only the
+// compaction that follows changes them.
+__global__ void __launch_bounds__(256) recheck_parked_kernel(const uint4 *__restrict__ spill, const uint32_t *__restrict__ spill_count, uint32_t spill_cap,
+                                                              const uint64_t *__restrict__ codes, const uint64_t *__restrict__ ids, uint64_t id_base, uint64_t row_end,
+                                                              const QSlot *__restrict__ slots, const uint64_t *__restrict__ kth_id,
+                                                              uint64_t *cand, uint32_t *count, uint32_t cap) {
     const uint32_t n = min(spill_count[blockIdx.x], spill_cap);
     const uint4 *mine = spill + (size_t)blockIdx.x * spill_cap;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // gridDim.y CTAs share a queue: the chain entry -> query slot -> codes -> append is all latency, so it wants many warps
+    for (uint32_t i = blockIdx.y * (blockDim.x >> 5) + warp; i < n; i += gridDim.y * (blockDim.x >> 5)) {
         const uint4 e = mine[i];
-        const uint32_t pos = atomicAdd(&count[e.x], 1u);
-        if (pos < cap) cand[(size_t)e.x * cap + pos] = (uint64_t)e.w << 32 | e.z;
+        const uint32_t q = e.x;
+        const uint64_t r0 = ((uint64_t)e.w << 32 | e.z) + 4 * lane;   // even first row: 16-byte aligned pairs
+        const QSlot s = slots[q];
+        const uint64_t kid = kth_id[q];
+        uint64_t code[4] = {0, 0, 0, 0};
+        if (r0 + 3 < row_end) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(codes + r0), b = *reinterpret_cast<const uint4 *>(codes + r0 + 2);
+            code[0] = (uint64_t)a.y << 32 | a.x; code[1] = (uint64_t)a.w << 32 | a.z;
+            code[2] = (uint64_t)b.y << 32 | b.x; code[3] = (uint64_t)b.w << 32 | b.z;
+        } else {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) if (r0 + h < row_end) code[h] = codes[r0 + h];
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const uint64_t r = r0 + h;
+            const uint32_t d = __popc((uint32_t)code[h] ^ s.lo) + __popc((uint32_t)(code[h] >> 32) ^ s.hi);
+            if (r >= row_end || d > s.thr) continue;
+            const uint64_t id = ids ? (d == s.thr ? ids[r] : 0) : id_base + r;
+            if (d < s.thr || id < kid) {
+                const uint32_t pos = atomicAdd(&count[q], 1u);
+                if (pos < cap) cand[(size_t)q * cap + pos] = ((uint64_t)d << 40) | r;
+            }
+        }
     }
 }
 
@@ -490,10 +516,14 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);   // the accumulators now live in registers: release the stage first
                 as ^= 1; aph ^= as ^ 1;
-                if (fired) {   // the bound of the hot test, recomputed: thr - 1 under implicit ids (0 when nothing can be admitted)
-                    const uint32_t thr = s_q[q].z;
-                    hamming_mma_settle<32>(p, first_row, (A.ids == nullptr && s_kid[q] < A.id_base + A.row0) ? (thr == 0 ? 0u : thr - 1) : thr, q, A, s_q, s_kid,
-                                           A.spill ? s_spill_n : nullptr);
+                if (fired) {
+                    const uint32_t slot = A.spill ? atomicAdd(s_spill_n, 1u) : 0xFFFFFFFFu;
+                    if (slot < A.spill_cap) {   // park the strip: nothing waits for this store
+                        A.spill[(size_t)blockIdx.x * A.spill_cap + slot] = make_uint4(q, 0u, (uint32_t)first_row, (uint32_t)(first_row >> 32));
+                    } else {   // queue full (or switched off): settle in place; the hot test's bound is thr - 1 under implicit ids
+                        const uint32_t thr = s_q[q].z;
+                        hamming_mma_settle<32>(p, first_row, (A.ids == nullptr && s_kid[q] < A.id_base + A.row0) ? (thr == 0 ? 0u : thr - 1) : thr, q, A, s_q, s_kid);
+                    }
                 }
             }
         }
@@ -588,8 +618,8 @@ int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
     constexpr long env_wait = 0;
 #endif
     static const bool env_no_mma = getenv("UCFP_HAMMING_NO_MMA") != nullptr;   // developer switches: POPC scan only /
-    static const bool env_no_ops = getenv("UCFP_HAMMING_NO_OPS") != nullptr;
-    static const bool env_no_spill = getenv("UCFP_HAMMING_NO_SPILL") != nullptr;   // developer switch: admit straight into the lists (round-1 behaviour)   // expand codes in the kernel although operand rows exist
+    static const bool env_no_ops = getenv("UCFP_HAMMING_NO_OPS") != nullptr;     // expand codes in the kernel although operand rows exist
+    static const bool env_no_spill = getenv("UCFP_HAMMING_NO_SPILL") != nullptr;   // developer switch: settle every fire inside the scan (round-1 behaviour)
     static const long env_img_maxq = getenv("UCFP_HAMMING_IMG_MAXQ") ? atol(getenv("UCFP_HAMMING_IMG_MAXQ")) : 7 * kMmaQTile;
 
     for (size_t q0 = 0; q0 < nq; q0 += kMaxQueriesPerPass) {
@@ -624,7 +654,7 @@ int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
         hamming_seed_kernel<<<dim3((seed + 255) / 256, nqp), 256, 0, st>>>(codes, seed, slots, cand, count, cap);
         count_launch(ctx, 2);
 
-        SelectState sel{cand, count, &slots[0].thr, 4, kth, flags, cap, flags + nqp, ctx->stats.as<unsigned long long>() + 1, emit_rows ? 1 : 0};
+        SelectState sel{cand, count, &slots[0].thr, 4, kth, flags, cap, flags + nqp, ctx->stats.as<unsigned long long>() + 1, emit_rows ? 1 : 0, /*small_keys=*/1};
         auto compact = [&](bool final_pass) {
             compact_lists(sel, nqp, (uint32_t)k, ids, c->id_base, final_pass, 0u, ids_out, dist_out, st);
             count_launch(ctx, 2);
@@ -679,8 +709,8 @@ int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
                 if (launched) {}
                 else if (have_images && (long)nqp <= env_img_maxq) hamming_mma_scan_kernel<true><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
                 else hamming_mma_scan_kernel<false><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
-                if (!launched && !env_no_spill) {   // the parked pairs of this launch join their queries' lists before the compaction
-                    spill_scatter_kernel<<<mma_grid, 256, 0, st>>>(spill, spill_count, kSpillCap, cand, count, cap);
+                if (!launched && !env_no_spill) {   // the strips this launch parked are settled before the compaction
+                    recheck_parked_kernel<<<dim3(mma_grid, kRecheckSlices), 256, 0, st>>>(spill, spill_count, kSpillCap, codes, ids, c->id_base, pos + n, slots, kth, cand, count, cap);
                     count_launch(ctx);
                 }
             } else {

@@ -50,6 +50,9 @@ struct ShapeDev {
     const RowEntry *rowtab; // [h] (stream kernel)
     const FinDesc *fin;    // finished rows in emission order
     const int *band_off;   // [nbands + 1] into fin
+    const uint32_t *hitems; // stream kernel: every horizontal output of every finished row, band after band, in emission order:
+                            //   tap index into hout << 24 | row's slot in the band's row buffer << 16 | byte offset into RegionGrids
+    const int *hitem_off;  // [nbands + 1] into hitems
     int band_rows, nbands, max_fin;
 };
 
@@ -225,6 +228,32 @@ int build_shape(ucfp_lane *ctx, int w, int h, ShapeTables &st) {
             }
         }
     }
+    // flat list of the horizontal outputs per band: a thread of the stream kernel takes items tid, tid + nt, ... and finds
+    // row, taps and destination byte in one word instead of walking every finished row of the band
+    std::vector<uint32_t> hitems;
+    std::vector<int> hitem_off;
+    if (ok) {
+        if (max_fin > 256) ok = false;
+        hitem_off.push_back(0);
+        for (size_t b = 0; ok && b + 1 < band_off.size(); ++b) {
+            for (int fi = band_off[b]; fi < band_off[b + 1]; ++fi) {
+                const FinDesc f = fin_rows[fi];
+                const int items = f.stream == 0 ? 32 : f.stream == 1 ? 17 : f.stream == 2 ? 128 : 68;   // fin_items()
+                for (int item = 0; item < items; ++item) {   // same mapping as hpass_item()
+                    int colset = 0, sub = item;
+                    if (f.stream >= 2) { const int per = f.stream == 2 ? 32 : 17; colset = 1 + item / per; sub = item % per; }
+                    const int region = f.stream < 2 ? 0 : 1 + 4 * f.r + (colset - 1);
+                    size_t dest; int tap;
+                    if ((f.stream & 1) == 0) { dest = offsetof(RegionGrids, g32) + (size_t)region * 1024 + f.o * 32 + sub; tap = colset * kHOuts + sub; }
+                    else if (sub < 9) { dest = offsetof(RegionGrids, g98) + (size_t)region * 72 + f.o * 9 + sub; tap = colset * kHOuts + 32 + sub; }
+                    else { dest = offsetof(RegionGrids, g8) + (size_t)region * 64 + f.o * 8 + (sub - 9); tap = colset * kHOuts + 41 + (sub - 9); }
+                    hitems.push_back((uint32_t)tap << 24 | (uint32_t)(fi - band_off[b]) << 16 | (uint32_t)dest);
+                }
+            }
+            hitem_off.push_back((int)hitems.size());
+        }
+    }
+    static_assert(sizeof(RegionGrids) < 65536 && 5 * kHOuts <= 256, "hitems packing");
     int cpt = w <= 512 ? 1 : (w <= 1024 ? 4 : 8);
     int threads = ((w + cpt - 1) / cpt + 31) / 32 * 32;
     if (threads > 512) ok = false;  // wider than 4096 px: generic kernel
@@ -270,7 +299,8 @@ int build_shape(ucfp_lane *ctx, int w, int h, ShapeTables &st) {
         rowtab[y].run = rowtab[y].flags ? 0u : 1u + (y + 1 < h ? rowtab[y + 1].run : 0u);
     size_t off_t = align16(off_w + wts.size() * 4), off_f = align16(off_t + rowtab.size() * sizeof(RowEntry));
     size_t off_b = align16(off_f + (ok ? fin_rows.size() * sizeof(FinDesc) : 0));
-    size_t total = align16(off_b + (ok ? band_off.size() * 4 : 0)) + 16;
+    size_t off_hi = align16(off_b + (ok ? band_off.size() * 4 : 0)), off_ho = align16(off_hi + (ok ? hitems.size() * 4 : 0));
+    size_t total = align16(off_ho + (ok ? hitem_off.size() * 4 : 0)) + 16;
     std::vector<uint8_t> host(total, 0);
     memcpy(&host[off_h], hout.data(), hout.size() * sizeof(Taps));
     memcpy(&host[off_v], vout.data(), vout.size() * sizeof(Taps));
@@ -279,6 +309,8 @@ int build_shape(ucfp_lane *ctx, int w, int h, ShapeTables &st) {
         memcpy(&host[off_t], rowtab.data(), rowtab.size() * sizeof(RowEntry));
         memcpy(&host[off_f], fin_rows.data(), fin_rows.size() * sizeof(FinDesc));
         memcpy(&host[off_b], band_off.data(), band_off.size() * 4);
+        memcpy(&host[off_hi], hitems.data(), hitems.size() * 4);
+        memcpy(&host[off_ho], hitem_off.data(), hitem_off.size() * 4);
     }
     UCFP_CUDA_TRY(cudaMalloc(&st.blob, total));
     st.blob_bytes = total;
@@ -291,6 +323,8 @@ int build_shape(ucfp_lane *ctx, int w, int h, ShapeTables &st) {
     d.rowtab = ok ? reinterpret_cast<const RowEntry *>(b + off_t) : nullptr;
     d.fin = ok ? reinterpret_cast<const FinDesc *>(b + off_f) : nullptr;
     d.band_off = ok ? reinterpret_cast<const int *>(b + off_b) : nullptr;
+    d.hitems = ok ? reinterpret_cast<const uint32_t *>(b + off_hi) : nullptr;
+    d.hitem_off = ok ? reinterpret_cast<const int *>(b + off_ho) : nullptr;
     d.band_rows = band_rows; d.nbands = ok ? (h + band_rows - 1) / band_rows : 0; d.max_fin = max_fin;
     return UCFP_OK;
 }
@@ -634,17 +668,13 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
         }
         __syncthreads();   // finished rows of this band are visible to everyone
         load_rowtab(band + 1);
-        {   // horizontal passes over the rows finished in this band
-            const int f_lo = S.band_off[band], f_hi = S.band_off[band + 1];
-            int start = 0;   // first thread of the current row's items; rows of a band run side by side
-            for (int fi = f_lo; fi < f_hi; ++fi) {
-                const FinDesc f = S.fin[fi];
-                const int items = fin_items(f.stream);   // <= 128 <= nt
-                int it = tid - start;
-                if (it < 0) it += nt;
-                if (it < items) hpass_item<true>(G, S, f, it, rowbuf + (size_t)(fi - f_lo) * row_words);
-                start += items;
-                if (start >= nt) start -= nt;
+        {   // horizontal passes over the rows finished in this band: one flat item list, lanes on neighbouring outputs of a row
+            const int i_lo = S.hitem_off[band], i_hi = S.hitem_off[band + 1];
+            uint8_t *grids = reinterpret_cast<uint8_t *>(&G);
+            for (int i = i_lo + tid; i < i_hi; i += nt) {
+                const uint32_t d = __ldg(S.hitems + i);
+                const Taps t = S.hout[d >> 24];
+                grids[d & 0xFFFFu] = hsample<true>(rowbuf + (size_t)((d >> 16) & 255u) * row_words, t, S.wts);
             }
         }
         __syncthreads();

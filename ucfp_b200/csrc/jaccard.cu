@@ -289,7 +289,7 @@ int jaccard_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
         const uint64_t *qp = q_dev + q0 * kSlots;
         uint64_t *ids_out = ids_out_dev + q0 * k;
         uint32_t *m_out = m_out_dev + q0 * k;
-        SelectState sel{cand, count, thr, 1, kth, flags, cap, flags + nqp, ctx->stats.as<unsigned long long>() + 1};
+        SelectState sel{cand, count, thr, 1, kth, flags, cap, flags + nqp, ctx->stats.as<unsigned long long>() + 1, 0, /*small_keys=*/1};
 
         jaccard_init_kernel<<<(nqp * kSketchWords + 255) / 256, 256, 0, st>>>(qp, nqp, qsk, thr, kth, count, flags);
         if (N == 0) {   // group scan, empty shard: contribute the trivial bound to every exchange

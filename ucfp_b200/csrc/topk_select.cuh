@@ -23,6 +23,8 @@ struct SelectState {      // per query pass, all device pointers
     unsigned long long *max_fill = nullptr;   // diagnostics (may be null): longest list any compaction of this scan has seen
     int emit_rows = 0;    // the final pass reports ROW indices instead of record ids (ties are still broken by record id): the coarse
                           // pass of the multi-hash re-rank needs the rows, and its candidate set must not depend on the row order
+    int small_keys = 0;   // keys are small integers (Hamming distance, 128 - MinHash matches): compaction first drops, by a 256-bin
+                          // histogram of the keys, every entry beyond the k-th key, and sorts the few that are left
 };
 
 constexpr uint32_t kSmallList = 1024;   // entries the small compaction launch sorts (16 KiB of shared memory)
@@ -48,14 +50,56 @@ __global__ void compact_kernel(SelectState S, uint32_t k, const uint64_t *__rest
         if (threadIdx.x == 0) S.big[q] = big ? 1u : 0u;
         if (big) return;
     } else if (!S.big[q]) return;
-    uint32_t P = 1;
-    while (P < n) P <<= 1;
-    uint64_t *s_id = sm, *s_dr = sm + P;
     uint64_t *list = S.cand + (size_t)q * S.cap;
-    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
-        uint64_t e = UINT64_MAX, id = UINT64_MAX;
-        if (i < n) { e = list[i]; uint64_t r = e & kRowMask; id = ids ? ids[r] : id_base + r; }
-        s_id[i] = id; s_dr[i] = e;
+    // Small integer keys: the entries that can be among the k best are those whose key is <= the k-th smallest KEY, which a
+    // histogram finds without sorting.  Of a seed list of 1024 random codes ~20 survive (k = 10), so the bitonic network below
+    // runs on 32 entries instead of 1024 (the seed compaction of a 1024-query batch was 91 us of a 5 ms shard scan).
+    __shared__ uint32_t s_hist[256], s_cut, s_keep, s_fill;
+    uint32_t n_keep = n, cut = 0xFFFFFFFFu;
+    if (S.small_keys && n > 32 && n > 2 * k) {
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+        if (threadIdx.x == 0) s_fill = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_hist[min((uint32_t)(list[i] >> 40), 255u)], 1u);
+        __syncthreads();
+        if (threadIdx.x < 32) {   // bin of the k-th smallest key and the number of entries up to and including that bin
+            const uint32_t lane = threadIdx.x;
+            uint32_t loc[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { loc[j] = s_hist[lane * 8 + j]; sum += loc[j]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+            uint32_t cum = incl - sum;
+            if (cum < k && k <= incl) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { cum += loc[j]; if (cum >= k) { s_cut = lane * 8 + j; s_keep = cum; break; } }
+            }
+            if (lane == 31 && incl < k) { s_cut = 255; s_keep = incl; }   // fewer than k entries: keep all (cannot happen with n > 2k)
+        }
+        __syncthreads();
+        cut = s_cut; n_keep = s_keep;
+    }
+    uint32_t P = 1;
+    while (P < n_keep) P <<= 1;
+    uint64_t *s_id = sm, *s_dr = sm + P;
+    if (cut != 0xFFFFFFFFu) {
+        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) { s_id[i] = UINT64_MAX; s_dr[i] = UINT64_MAX; }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint64_t e = list[i];
+            if (min((uint32_t)(e >> 40), 255u) <= cut) {   // slot order is arbitrary; the sort's order is total (ids are unique)
+                const uint32_t slot = atomicAdd(&s_fill, 1u);
+                const uint64_t r = e & kRowMask;
+                s_dr[slot] = e; s_id[slot] = ids ? ids[r] : id_base + r;
+            }
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+            uint64_t e = UINT64_MAX, id = UINT64_MAX;
+            if (i < n) { e = list[i]; uint64_t r = e & kRowMask; id = ids ? ids[r] : id_base + r; }
+            s_id[i] = id; s_dr[i] = e;
+        }
     }
     __syncthreads();
     for (uint32_t size = 2; size <= P; size <<= 1) {
@@ -71,7 +115,7 @@ __global__ void compact_kernel(SelectState S, uint32_t k, const uint64_t *__rest
             __syncthreads();
         }
     }
-    const uint32_t m = min(n, k);
+    const uint32_t m = min(n_keep, k);
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) list[i] = s_dr[i];
     if (final_pass) {
         for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
