@@ -1,6 +1,6 @@
 """Multi-GPU through the boundary (SURVEY 8e process model: a single process driving the GPUs of one box with
 ncclCommInitAll).  ucfp_group_scan_* over record-range shards must be byte-identical to the single-corpus scan and
-to the oracle; the Hamming scan exchanges admission bounds between the ranks while it walks its shard.  Uses as many
+to the oracle, with and without the exchange of admission bounds between the ranks while they walk their shards.  Uses as many
 GPUs as the box has (1, 2, 4 or 8); with one GPU the group degenerates to a plain scan and only the plumbing is checked."""
 import numpy as np
 import pytest
@@ -18,9 +18,14 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.fixture(scope="module")
-def group():
+@pytest.fixture(scope="module", params=[0, 4], ids=["no-bound-exchange", "4-bound-exchanges"])
+def group(request):
+    """The default group filters every shard at its own bound; UCFP_GROUP_EXCHANGES (read at group creation) turns on the
+    cross-rank bound exchange.  Both must give the same bytes."""
+    import os
+    os.environ["UCFP_GROUP_EXCHANGES"] = str(request.param)
     g = Group.local(list(range(min(_n_gpus(), 8))))
+    del os.environ["UCFP_GROUP_EXCHANGES"]
     yield g
     g.close()
 

@@ -55,7 +55,9 @@ def test_reference_ramp_images(ctx):
 
 
 @pytest.mark.parametrize("w,h", [(256, 256), (1024, 1024), (640, 480), (1000, 700), (1920, 1080), (513, 129), (128, 128),
-                                 (2048, 1536), (4096, 512)])
+                                 (2048, 1536), (4096, 512),
+                                 # two columns per thread (even widths 128..512): bulk-staged, halfword and ragged variants; odd widths stay on one
+                                 (130, 200), (132, 140), (384, 216), (510, 300), (512, 512), (200, 200), (257, 300), (511, 64)])
 def test_stream_kernel_shapes(ctx, w, h):
     check(ctx, [noise(w, h, 1), photo_like(w, h, 2)])
 

@@ -98,6 +98,7 @@ struct ucfp_exchange {
     int (*allgather)(void *comm, const void *send, void *recv, size_t bytes, cudaStream_t st) = nullptr;
     ucfp::DevBuf send, recv;
     int done = 0;   // exchanges performed in the query pass in hand
+    int max_real = 0;   // of the kBoundExchanges slots of a pass, how many really exchange (the rest only count): see group.cu
 };
 
 // One stream plus the scratch a call needs.  An entry point LEASES a lane for its whole duration (api.cu, LaneLease), so

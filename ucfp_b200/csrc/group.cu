@@ -61,6 +61,18 @@ int nccl_load() {
         }                                                                                            \
     } while (0)
 
+// How many of a query pass's bound exchanges (topk_select.cuh) really run.  Measured on 8 B200s, 1 B Hamming codes, 1 024 queries
+// (profiles/r02_bound_exchange_n8.md): 0 / 1 / 2 / 4 exchanges = 205.3 / 204.3 / 203.1 / 201.3 K queries/s with the scan kernels at
+// 4.70 ms in every case -- since fired strips are parked (hamming.cu) a looser bound costs a shard nothing measurable, and each
+// exchange is ~25 us of pack + all-gather + fold.  The Jaccard scan did not gain either (33.0 K vs 33.4 K queries/s).  Default 0;
+// UCFP_GROUP_EXCHANGES=n (read when the group is created, and it must agree on every rank) turns them on for corpora whose shards
+// are very unequal in how close their rows are to the queries.
+int bound_exchanges() {
+    const char *e = getenv("UCFP_GROUP_EXCHANGES");
+    const long n = e ? atol(e) : 0;
+    return (int)(n < 0 ? 0 : n > 64 ? 64 : n);
+}
+
 int allgather_hook(void *comm, const void *send, void *recv, size_t bytes, cudaStream_t st) {
     UCFP_NCCL_TRY(g_nccl.AllGather(send, recv, bytes, ncclChar, static_cast<ncclComm_t>(comm), st));
     return UCFP_OK;
@@ -279,7 +291,7 @@ int ucfp_group_create(const int *devices, int n, ucfp_group **out) {
         for (int i = 0; i < n; ++i) {
             Rank &R = g->ranks[i];
             R.comm = comms[i];
-            R.xch.comm = comms[i]; R.xch.world = n; R.xch.allgather = allgather_hook;
+            R.xch.comm = comms[i]; R.xch.world = n; R.xch.allgather = allgather_hook; R.xch.max_real = bound_exchanges();
             R.worker = new Worker();
             R.worker->th = std::thread(&Worker::run, R.worker);
         }
@@ -319,7 +331,7 @@ int ucfp_group_join(ucfp_ctx *ctx, const void *id128, int rank, int world, ucfp_
         memcpy(&id, id128, sizeof(id));
         ncclResult_t r = g_nccl.CommInitRank(&R.comm, world, id, rank);
         if (r != ncclSuccess) { ucfp::set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); R.ctx = nullptr; group_free(g); return UCFP_E_CUDA; }
-        R.xch.comm = R.comm; R.xch.world = world; R.xch.allgather = allgather_hook;
+        R.xch.comm = R.comm; R.xch.world = world; R.xch.allgather = allgather_hook; R.xch.max_real = bound_exchanges();
     }
     *out = g;
     return UCFP_OK;

@@ -254,7 +254,8 @@ int build_shape(ucfp_lane *ctx, int w, int h, ShapeTables &st) {
         }
     }
     static_assert(sizeof(RegionGrids) < 65536 && 5 * kHOuts <= 256, "hitems packing");
-    int cpt = w <= 512 ? 1 : (w <= 1024 ? 4 : 8);
+    static const long env_cpt2 = getenv("UCFP_IMG_NO_CPT2") ? 0 : 1;   // developer switch: one column per thread up to 512 px as before
+    int cpt = w <= 512 ? ((env_cpt2 && w >= 128 && w % 2 == 0) ? 2 : 1) : (w <= 1024 ? 4 : 8);
     int threads = ((w + cpt - 1) / cpt + 31) / 32 * 32;
     if (threads > 512) ok = false;  // wider than 4096 px: generic kernel
     if (threads < 128) threads = 128;
@@ -607,6 +608,11 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
                     for (int g = 0; g < CPT / 4; ++g)   // 4 pixels = 12 bytes = 3 words
                         luma4(p32[3 * g], p32[3 * g + 1], p32[3 * g + 2], v[(4 * g) % CPT], v[(4 * g + 1) % CPT], v[(4 * g + 2) % CPT],
                               v[(4 * g + 3) % CPT]);
+                } else if (CPT == 2 && (BULK || I.aligned4)) {   // cpt 2 is chosen for even widths only: 2 pixels = 6 bytes at an even offset
+                    const uint16_t *p16 = reinterpret_cast<const uint16_t *>(px);
+                    const uint32_t a = (uint32_t)p16[0] | (uint32_t)p16[1] << 16, b = p16[2];   // a = R0 G0 B0 R1, b = G1 B1
+                    v[0] = luma_to_f32(__dp2a_hi(UCFP_W16(722, 0), a, __dp2a_lo(UCFP_W16(2126, 7152), a, 0u)));
+                    v[1 % CPT] = luma_to_f32(__dp2a_lo(UCFP_W16(7152, 722), b, __dp2a_hi(UCFP_W16(0, 2126), a, 0u)));
                 } else {
 #pragma unroll
                     for (int cc = 0; cc < CPT; ++cc) {
@@ -824,6 +830,7 @@ int image_hash_batch(ucfp_lane *ctx, const ucfp_image_desc *descs, size_t n, uin
                 bool all_bulk = true;
                 for (size_t j = 0; j < cnt; ++j) all_bulk = all_bulk && hostdesc[g.desc_off + j].aligned4 == 2;
                 if (T.cpt == 1) { if (all_bulk) launch(image_stream_kernel<1, 512, true>); else launch(image_stream_kernel<1, 512, false>); }
+                else if (T.cpt == 2) { if (all_bulk) launch(image_stream_kernel<2, 256, true>); else launch(image_stream_kernel<2, 256, false>); }
                 else if (T.cpt == 4) { if (all_bulk) launch(image_stream_kernel<4, 256, true>); else launch(image_stream_kernel<4, 256, false>); }
                 else { if (all_bulk) launch(image_stream_kernel<8, 512, true>); else launch(image_stream_kernel<8, 512, false>); }
             } else {
@@ -853,6 +860,8 @@ int image_device_init(ucfp_ctx *) {
     const int optin = 200 * 1024;
     UCFP_CUDA_TRY(cudaFuncSetAttribute(image_stream_kernel<1, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     UCFP_CUDA_TRY(cudaFuncSetAttribute(image_stream_kernel<1, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(image_stream_kernel<2, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(image_stream_kernel<2, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     UCFP_CUDA_TRY(cudaFuncSetAttribute(image_stream_kernel<4, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     UCFP_CUDA_TRY(cudaFuncSetAttribute(image_stream_kernel<4, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     UCFP_CUDA_TRY(cudaFuncSetAttribute(image_stream_kernel<8, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));

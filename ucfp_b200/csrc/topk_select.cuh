@@ -170,6 +170,7 @@ __global__ void bounds_min_kernel(const BoundRec *__restrict__ all, uint32_t wor
 // One exchange on the lane's stream: pack, all-gather through the hook the group installed, fold the minimum back in.
 static int exchange_bounds(ucfp_lane *ctx, const SelectState &S, uint32_t nq) {
     ucfp_exchange *x = ctx->xch;
+    if (x->done >= x->max_real) { x->done++; return UCFP_OK; }   // the same on every rank (group.cu): collectives stay matched
     UCFP_TRY(x->send.reserve(sizeof(BoundRec) * nq));
     UCFP_TRY(x->recv.reserve(sizeof(BoundRec) * (size_t)nq * x->world));
     bounds_pack_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(S.thr, S.thr_stride, S.kth_id, nq, x->send.as<BoundRec>());
