@@ -43,14 +43,15 @@ def _deps_mtime() -> float:
 def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
     """experiments=True also compiles csrc/hamming_experiments.cuh (round-2 tensor-scan schedules that were measured and not
     adopted; selected with UCFP_HAMMING_MMA_V / UCFP_HAMMING_EPI_WARPS)."""
-    if not force and not experiments and os.path.exists(SO) and os.path.getmtime(SO) >= _deps_mtime():
+    extra_defs = os.environ.get("UCFP_BUILD_DEFINES", "").split()   # developer: -D switches for A/B builds on the GPU box
+    if not force and not experiments and not extra_defs and os.path.exists(SO) and os.path.getmtime(SO) >= _deps_mtime():
         return SO
     os.makedirs(OBJ, exist_ok=True)
     cc = nvcc()
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [cc, *NVCC_FLAGS, *EXTRA.get(src, []), *(["-DUCFP_HAMMING_EXPERIMENTS"] if experiments and src == "hamming.cu" else []),
+        cmd = [cc, *NVCC_FLAGS, *EXTRA.get(src, []), *(["-DUCFP_HAMMING_EXPERIMENTS"] if experiments and src == "hamming.cu" else []), *extra_defs,
                "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

@@ -64,7 +64,7 @@ struct RegionGrids {         // shared memory, per CTA, lives for the whole imag
 struct HashScratch {         // shared memory used only by hash_regions (may alias streaming buffers)
     float R[kRegions][32][8];
     float D[kRegions][64];
-    float C[8][33];              // 33: the 8 threads of an output row read C[v][x], v = 0..7, in distinct banks
+    float Ct[32][8];             // DCT cosines transposed: Ct[x][v] = C[v][x], four frequencies per LDS.128
     float med_lo[kRegions], med_hi[kRegions];
 };
 constexpr size_t kGridsBytes = (sizeof(RegionGrids) + 127) & ~size_t(127);
@@ -383,24 +383,39 @@ __device__ __forceinline__ void hpass_item(RegionGrids &G, const ShapeDev &S, Fi
 // PHash / AHash / DHash of the 17 regions from the u8 grids in shared memory (spec sections 3-5).
 __device__ void hash_regions(RegionGrids &G, HashScratch &H, uint32_t algo_mask, uint64_t *out /* 51 words */) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < 256; i += nt) H.C[i >> 5][i & 31] = c_dct_cos[i >> 5][i & 31];
+    for (int i = tid; i < 256; i += nt) H.Ct[i & 31][i >> 5] = c_dct_cos[i >> 5][i & 31];
     __syncthreads();
     if (algo_mask & UCFP_ALGO_PHASH) {
-        for (int it = tid; it < kRegions * 256; it += nt) {       // R[y][v] = sum_x g[y][x] * C[v][x]
-            int reg = it >> 8, y = (it >> 3) & 31, v = it & 7;
-            const uint8_t *g = &G.g32[reg][y * 32];
-            float t = 0.0f;
-#pragma unroll 8
-            for (int x = 0; x < 32; ++x) t = t + (float)g[x] * H.C[v][x];
-            H.R[reg][y][v] = t;
+        // R[y][v] = sum_x g[y][x] * C[v][x], x ascending.  One thread = one grid row and FOUR frequencies: a pixel is converted
+        // once for four products and the four cosines come with one LDS.128 from the transposed table.
+        for (int it = tid; it < kRegions * 64; it += nt) {
+            const int reg = it >> 6, y = (it >> 1) & 31, vh = it & 1;
+            const uint32_t *g = reinterpret_cast<const uint32_t *>(&G.g32[reg][y * 32]);
+            float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
+#pragma unroll
+            for (int xw = 0; xw < 8; ++xw) {
+                const uint32_t w = g[xw];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const float gv = (float)((w >> (8 * b)) & 255u);
+                    const float4 c = *reinterpret_cast<const float4 *>(&H.Ct[4 * xw + b][4 * vh]);
+                    t0 = t0 + gv * c.x; t1 = t1 + gv * c.y; t2 = t2 + gv * c.z; t3 = t3 + gv * c.w;
+                }
+            }
+            *reinterpret_cast<float4 *>(&H.R[reg][y][4 * vh]) = make_float4(t0, t1, t2, t3);
         }
         __syncthreads();
-        for (int it = tid; it < kRegions * 64; it += nt) {        // D[u][v] = sum_y C[u][y] * R[y][v]
-            int reg = it >> 6, u = (it >> 3) & 7, v = it & 7;
-            float t = 0.0f;
+        // D[u][v] = sum_y C[u][y] * R[y][v], y ascending; one thread = one u and four v
+        for (int it = tid; it < kRegions * 16; it += nt) {
+            const int reg = it >> 4, u = (it >> 1) & 7, vh = it & 1;
+            float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
 #pragma unroll 8
-            for (int y = 0; y < 32; ++y) t = t + H.C[u][y] * H.R[reg][y][v];
-            H.D[reg][it & 63] = t;
+            for (int y = 0; y < 32; ++y) {
+                const float c = H.Ct[y][u];
+                const float4 r = *reinterpret_cast<const float4 *>(&H.R[reg][y][4 * vh]);
+                t0 = t0 + c * r.x; t1 = t1 + c * r.y; t2 = t2 + c * r.z; t3 = t3 + c * r.w;
+            }
+            *reinterpret_cast<float4 *>(&H.D[reg][u * 8 + 4 * vh]) = make_float4(t0, t1, t2, t3);
         }
         __syncthreads();
         for (int it = tid; it < kRegions * 64; it += nt) {        // ranks 31 and 32 of the 64 coefficients
@@ -633,6 +648,7 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
             };
             int y = y_lo;
             while (y < y_hi) {
+#ifndef UCFP_IMG_SINGLE_LOOP
                 // a run of rows on which no output completes and no third output is active: nothing but arithmetic
                 const int run = min((int)rt[y - band_lo].run, y_hi - y);
                 for (int i = 0; i < run; ++i, ++y) {
@@ -640,6 +656,7 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
                     row_body(y, rt[y - band_lo], v);
                 }
                 if (y >= y_hi) break;
+#endif
                 const RowEntry &e = rt[y - band_lo];
                 float v[CPT];
                 row_body(y, e, v);
@@ -653,7 +670,7 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
 #pragma unroll
                             for (int cc = 0; cc < CPT; ++cc) acc[s][2][cc] = acc[s][2][cc] + v[cc] * w2;
                         }
-                        for (uint32_t f = 0; f < (fl >> 1); ++f) {  // the lowest active output of this pass is complete
+                        auto finish = [&]() {   // the lowest active output of this pass is complete
                             float *dst = rowbuf + (size_t)slot * row_words;
 #pragma unroll
                             for (int cc = 0; cc < CPT; ++cc) {
@@ -661,6 +678,11 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
                                 acc[s][0][cc] = acc[s][1][cc]; acc[s][1][cc] = acc[s][2][cc]; acc[s][2][cc] = 0.0f;
                             }
                             slot++;
+                        };
+                        const uint32_t nf = fl >> 1;   // <= 3: a pass has at most three active outputs (build_shape checks)
+                        if (nf) {
+                            finish();
+                            if (nf > 1) { finish(); if (nf > 2) finish(); }
                         }
                     }
                 }
@@ -677,10 +699,14 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
         {   // horizontal passes over the rows finished in this band: one flat item list, lanes on neighbouring outputs of a row
             const int i_lo = S.hitem_off[band], i_hi = S.hitem_off[band + 1];
             uint8_t *grids = reinterpret_cast<uint8_t *>(&G);
-            for (int i = i_lo + tid; i < i_hi; i += nt) {
-                const uint32_t d = __ldg(S.hitems + i);
+            int i = i_lo + tid;
+            uint32_t d = i < i_hi ? __ldg(S.hitems + i) : 0u;
+            while (i < i_hi) {   // the next item's word is in flight while this one's taps are summed
+                const int in = i + nt;
+                const uint32_t dn = in < i_hi ? __ldg(S.hitems + in) : 0u;
                 const Taps t = S.hout[d >> 24];
                 grids[d & 0xFFFFu] = hsample<true>(rowbuf + (size_t)((d >> 16) & 255u) * row_words, t, S.wts);
+                d = dn; i = in;
             }
         }
         __syncthreads();
