@@ -285,9 +285,10 @@ UCFP_API int ucfp_batcher_stats(const ucfp_batcher *b, uint64_t *queries, uint64
  * Record-range shards over the GPUs of one box: rank r holds rows [r*N/G, (r+1)*N/G) with GLOBAL record ids
  * (ucfp_corpus_set_id_base or explicit ids); every rank scans its shard against the whole query batch, the per-rank
  * top-k lists are exchanged as packed 16-byte (id, key) records in ONE NCCL all-gather and every rank runs the same
- * deterministic merge, so the result is byte-identical to the single-corpus scan.  While a Hamming batch walks its
- * shard the ranks also exchange their per-query admission bounds (one small all-gather per chunk boundary), so every
- * shard filters at the best bound any rank has found so far.
+ * deterministic merge, so the result is byte-identical to the single-corpus scan.  Optionally (environment variable
+ * UCFP_GROUP_EXCHANGES=1..4, read when the group is created, the same on every rank) the ranks also exchange their
+ * per-query admission bounds at up to four chunk boundaries of a Hamming or Jaccard batch, so that every shard filters at
+ * the best bound any rank has found so far; off by default: on 8 B200s it cost more than it saved.
  * NCCL is loaded at the first group call (dlopen of libnccl.so.2, the copy already in the process if there is one),
  * not at library load: hosts that never form a group do not need it. */
 typedef struct ucfp_group ucfp_group;

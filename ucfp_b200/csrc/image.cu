@@ -18,6 +18,7 @@
 // Both end in hash_regions(): 17 x {8x32 . 32x32 . 32x8 partial DCT-II, median, mean, gradient, ballot}.
 #include <stdlib.h>
 
+#include <algorithm>
 #include <map>
 
 #include "common.cuh"
@@ -250,6 +251,11 @@ int build_shape(ucfp_lane *ctx, int w, int h, ShapeTables &st) {
                     hitems.push_back((uint32_t)tap << 24 | (uint32_t)(fi - band_off[b]) << 16 | (uint32_t)dest);
                 }
             }
+            // Within a band the order of the items is free (each writes its own byte): sort them by tap count, so that the lanes
+            // of a warp run the same number of taps.  Unsorted, a warp straddling 4-tap (block -> 32) and 15/16-tap (block -> 9/8)
+            // outputs executed every unrolled remainder of the tap loop: 170 instead of ~75 instructions per 4-tap item.
+            std::stable_sort(hitems.begin() + hitem_off.back(), hitems.end(),
+                             [&](uint32_t a, uint32_t b) { return hout[a >> 24].n < hout[b >> 24].n; });
             hitem_off.push_back((int)hitems.size());
         }
     }
@@ -648,15 +654,17 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
             };
             int y = y_lo;
             while (y < y_hi) {
-#ifndef UCFP_IMG_SINGLE_LOOP
-                // a run of rows on which no output completes and no third output is active: nothing but arithmetic
-                const int run = min((int)rt[y - band_lo].run, y_hi - y);
-                for (int i = 0; i < run; ++i, ++y) {
-                    float v[CPT];
-                    row_body(y, rt[y - band_lo], v);
+                if constexpr (CPT >= 8) {
+                    // a run of rows on which no output completes and no third output is active: nothing but arithmetic.  (With
+                    // <= 4 columns per thread one loop body is faster -- 2.19 -> 2.29 M img/s at 256x256: the second copy of the
+                    // row arithmetic costs more in register moves at the joins than the skipped flag test saves.)
+                    const int run = min((int)rt[y - band_lo].run, y_hi - y);
+                    for (int i = 0; i < run; ++i, ++y) {
+                        float v[CPT];
+                        row_body(y, rt[y - band_lo], v);
+                    }
+                    if (y >= y_hi) break;
                 }
-                if (y >= y_hi) break;
-#endif
                 const RowEntry &e = rt[y - band_lo];
                 float v[CPT];
                 row_body(y, e, v);
@@ -680,7 +688,9 @@ image_stream_kernel(ShapeDev S, StreamSmem L, const ImgDev *__restrict__ imgs, u
                             slot++;
                         };
                         const uint32_t nf = fl >> 1;   // <= 3: a pass has at most three active outputs (build_shape checks)
-                        if (nf) {
+                        if constexpr (CPT >= 8) {   // 96 accumulators: three inlined copies of the rotation spill
+                            for (uint32_t f = 0; f < nf; ++f) finish();
+                        } else if (nf) {
                             finish();
                             if (nf > 1) { finish(); if (nf > 2) finish(); }
                         }
