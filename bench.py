@@ -179,6 +179,55 @@ def _crc(ids, keys) -> int:
     return zlib.crc32(np.ascontiguousarray(keys).tobytes(), zlib.crc32(np.ascontiguousarray(ids).tobytes()))
 
 
+def secondary_jpeg(ctx, rank, world, check):
+    """SURVEY 8f N3 / the reference's only image bench shape (benches/end_to_end.rs:40-53 starts from ENCODED bytes): images/s from
+    JPEG bitstreams in host memory -- nvJPEG decode on the device + multi-hash in ONE C-ABI call -- next to the host doing the
+    same job (Pillow = libjpeg-turbo decode + the oracle's hash, one thread, a bounded sample).  Wall clock: the call is
+    synchronous and starts from host bytes."""
+    import io
+    import time
+    try:
+        from PIL import Image
+    except Exception as e:  # no encoder on this box: nothing to feed the path with
+        return {"unavailable": f"Pillow missing: {e}"}
+    w = h = 1024
+    blobs = []
+    for seed in range(8):   # smooth synthetic scenes (JPEG of noise is meaningless), quality 85, 4:2:0
+        rng = np.random.default_rng(100 + seed)
+        y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+        img = np.zeros((h, w, 3), np.float32)
+        for c in range(3):
+            for _ in range(6):
+                fx, fy = rng.uniform(0.002, 0.05, 2)
+                img[..., c] += rng.uniform(20, 60) * np.sin(fx * x + fy * y + rng.uniform(0, 6.28))
+        buf = io.BytesIO()
+        Image.fromarray(np.clip(img + 128, 0, 255).astype(np.uint8)).save(buf, format="JPEG", quality=85, subsampling=2)
+        blobs.append(buf.getvalue())
+    batch = blobs * 32                                    # 256 images per call
+    ctx.image_hash_jpeg_batch(batch[:16])
+    ctx.image_hash_jpeg_batch(batch)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        words, status, _ = ctx.image_hash_jpeg_batch(batch)
+    dt = (time.perf_counter() - t0) / reps
+    out = {"metric": "images_hashed_per_s_from_jpeg_bytes", "value": world * len(batch) / dt, "unit": "images/s",
+           "images_per_gpu_per_step": len(batch), "encoded_mb_per_step": sum(len(b) for b in batch) / 1e6, "shape": "1024x1024, q85, 4:2:0",
+           "decoded_on_device": int((status == 0).sum()), "timing": "wall clock around the synchronous C-ABI call, host bytes in, host hashes out"}
+    if rank == 0 and check:
+        import oracle
+        w2, st2, _, px = ctx.image_hash_jpeg_batch(blobs[:4], want_pixels=True)
+        ok = bool((st2 == 0).all()) and all((w2[i] == oracle.image_multihash(px[i])).all() for i in range(4))
+        out["parity_check"] = {"images": 4, "ok": ok, "against": "oracle/ over the pixels the device decoded (JPEG decoders are not bit-identical to each other)"}
+        t0 = time.perf_counter()
+        n_cpu = 8
+        for b in blobs[:n_cpu]:
+            oracle.image_multihash(np.asarray(Image.open(io.BytesIO(b)).convert("RGB")))
+        out["cpu_decode_and_hash"] = {"value": n_cpu / (time.perf_counter() - t0), "unit": "images/s", "cores": 1,
+                                      "kind": "port", "sample": f"{n_cpu} images: Pillow (libjpeg-turbo) decode + oracle multi-hash, one thread"}
+    return out
+
+
 def secondary_jaccard(torch, ctx, group, rank, world, dev, timed, peak, small):
     """BASELINE configs[2]: MinHash-128 Jaccard top-10 over 50 M synthetic signatures (1 % of the rows copy a query's slots
     with p in {.9,.7,.5}), 256-query batch, record-range shards over the N ranks.  Row contents depend on the GLOBAL row
@@ -544,6 +593,10 @@ def main() -> int:
                                              "h2d_bytes_per_step": n_host * 3 * w * h, "d2h_bytes_per_step": n_host * 408},
                                      "parity_check": img_parity}
             del px, out, px_host
+        try:
+            secondary["jpeg_1024x1024"] = secondary_jpeg(ctx, rank, world, args.parity_queries > 0)
+        except Exception as e:   # nvJPEG is loaded with dlopen at the first call: a box without it still benches the rest
+            secondary["jpeg_1024x1024"] = {"unavailable": f"{type(e).__name__}: {e}"}
     # the other two scans of the hot path at BASELINE.json's shapes, sharded like the headline (configs[2], configs[3])
     if not args.no_paths:
         try:

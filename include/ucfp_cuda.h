@@ -151,7 +151,9 @@ UCFP_API int ucfp_image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *imgs, s
                                    ucfp_image_hashes *out, int32_t *status);
 
 /* Same, for `n` equally-sized images laid out `image_stride` bytes apart starting
- * at `pixels` (the batch-ingest layout; one descriptor for the whole batch). */
+ * at `pixels` (the batch-ingest layout; one descriptor for the whole batch).  The
+ * buffer must lie in ONE kind of memory, all host or all device: its first and last
+ * byte are checked once, not every image (UCFP_E_INVALID when they disagree). */
 UCFP_API int ucfp_image_hash_uniform(ucfp_ctx *ctx, const uint8_t *pixels, size_t n, uint32_t width, uint32_t height,
                                      uint64_t row_stride, uint64_t image_stride, uint32_t algo_mask,
                                      ucfp_image_hashes *out);

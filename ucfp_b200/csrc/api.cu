@@ -590,6 +590,31 @@ static int run_merge(ucfp_ctx *ctx, const uint64_t *ids_in, const Key *keys_in, 
     return finish_call(lane, ids_host || keys_host);
 }
 
+// shared body of the two image entry points (pixels_mem: see image_hash_batch)
+static int image_batch_call(ucfp_ctx *ctx, const ucfp_image_desc *imgs, size_t n, uint32_t algo_mask, ucfp_image_hashes *out, int32_t *status,
+                            int pixels_mem) {
+    using namespace ucfp;
+    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    UCFP_LEASE(ctx);
+    if (n == 0) return UCFP_OK;
+    UCFP_REQUIRE(imgs && out, UCFP_E_INVALID, "NULL image descriptors or output");
+    UCFP_REQUIRE((algo_mask & ~UCFP_ALGO_MULTI) == 0 && algo_mask != 0, UCFP_E_INVALID, "bad algo_mask 0x%x", algo_mask);
+    void *out_dev = nullptr;
+    bool out_host = false;
+    UCFP_TRY(stage_out(lane->img_out_dev, out, sizeof(ucfp_image_hashes) * n, &out_dev, &out_host));
+    // per-image status: straight into the caller's array when it is host memory, else through the lane's pinned staging
+    const bool status_dev = status && classify(status) == Mem::Device;
+    int32_t *st_host = status;
+    if (!status || status_dev) {
+        UCFP_TRY(lane->pin_b.reserve(4 * n));
+        st_host = lane->pin_b.as<int32_t>();
+    }
+    UCFP_TRY(image_hash_batch(lane, imgs, n, algo_mask, static_cast<ucfp_image_hashes *>(out_dev), st_host, pixels_mem));
+    if (out_host) UCFP_TRY(copy_back(lane, out, out_dev, sizeof(ucfp_image_hashes) * n));
+    if (status_dev) UCFP_CUDA_TRY(cudaMemcpyAsync(status, st_host, 4 * n, cudaMemcpyHostToDevice, lane->stream));
+    return finish_call(lane, out_host || status_dev);
+}
+
 extern "C" {
 
 int ucfp_merge_topk_u32(ucfp_ctx *ctx, const uint64_t *ids_in, const uint32_t *keys_in, size_t parts, size_t nq, size_t k,
@@ -617,25 +642,7 @@ int ucfp_merge_topk_f32(ucfp_ctx *ctx, const uint64_t *ids_in, const float *scor
 int ucfp_image_hash_batch(ucfp_ctx *ctx, const ucfp_image_desc *imgs, size_t n, uint32_t algo_mask, ucfp_image_hashes *out,
                           int32_t *status) {
     UCFP_API_BEGIN
-    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
-    UCFP_LEASE(ctx);
-    if (n == 0) return UCFP_OK;
-    UCFP_REQUIRE(imgs && out, UCFP_E_INVALID, "NULL image descriptors or output");
-    UCFP_REQUIRE((algo_mask & ~UCFP_ALGO_MULTI) == 0 && algo_mask != 0, UCFP_E_INVALID, "bad algo_mask 0x%x", algo_mask);
-    void *out_dev = nullptr;
-    bool out_host = false;
-    UCFP_TRY(stage_out(lane->img_out_dev, out, sizeof(ucfp_image_hashes) * n, &out_dev, &out_host));
-    // per-image status: straight into the caller's array when it is host memory, else through the lane's pinned staging
-    const bool status_dev = status && classify(status) == Mem::Device;
-    int32_t *st_host = status;
-    if (!status || status_dev) {
-        UCFP_TRY(lane->pin_b.reserve(4 * n));
-        st_host = lane->pin_b.as<int32_t>();
-    }
-    UCFP_TRY(image_hash_batch(lane, imgs, n, algo_mask, static_cast<ucfp_image_hashes *>(out_dev), st_host));
-    if (out_host) UCFP_TRY(copy_back(lane, out, out_dev, sizeof(ucfp_image_hashes) * n));
-    if (status_dev) UCFP_CUDA_TRY(cudaMemcpyAsync(status, st_host, 4 * n, cudaMemcpyHostToDevice, lane->stream));
-    return finish_call(lane, out_host || status_dev);
+    return image_batch_call(ctx, imgs, n, algo_mask, out, status, -1);
     UCFP_API_END
 }
 
@@ -651,7 +658,11 @@ int ucfp_image_hash_uniform(ucfp_ctx *ctx, const uint8_t *pixels, size_t n, uint
     std::vector<ucfp_image_desc> d(n);
     for (size_t i = 0; i < n; ++i) d[i] = ucfp_image_desc{pixels + i * image_stride, width, height, row_stride};
     std::vector<int32_t> st(n, 0);
-    int rc = ucfp_image_hash_batch(ctx, d.data(), n, algo_mask, out, st.data());
+    // one buffer: ask once where it lives (its first and last byte), not once per image
+    const uint8_t *last = pixels + (n - 1) * image_stride + row_stride * (height - 1) + 3ull * width - 1;
+    const Mem m0 = classify(pixels), m1 = classify(last);
+    UCFP_REQUIRE(m0 == m1, UCFP_E_INVALID, "the pixel buffer starts and ends in different kinds of memory");
+    int rc = image_batch_call(ctx, d.data(), n, algo_mask, out, st.data(), m0 == Mem::Device ? 1 : 0);
     if (rc != UCFP_OK) return rc;
     for (size_t i = 0; i < n; ++i)
         if (st[i] != UCFP_OK) { set_error("image %zu failed with status %d", i, st[i]); return st[i]; }

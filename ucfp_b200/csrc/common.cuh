@@ -230,8 +230,9 @@ int merge_f32(ucfp_lane *ctx, const uint64_t *ids_in, const float *keys_in, size
 int pack_topk(ucfp_lane *ctx, const uint64_t *ids, const void *keys32, size_t n, void *records_out);
 int merge_packed(ucfp_lane *ctx, const void *records, size_t parts, size_t nq, size_t k, int key_is_f32, int descending, uint64_t *ids_out, void *keys_out);
 int synth_fill_u64(ucfp_lane *ctx, uint64_t *dst_dev, uint64_t nwords, uint64_t seed, uint64_t start_word);
+// pixels_mem: -1 = ask the driver where each image lives; 0 / 1 = every image is in host / device memory (the caller knows)
 int image_hash_batch(ucfp_lane *ctx, const ucfp_image_desc *descs_host, size_t n, uint32_t algo_mask,
-                     ucfp_image_hashes *out_dev, int32_t *status_host);
+                     ucfp_image_hashes *out_dev, int32_t *status_host, int pixels_mem = -1);
 // once per context, with the context's device current: kernel attributes (dynamic shared memory opt-in) and occupancies
 int hamming_device_init(ucfp_ctx *ctx);
 int jaccard_device_init(ucfp_ctx *ctx);

@@ -164,7 +164,7 @@ int ucfp_image_hash_jpeg_batch(ucfp_ctx *ctx, const uint8_t *const *jpegs, const
     bool out_host = false;
     UCFP_TRY(stage_out(lane->img_out_dev, out, sizeof(ucfp_image_hashes) * n, &out_dev, &out_host));
     std::vector<int32_t> hst(n, 0);
-    UCFP_TRY(image_hash_batch(lane, descs.data(), n, algo_mask, static_cast<ucfp_image_hashes *>(out_dev), hst.data()));
+    UCFP_TRY(image_hash_batch(lane, descs.data(), n, algo_mask, static_cast<ucfp_image_hashes *>(out_dev), hst.data(), /*pixels_mem=*/1));   // the decoder's own device buffer
     for (size_t i = 0; i < n; ++i)
         if (status[i] == UCFP_OK) status[i] = hst[i];
     if (out_host) UCFP_TRY(copy_back(lane, out, out_dev, sizeof(ucfp_image_hashes) * n));
