@@ -211,6 +211,72 @@ jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint32_t *__restr
     }
 }
 
+// ---- probe: a cheap first look for real neighbours --------------------------------------------------------------------
+// Until a query's list holds k good rows its bound is loose, and a chunk scanned under a loose bound costs ~10x more per
+// row (no early exit after the first 32 slots, every chance byte collision is verified): on a 6.25 M-row shard that was
+// 3.4 of 7.4 ms.  The probe walks the first kProbeRows rows looking at the first 32 slots only and verifies, with the
+// whole warp, just the rows in which >= kProbeMinBytes of those 32 low bytes agree (a row sharing a quarter of its slots
+// with the query; chance: 32 choose 8 / 256^8).  Its hits go to lists of their own; their k-th best (key, id) is a valid
+// upper bound of the true k-th best -- it is made of k real rows of this corpus -- and the main scan starts from it
+// (adopt_probe_bound_kernel).  The lists of the main scan never see a probe entry, so nothing is inserted twice; a query
+// without k such neighbours keeps its loose bound and behaves as before.
+constexpr uint64_t kProbeRows = 1ULL << 19;
+constexpr uint64_t kProbeMinCorpus = 1ULL << 17;   // below this the whole scan is cheaper than a probe
+constexpr uint32_t kProbeMinBytes = 8;
+constexpr int kProbeWords = 8;                     // sketch words of the first 32 slots
+
+__global__ void jaccard_probe_init_kernel(uint32_t nq, uint32_t *pthr, uint64_t *pkid, uint32_t *pcount, uint32_t *pflags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) { pthr[i] = 128; pkid[i] = UINT64_MAX; pcount[i] = 0; pflags[i] = 0; }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+jaccard_probe_kernel(const uint32_t *__restrict__ sketch, const uint64_t *__restrict__ sigs, uint64_t row0, uint64_t nrows,
+                     const uint64_t *__restrict__ q, const uint32_t *__restrict__ qsketch, uint32_t nq,
+                     uint64_t *pcand, uint32_t *pcount, uint32_t cap) {
+    extern __shared__ uint32_t smem[];   // [nq][8]: plane-0 sketch words of the first 32 slots
+    for (uint32_t i = threadIdx.x; i < nq * kProbeWords; i += kScanThreads) smem[i] = qsketch[(size_t)(i / kProbeWords) * kSketchWords + i % kProbeWords];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t row_end = row0 + nrows;
+    const uint64_t ntiles = (nrows + kScanThreads - 1) / kScanThreads;   // row0 is a multiple of 32
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t row = row0 + tile * kScanThreads + threadIdx.x;
+        const bool valid = row < row_end;
+        uint32_t w[kProbeWords];
+        const uint32_t *sp = sketch + sketch_index(row & ~31ULL, 0) + lane;   // padded allocation: always readable
+#pragma unroll
+        for (int j = 0; j < kProbeWords; ++j) w[j] = __ldg(sp + j * 32);
+        for (uint32_t qi = 0; qi < nq; ++qi) {
+            const uint4 *qv = reinterpret_cast<const uint4 *>(smem + (size_t)qi * kProbeWords);
+            const uint32_t bm = 32u - (uint32_t)__popc(ne_bytes_8words(w, qv[0], qv[1]));
+            unsigned hits = __ballot_sync(0xffffffffu, valid && bm >= kProbeMinBytes);
+            while (hits) {
+                const int src = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const uint64_t srow = __shfl_sync(0xffffffffu, row, src);
+                const uint32_t m = warp_matches(sigs + srow * kSlots, q + (size_t)qi * kSlots, lane);
+                if (lane == 0) {
+                    const uint32_t pos = atomicAdd(&pcount[qi], 1u);   // beyond cap the entry is dropped: any subset of real rows bounds the k-th best
+                    if (pos < cap) pcand[(size_t)qi * cap + pos] = ((uint64_t)(128u - m) << 40) | srow;
+                }
+            }
+        }
+    }
+}
+
+// (pthr, pkid) = k-th best of a query's probe list, if it found k rows.  The main scan must admit those k rows themselves when
+// it reaches them, so the bound it starts from is "at or before (pthr, pkid)" = strictly before (pthr, pkid + 1).
+__global__ void adopt_probe_bound_kernel(uint32_t nq, const uint32_t *__restrict__ pthr, const uint64_t *__restrict__ pkid, uint32_t *thr, uint64_t *kth_id) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const uint32_t t = pthr[i];
+    uint64_t id = pkid[i];
+    if (t == 128 && id == UINT64_MAX) return;   // fewer than k neighbours in the probe: nothing learned
+    if (id != UINT64_MAX) id += 1;
+    if (t < thr[i] || (t == thr[i] && id < kth_id[i])) { thr[i] = t; kth_id[i] = id; }
+}
+
 // exact-selection key for flagged queries: true slot matches of one row, one thread per row
 struct JaccardKey {
     static constexpr int kKeyBits = 8;
@@ -306,6 +372,28 @@ int jaccard_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
             count_launch(ctx, 2);
         };
         compact(seed == N);
+        static const bool env_no_probe = getenv("UCFP_JACCARD_NO_PROBE") != nullptr;   // developer switch
+        if (!env_no_probe && nqp > 8 && N >= kProbeMinCorpus) {
+            const uint64_t pn = (N - seed < kProbeRows) ? N - seed : kProbeRows;
+            // probe lists, bounds and flags of their own, in the lane's spill buffer
+            const size_t off_cnt = sizeof(uint64_t) * (size_t)cap * nqp, off_kid = off_cnt + sizeof(uint32_t) * 4 * (size_t)nqp;
+            UCFP_TRY(ctx->spill.reserve(off_kid + sizeof(uint64_t) * nqp + 64));
+            unsigned char *pb = ctx->spill.as<unsigned char>();
+            uint64_t *pcand = reinterpret_cast<uint64_t *>(pb);
+            uint32_t *pcount = reinterpret_cast<uint32_t *>(pb + off_cnt), *pthr = pcount + nqp, *pflags = pthr + nqp;   // pflags[2 nqp]: overflow, big
+            uint64_t *pkid = reinterpret_cast<uint64_t *>(pb + off_kid);
+            jaccard_probe_init_kernel<<<(nqp + 255) / 256, 256, 0, st>>>(nqp, pthr, pkid, pcount, pflags);
+            const uint64_t ptiles = (pn + kScanThreads - 1) / kScanThreads, pslots = (uint64_t)ctx->sm_count * 4;
+            {
+                ProfScope ps(ctx, UCFP_PROF_JACCARD_SCAN, 256.0 * (double)pn * nqp);   // a quarter of the slots
+                jaccard_probe_kernel<<<(unsigned)(ptiles < pslots ? ptiles : pslots), kScanThreads, (size_t)nqp * kProbeWords * 4, st>>>(
+                    sketch, sigs, seed, pn, qp, qsk, nqp, pcand, pcount, cap);
+            }
+            SelectState probe{pcand, pcount, pthr, 1, pkid, pflags, cap, pflags + nqp, nullptr, 0, /*small_keys=*/1};
+            compact_lists(probe, nqp, (uint32_t)k, ids, c->id_base, false, 128u, nullptr, nullptr, st);
+            adopt_probe_bound_kernel<<<(nqp + 255) / 256, 256, 0, st>>>(nqp, pthr, pkid, thr, kth);
+            count_launch(ctx, 5);
+        }
         // Chunks scanned under a loose bound cost ~8x more per row (no early exit, every chance collision is verified), and the
         // bound only tightens between chunks: x4 steps reach a useful bound after ~340 K rows of config 3 instead of ~590 K.
         static const long env_growth = getenv("UCFP_JACCARD_GROWTH") ? atol(getenv("UCFP_JACCARD_GROWTH")) : 0;   // developer knob
