@@ -314,14 +314,19 @@ cosine_coarse_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
 #pragma unroll
                     for (int c = 0; c < 32; ++c) any |= __uint_as_float(v[c]) >= tau[c];
                     if (any && valid) {
+                        // All the list slots are requested first, then filled: an in-order thread that tests each returned
+                        // position before asking for the next one pays the ~2 us round trip of a contended atomic once per
+                        // survivor -- with the loose bounds of a batch's first chunks that was most of a small launch
+                        // (4 096 rows: 85 us, tensor pipe 3 % active).
+                        uint32_t pos[32];
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
-                            if (__uint_as_float(v[c]) >= tau[c]) {
-                                const uint32_t qi = qt * n_tile + c0 + c;
-                                uint32_t pos = atomicAdd(&S.count[qi], 1u);
-                                if (pos < kCap) S.cand[(size_t)qi * kCap + pos] = (uint32_t)my_row;
-                            }
+                            pos[c] = kCap;
+                            if (__uint_as_float(v[c]) >= tau[c]) pos[c] = atomicAdd(&S.count[qt * n_tile + c0 + c], 1u);
                         }
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (pos[c] < kCap) S.cand[(size_t)(qt * n_tile + c0 + c) * kCap + pos[c]] = (uint32_t)my_row;
                     }
                 }
                 tcgen05_fence_before();
