@@ -197,7 +197,45 @@ cosine_rescore_kernel(CosState S, uint32_t k, const float *__restrict__ rows, co
         S.kept_n[q] = m;
         S.count[q] = 0;
         if (n_raw > kCap) S.flags[q] = 1;
-        S.thr[q] = m >= k ? s_sc[k - 1] : -INFINITY;
+        S.thr[q] = fmaxf(S.thr[q], m >= k ? s_sc[k - 1] : -INFINITY);   // never below a bound the probe established (it is made of k real rows too)
+    }
+}
+
+// ---- probe: a bound before the first chunk ------------------------------------------------------------------
+// The exhaustive seed (512 rows x every query, exact) re-read the same 1 MB of rows once per query: 265 us of a 3.2 ms
+// shard scan, L2-bound.  The probe asks the tensor pass instead: a coarse launch over the first kProbeRows rows in which
+// every warp names, per query, the best row of its 32 (cosine_coarse_kernel, probe != 0), then ONE CTA per query scores those
+// kProbeRows / 32 rows exactly.  The k-th best of them is a valid lower bound of the true k-th best score -- k real rows of
+// this corpus reach it -- and the main scan starts from it at row 0 with nothing in its lists, so no row is ever
+// inserted twice.  Exactness never depends on which rows the probe picked.
+constexpr uint32_t kProbeRows = 2048;        // a multiple of the 128-row tile; 64 candidates per query
+constexpr uint32_t kProbeRowsMax = 8192;
+constexpr uint64_t kProbeMinCorpus = 1ULL << 15;
+
+__global__ void __launch_bounds__(256)
+cosine_probe_bound_kernel(CosState S, uint32_t k, uint32_t n_cand, const float *__restrict__ rows, const float *__restrict__ row_norm, uint32_t dim,
+                          const float *__restrict__ queries, const float *__restrict__ q_norm) {
+    __shared__ float s_sc[kProbeRowsMax / 32];
+    const uint32_t q = blockIdx.x;
+    const float qn = q_norm[q];
+    const float *qv = queries + (size_t)q * dim;
+    const int lane = threadIdx.x & 31, j = lane & 7, gbase = lane & ~7;
+    const unsigned gmask = 0xFFu << gbase;
+    const uint32_t groups = blockDim.x / 8;
+    for (uint32_t c = threadIdx.x / 8; c < ((n_cand + groups - 1) / groups) * groups; c += groups) {
+        if (c < n_cand) {   // uniform within a group of 8 lanes
+            const uint32_t r = S.cand[(size_t)q * kCap + c];
+            const float vn = row_norm[r];
+            const float dot = dot8_group(qv, rows + (size_t)r * dim, dim, j, gmask, gbase);
+            if (j == 0) s_sc[c] = (vn != 0.0f && qn != 0.0f) ? dot / (qn * vn) : -INFINITY;   // the rescoring step's arithmetic
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < n_cand && k <= n_cand) {   // rank by counting: the candidate with exactly k - 1 better ones is the k-th best
+        const float mine = s_sc[threadIdx.x];
+        uint32_t better = 0;
+        for (uint32_t i = 0; i < n_cand; ++i) { const float o = s_sc[i]; better += (o > mine) || (o == mine && i < threadIdx.x); }
+        if (better == k - 1 && mine > -INFINITY) S.thr[q] = mine;
     }
 }
 
@@ -207,7 +245,7 @@ cosine_rescore_kernel(CosState S, uint32_t k, const float *__restrict__ rows, co
 // the query's admission bound while the next tile's MMAs are already running.
 __global__ void __launch_bounds__(kGemmThreads, 1)
 cosine_coarse_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_q,
-                     uint64_t row0, uint64_t row_end, uint32_t nq, uint32_t n_tile, uint32_t k_chunks, uint32_t q_groups, CosState S) {
+                     uint64_t row0, uint64_t row_end, uint32_t nq, uint32_t n_tile, uint32_t k_chunks, uint32_t q_groups, CosState S, int probe) {
     extern __shared__ unsigned char smem_raw[];
     // 128B-swizzled operand tiles must start on a 1024-byte boundary of the shared window
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -304,6 +342,21 @@ cosine_coarse_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
                 for (uint32_t c0 = 0; c0 < cols; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((quad * 32u) << 16) + as * kMaxNTile + c0, v);
+                    if (probe) {
+                        // probe launch (cosine_scan): no bound exists yet.  Every warp reports, per query, the row with the best
+                        // COARSE score among its 32 rows: S.cand[q][group of 32 rows].  One REDUX per column on the score's
+                        // order-preserving integer image, the low 5 bits traded for the lane; no atomics, no lists.
+                        const uint32_t group = (uint32_t)((my_row - row0) >> 5);
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const uint32_t b = v[c];
+                            const uint32_t ordered = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+                            const uint32_t best = __reduce_max_sync(0xffffffffu, valid ? ((ordered & ~31u) | (31u - (uint32_t)lane)) : 0u);
+                            if (lane == 0 && c0 + c < cols)
+                                S.cand[(size_t)(qt * n_tile + c0 + c) * kCap + group] = (uint32_t)(my_row + (31u - (best & 31u)));
+                        }
+                        continue;
+                    }
                     // admission bounds of these 32 queries (padded with +inf): 8 broadcast LDS.128, then one pass
                     // that only records whether ANY score clears its bound -- survivors are rare
                     const float4 *tp = reinterpret_cast<const float4 *>(s_tau + qt * n_tile + c0);
@@ -469,9 +522,15 @@ int cosine_scan(ucfp_lane *ctx, ucfp_corpus *c, const float *q_dev, size_t nq, s
         UCFP_CUDA_TRY(cudaMemsetAsync(q_unit, 0, off_norm, st));
         cosine_prepare_kernel<<<(nqp * 8 + 255) / 256, 256, 0, st>>>(qp, 0, nqp, dim, dim_pad, q_norm, q_unit);
         cosine_init_kernel<<<(nqp + 255) / 256, 256, 0, st>>>(S, nqp);
-        const uint32_t seed = (uint32_t)(N < kSeedRows ? N : kSeedRows);
-        cosine_seed_kernel<<<dim3((seed + 255) / 256, nqp), 256, 0, st>>>(S, seed);
-        count_launch(ctx, 3);
+        static const bool env_no_probe = getenv("UCFP_COSINE_NO_PROBE") != nullptr;   // developer switch: the exhaustive 512-row seed
+        static const long env_probe_rows = getenv("UCFP_COSINE_PROBE_ROWS") ? atol(getenv("UCFP_COSINE_PROBE_ROWS")) : 0;       // developer knobs
+        static const long env_probe_growth = getenv("UCFP_COSINE_PROBE_GROWTH") ? atol(getenv("UCFP_COSINE_PROBE_GROWTH")) : 0;
+        const uint32_t probe_rows = env_probe_rows >= 128 && env_probe_rows <= (long)kProbeRowsMax ? (uint32_t)env_probe_rows / 128 * 128 : kProbeRows;
+        const uint32_t probe_growth = env_probe_growth > 0 ? (uint32_t)env_probe_growth : 8;
+        const bool use_probe = !env_no_probe && N >= kProbeMinCorpus && nqp >= 16 && k <= probe_rows / 64;
+        const uint32_t seed = use_probe ? 0u : (uint32_t)(N < kSeedRows ? N : kSeedRows);
+        if (!use_probe) cosine_seed_kernel<<<dim3((seed + 255) / 256, nqp), 256, 0, st>>>(S, seed);
+        count_launch(ctx, use_probe ? 2 : 3);
         auto rescore = [&](bool final_pass) {
             cosine_rescore_kernel<<<nqp, 256, 16 * kSmallList, st>>>(S, (uint32_t)k, rows, row_norm, dim, qp, q_norm, ids, c->id_base,
                                                                     final_pass ? 1 : 0, ids_out, score_out, kSmallList, 0);
@@ -479,11 +538,22 @@ int cosine_scan(ucfp_lane *ctx, ucfp_corpus *c, const float *q_dev, size_t nq, s
                                                               final_pass ? 1 : 0, ids_out, score_out, 8192, 1);
             count_launch(ctx, 2);
         };
-        rescore(seed == N);
+        if (!use_probe) rescore(seed == N);
 
         CUtensorMap map_q;
         UCFP_TRY(make_map(&map_q, q_unit, nq_pad, dim_pad, n_tile));
-        uint64_t pos = seed, chunk = (uint64_t)seed * 8;
+        if (use_probe) {
+            const uint32_t tiles = probe_rows / kTileRows, q_tiles = (nqp + n_tile - 1) / n_tile;
+            uint32_t q_groups = (uint32_t)ctx->sm_count / tiles < q_tiles ? (uint32_t)ctx->sm_count / tiles : q_tiles;
+            if (q_groups < 1) q_groups = 1;
+            {
+                ProfScope ps(ctx, UCFP_PROF_COSINE_SCAN, 2.0 * (double)probe_rows * dim * nqp);
+                cosine_coarse_kernel<<<tiles * q_groups, kGemmThreads, kGemmSmem, st>>>(map_rows, map_q, 0, probe_rows, nqp, n_tile, dim_pad / kBlockK, q_groups, S, 1);
+            }
+            cosine_probe_bound_kernel<<<nqp, 256, 0, st>>>(S, (uint32_t)k, probe_rows / 32, rows, row_norm, dim, qp, q_norm);
+            count_launch(ctx, 2);
+        }
+        uint64_t pos = seed, chunk = use_probe ? (uint64_t)probe_rows * probe_growth : (uint64_t)seed * 8;
         while (pos < N) {
             uint64_t n = (N - pos < chunk) ? N - pos : chunk;
             uint32_t tiles = (uint32_t)((n + kTileRows - 1) / kTileRows);
@@ -496,7 +566,7 @@ int cosine_scan(ucfp_lane *ctx, ucfp_corpus *c, const float *q_dev, size_t nq, s
                     q_groups = (uint32_t)ctx->sm_count / tiles < q_tiles ? (uint32_t)ctx->sm_count / tiles : q_tiles;
                     grid = tiles * q_groups;
                 }
-                cosine_coarse_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(map_rows, map_q, pos, pos + n, nqp, n_tile, dim_pad / kBlockK, q_groups, S);
+                cosine_coarse_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(map_rows, map_q, pos, pos + n, nqp, n_tile, dim_pad / kBlockK, q_groups, S, 0);
             }
             count_launch(ctx);
             pos += n;
