@@ -84,7 +84,7 @@ def test_duplicate_flood_takes_exact_fallback(ctx):
 
 # ---- batches of >= 16 queries run chunks of >= 2^19 rows on the int8 tensor pipe (hamming_mma_scan_kernel) ----------
 @pytest.mark.parametrize("n,nq,k", [(700_001, 16, 10), (1_500_000, 130, 10), (2_000_003, 1024, 10), (1_250_000, 1000, 3),
-                                    (900_000, 1025, 10), (1_100_000, 257, 100)])
+                                    (900_000, 1025, 10), (1_100_000, 257, 100), (1_000_000, 640, 10), (800_000, 100, 10)])
 def test_tensor_path_matches_oracle(ctx, n, nq, k):
     """Ragged query counts (partial 128-query tiles, > 1024 -> two passes) and ragged row counts (odd tails,
     partial 512-code tiles) through the tensor-core filter: bit-exact ids and distances."""
@@ -168,9 +168,12 @@ def test_tensor_path_incremental_appends_rebuild_pair_rows(ctx):
     corpus.close()
 
 
-def test_tensor_path_without_operand_rows_in_a_fresh_process():
+@pytest.mark.parametrize("switch", ["UCFP_HAMMING_NO_OPS=1", "UCFP_HAMMING_STAGGER=0"])
+def test_tensor_path_variants_in_a_fresh_process(switch):
     """The scan also runs without the pre-built operand rows (their allocation is optional): the producer warps then expand
-    the codes in the kernel.  The switch is read once per process, hence the subprocess."""
+    the codes in the kernel (NO_OPS).  STAGGER=0 selects the lock-step epilogue of the stage-image kernel (the product path is the
+    two-group epilogue).  The switches are read once per process, hence the subprocess; 200 and 1000 queries = two and eight
+    query tiles (an even and an odd share of the accumulator items per epilogue group)."""
     import os
     import subprocess
     import sys
@@ -183,8 +186,14 @@ def test_tensor_path_without_operand_rows_in_a_fresh_process():
             "gi, gd = c.scan_hamming(q, 10)\n"
             "oi, od = oracle.hamming_topk(codes, q, 10, threads=oracle.host_threads())\n"
             "assert (gi == oi).all() and (gd == od).all() and ctx.last_scan_fallbacks() == 0\n"
+            "q = oracle.fill_u64(1000, 43); q[:3] = codes[[7, 600_000, 1_234_560]]\n"
+            "gi, gd = c.scan_hamming(q, 10)\n"
+            "oi, od = oracle.hamming_topk(codes, q, 10, threads=oracle.host_threads())\n"
+            "assert (gi == oi).all() and (gd == od).all() and ctx.last_scan_fallbacks() == 0\n"
             "print('ok')\n")
-    env = dict(os.environ, UCFP_HAMMING_NO_OPS="1", PYTHONPATH=root)
+    name, value = switch.split("=")
+    env = dict(os.environ, PYTHONPATH=root)
+    env[name] = value
     out = subprocess.run([sys.executable, "-c", prog], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 

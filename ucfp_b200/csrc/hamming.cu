@@ -189,6 +189,7 @@ constexpr int kMmaImgBytes = kMmaRows * 64;          // pre-built stage image: 1
 constexpr int kMmaMaxImgStages = 8;
 constexpr int kMmaExpWarps = 4, kMmaEpiWarps = 16;
 constexpr int kMmaThreads = 32 * (1 + kMmaExpWarps + kMmaEpiWarps);
+constexpr int kMmaStaggerThreads = 32 * (2 + kMmaEpiWarps);   // two-group epilogue: MMA issuer, one TMA thread, 16 epilogue warps: 112 registers per thread
 constexpr int kMmaColsPerWarp = kMmaRows / (kMmaEpiWarps / 4);
 constexpr uint32_t kMmaMaxQueries = 1024;
 constexpr uint32_t kMmaMinQueries = 64;              // measured crossover: the POPC scan costs 0.24 ms per query and 1 B rows, the tensor scan >= 15 ms per batch
@@ -355,9 +356,52 @@ __global__ void __launch_bounds__(256) recheck_parked_kernel(const uint4 *__rest
     }
 }
 
-template <bool kPreExpanded>
-__global__ void __launch_bounds__(kMmaThreads, 1)
+#ifdef UCFP_HAMMING_DIAG   // developer build: A.wait_flags bit 0 skips the min/max test, bit 1 also the TMEM loads (what is left is the MMA pipeline and its hand-overs)
+#define UCFP_DIAG_NO_TEST(A) ((A).wait_flags & 3u)
+#define UCFP_DIAG_NO_LD(A) ((A).wait_flags & 2u)
+#else
+#define UCFP_DIAG_NO_TEST(A) false
+#define UCFP_DIAG_NO_LD(A) false
+#endif
+constexpr uint32_t kMmaNeverHiPk = 0x7FFE7FFEu;   // hi16 - 1 (both halfwords) of a query that can never fire: no accumulator crosses it
+// The hot test of one 64-column strip: per-halfword signed max of D and min of D << 9 (VIMNMX3.S16x2: two columns per lane-op)
+// against the query's two bounds; true when some halfword exceeded hi16 - 1 or fell below lo16 + 1.
+__device__ __forceinline__ bool hamming_mma_strip_test(const uint32_t (&p)[32], uint32_t hi_pk, uint32_t lo_pk) {
+    uint32_t mx[4], mn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mx[j] = p[j]; mn[j] = p[j] * 512u; }
+#pragma unroll
+    for (int c = 4; c < 28; c += 8)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            mx[j] = __vimax3_s16x2(mx[j], p[c + j], p[c + 4 + j]);
+            mn[j] = __vimin3_s16x2(mn[j], p[c + j] * 512u, p[c + 4 + j] * 512u);
+        }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mx[j] = __vmaxs2(mx[j], p[28 + j]); mn[j] = __vmins2(mn[j], p[28 + j] * 512u); }
+    const uint32_t m2 = __vimax3_s16x2(__vimax3_s16x2(mx[0], mx[1], mx[2]), mx[3], hi_pk);
+    const uint32_t n2 = __vimin3_s16x2(__vimin3_s16x2(mn[0], mn[1], mn[2]), mn[3], lo_pk);
+    return (m2 != hi_pk) | (n2 != lo_pk);
+}
+
+// A fired strip is parked for recheck_parked_kernel, or settled in place from the register image when the CTA's queue is full.
+__device__ __forceinline__ void hamming_mma_fire(const uint32_t (&p)[32], uint64_t first_row, uint32_t q, const MmaScanArgs &A,
+                                                 uint32_t *s_spill_n, const uint4 *s_q, const uint64_t *s_kid) {
+    const uint32_t slot = A.spill ? atomicAdd(s_spill_n, 1u) : 0xFFFFFFFFu;
+    if (slot < A.spill_cap) {   // park the strip: nothing waits for this store
+        A.spill[(size_t)blockIdx.x * A.spill_cap + slot] = make_uint4(q, 0u, (uint32_t)first_row, (uint32_t)(first_row >> 32));
+    } else {   // queue full (or switched off): settle in place; the hot test's bound is thr - 1 under implicit ids
+        const uint32_t thr = s_q[q].z;
+        hamming_mma_settle<32>(p, first_row, (A.ids == nullptr && s_kid[q] < A.id_base + A.row0) ? (thr == 0 ? 0u : thr - 1) : thr, q, A, s_q, s_kid);
+    }
+}
+
+
+template <bool kPreExpanded, bool kStagger>
+__global__ void __launch_bounds__(kStagger ? kMmaStaggerThreads : kMmaThreads, 1)
 hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
+    static_assert(kPreExpanded || !kStagger, "the two-group epilogue exists for the stage-image form only");
+    constexpr int kProdWarps = kStagger ? 1 : kMmaExpWarps;   // warps between the MMA issuer and the epilogue warps
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -403,7 +447,7 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
     if (threadIdx.x == 0) {
         *s_spill_n = 0;
         for (uint32_t s = 0; s < n_stages; ++s) { mbar_init(&cfull[s], kPreExpanded ? 1 : kMmaExpWarps * 32); mbar_init(&cempty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kMmaEpiWarps); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kStagger ? kMmaEpiWarps / 2 : kMmaEpiWarps); }
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc_512(tmem_slot);   // two accumulator stages of 256 columns
@@ -437,7 +481,7 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
             if (lane == 0) umma_commit(&cempty[s]);   // frees the operand stage when its MMAs retire
             __syncwarp();
         }
-    } else if (warp <= kMmaExpWarps) {
+    } else if (warp <= kProdWarps) {
         // ===== producers: thread t fills operand rows t and t + 128 of a stage =====
         const uint32_t t = threadIdx.x - 32;
         uint32_t it = 0;
@@ -481,8 +525,48 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
             }
         }
     } else {
+        const uint32_t quad = warp & 3, part = (warp - 1 - kProdWarps) >> 2;
+        if constexpr (kStagger) {
+            // ===== epilogue, two groups out of phase: group g (8 warps) serves accumulator stage g, i.e. every second item =====
+            // warp -> TMEM lane quadrant (warp % 4) and 128 of the stage's 256 columns, read as two 64-column strips into two
+            // register images.  The stage goes back to the MMA issuer as soon as both strips have landed; the min/max work of this
+            // group then overlaps the other group's barrier round trip and tcgen05.ld, which all sixteen warps of the lock-step
+            // schedule (kStagger = false below) sit out together.  Needs 64 payload registers per thread: only the stage-image form
+            // of the kernel (18 warps, 112 registers) has them.
+            const uint32_t grp = part & 1, colh = part >> 1;
+            const uint32_t taddr0 = tmem_base + ((quad * 32u) << 16) + grp * kMmaRows + colh * (2 * kMmaColsPerWarp);
+            const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            const uint2 *my_bnd = s_bnd + quad * 32 + lane;
+            // the strip's first row, computed only when a strip fires: tile ti of this CTA, query tile mt
+            auto strip_row = [&](uint32_t ti, uint32_t strip) {
+                return A.row0 + (uint64_t)(blockIdx.x + ti * gridDim.x) * kMmaTileCodes + 2 * (2 * colh + strip) * kMmaColsPerWarp;
+            };
+            uint32_t aph = 0, ti = 0, mt = grp;   // items in issue order are (tile, query tile); this group takes every second one
+            for (;;) {
+                while (mt >= q_tiles) { mt -= q_tiles; ++ti; }
+                if (ti >= my_tiles) break;
+                const uint2 bnd = my_bnd[mt * kMmaQTile];
+                mbar_wait_sleep(&tfull[grp], aph);
+                tcgen05_fence_after();
+                uint32_t p0[32], p1[32];   // register c = (D of column 2c+1) << 16 | (D of column 2c) & 0xFFFF
+                if (!UCFP_DIAG_NO_LD(A)) {
+                    tmem_ld64_pack16_async(taddr0, p0);
+                    tmem_ld64_pack16_async(taddr0 + kMmaColsPerWarp, p1);
+                    tmem_ld_wait(p0);
+                    tmem_ld_tie(p1);
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[grp]);   // both strips have left TMEM: release the stage
+                aph ^= 1;
+                if (!UCFP_DIAG_NO_TEST(A) && hamming_mma_strip_test(p0, bnd.x, bnd.y))
+                    hamming_mma_fire(p0, strip_row(ti, 0), mt * kMmaQTile + quad * 32 + lane, A, s_spill_n, s_q, s_kid);
+                if (!UCFP_DIAG_NO_TEST(A) && hamming_mma_strip_test(p1, bnd.x, bnd.y))
+                    hamming_mma_fire(p1, strip_row(ti, 1), mt * kMmaQTile + quad * 32 + lane, A, s_spill_n, s_q, s_kid);
+                mt += 2;
+            }
+        } else {
         // ===== epilogue: warp -> TMEM lane quadrant (warp % 4) and 64 of the 256 columns =====
-        const uint32_t quad = warp & 3, part = (warp - 1 - kMmaExpWarps) >> 2;
         uint32_t as = 0, aph = 0;   // accumulator stage in use and its mbarrier phase
         const uint32_t taddr0 = tmem_base + ((quad * 32u) << 16) + part * kMmaColsPerWarp;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -490,42 +574,19 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
             for (uint32_t mt = 0; mt < q_tiles; ++mt) {
                 const uint32_t q = mt * kMmaQTile + quad * 32 + lane;
                 const uint2 bnd = s_bnd[q];
-                const uint32_t hi_pk = bnd.x, lo_pk = bnd.y;   // hi16 - 1, lo16 + 1 in both halfwords
                 mbar_wait_sleep(&tfull[as], aph);
                 tcgen05_fence_after();
                 const uint32_t taddr = taddr0 + as * kMmaRows;
                 uint32_t p[32];   // register c = (D of column 2c+1) << 16 | (D of column 2c) & 0xFFFF
-                tmem_ld64_pack16_async(taddr, p);
-                tmem_ld_wait(p);
-                uint32_t mx[4], mn[4];   // per-halfword signed max of D, min of D << 9 (VIMNMX3.S16x2: two columns per lane-op)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { mx[j] = p[j]; mn[j] = p[j] * 512u; }
-#pragma unroll
-                for (int c = 4; c < 28; c += 8)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        mx[j] = __vimax3_s16x2(mx[j], p[c + j], p[c + 4 + j]);
-                        mn[j] = __vimin3_s16x2(mn[j], p[c + j] * 512u, p[c + 4 + j] * 512u);
-                    }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { mx[j] = __vmaxs2(mx[j], p[28 + j]); mn[j] = __vmins2(mn[j], p[28 + j] * 512u); }
-                const uint32_t m2 = __vimax3_s16x2(__vimax3_s16x2(mx[0], mx[1], mx[2]), mx[3], hi_pk);
-                const uint32_t n2 = __vimin3_s16x2(__vimin3_s16x2(mn[0], mn[1], mn[2]), mn[3], lo_pk);
-                const bool fired = (m2 != hi_pk) | (n2 != lo_pk);   // some halfword exceeded hi16 - 1 / fell below lo16 + 1
+                if (!UCFP_DIAG_NO_LD(A)) { tmem_ld64_pack16_async(taddr, p); tmem_ld_wait(p); }
+                const bool fired = !UCFP_DIAG_NO_TEST(A) && hamming_mma_strip_test(p, bnd.x, bnd.y);
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);   // the accumulators now live in registers: release the stage first
                 as ^= 1; aph ^= as ^ 1;
-                if (fired) {
-                    const uint32_t slot = A.spill ? atomicAdd(s_spill_n, 1u) : 0xFFFFFFFFu;
-                    if (slot < A.spill_cap) {   // park the strip: nothing waits for this store
-                        A.spill[(size_t)blockIdx.x * A.spill_cap + slot] = make_uint4(q, 0u, (uint32_t)first_row, (uint32_t)(first_row >> 32));
-                    } else {   // queue full (or switched off): settle in place; the hot test's bound is thr - 1 under implicit ids
-                        const uint32_t thr = s_q[q].z;
-                        hamming_mma_settle<32>(p, first_row, (A.ids == nullptr && s_kid[q] < A.id_base + A.row0) ? (thr == 0 ? 0u : thr - 1) : thr, q, A, s_q, s_kid);
-                    }
-                }
+                if (fired) hamming_mma_fire(p, first_row, q, A, s_spill_n, s_q, s_kid);
             }
+        }
         }
     }
     tcgen05_fence_before();
@@ -576,8 +637,9 @@ int hamming_device_init(ucfp_ctx *ctx) {
     int occ = 0;
     UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_scan_kernel, kScanThreads, sizeof(QSlot) * kMaxQueriesPerPass));
     ctx->ham_scan_occ = occ < 1 ? 1 : occ;
-    UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
-    UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
+    UCFP_CUDA_TRY((cudaFuncSetAttribute(hamming_mma_scan_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem)));
+    UCFP_CUDA_TRY((cudaFuncSetAttribute(hamming_mma_scan_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem)));
+    UCFP_CUDA_TRY((cudaFuncSetAttribute(hamming_mma_scan_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem)));
 #ifdef UCFP_HAMMING_EXPERIMENTS
     UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
     UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
@@ -614,12 +676,20 @@ int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
     static const long env_wait = getenv("UCFP_HAMMING_WAIT") ? atol(getenv("UCFP_HAMMING_WAIT")) : 0;
     static const long env_epi_w = getenv("UCFP_HAMMING_EPI_WARPS") ? atol(getenv("UCFP_HAMMING_EPI_WARPS")) : 16;
     static const long env_mma_v = getenv("UCFP_HAMMING_MMA_V") ? atol(getenv("UCFP_HAMMING_MMA_V")) : 1;
+#elif defined(UCFP_HAMMING_DIAG)
+    static const long env_wait = getenv("UCFP_HAMMING_DIAG") ? atol(getenv("UCFP_HAMMING_DIAG")) : 0;
 #else
     constexpr long env_wait = 0;
 #endif
     static const bool env_no_mma = getenv("UCFP_HAMMING_NO_MMA") != nullptr;   // developer switches: POPC scan only /
     static const bool env_no_ops = getenv("UCFP_HAMMING_NO_OPS") != nullptr;     // expand codes in the kernel although operand rows exist
     static const bool env_no_spill = getenv("UCFP_HAMMING_NO_SPILL") != nullptr;   // developer switch: settle every fire inside the scan (round-1 behaviour)
+    static const bool env_stagger = getenv("UCFP_HAMMING_STAGGER") ? atol(getenv("UCFP_HAMMING_STAGGER")) != 0 : true;   // developer switch: 0 = lock-step epilogue in the image form too
+    // Batches above this size expand the codes in the kernel even when stage images exist.  Measured (scripts/r2/gpu_step26-31.sh, 250 M
+    // codes, whole scan): image form with the two-group epilogue 1.95 / 2.90 / 5.13 ms at 128 / 256 / 512 queries against 1.99 / 2.90 /
+    // 5.50 lock-step; at 1024 queries 9.40 against 9.68 for the expansion form, but over 1 B codes the extra 24 GB of image reads per
+    // batch draw enough power to cost the clock 2 % (1927 vs 1965 MHz under sw_power_cap) and the two forms tie: 897-1024 queries stay
+    // on the expansion form, whose HBM traffic is the algorithmic 8 B per code.
     static const long env_img_maxq = getenv("UCFP_HAMMING_IMG_MAXQ") ? atol(getenv("UCFP_HAMMING_IMG_MAXQ")) : 7 * kMmaQTile;
 
     for (size_t q0 = 0; q0 < nq; q0 += kMaxQueriesPerPass) {
@@ -707,8 +777,10 @@ int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
                 else launched = false;
 #endif
                 if (launched) {}
-                else if (have_images && (long)nqp <= env_img_maxq) hamming_mma_scan_kernel<true><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
-                else hamming_mma_scan_kernel<false><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
+                else if (have_images && (long)nqp <= env_img_maxq) {
+                    if (env_stagger) hamming_mma_scan_kernel<true, true><<<mma_grid, kMmaStaggerThreads, kMmaSmem, st>>>(margs);
+                    else hamming_mma_scan_kernel<true, false><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
+                } else hamming_mma_scan_kernel<false, false><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
                 if (!launched && !env_no_spill) {   // the strips this launch parked are settled before the compaction
                     recheck_parked_kernel<<<dim3(mma_grid, kRecheckSlices), 256, 0, st>>>(spill, spill_count, kSpillCap, codes, ids, c->id_base, pos + n, slots, kth, cand, count, cap);
                     count_launch(ctx);

@@ -60,7 +60,6 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[64]) {
                       "+r"(v[43]), "+r"(v[44]), "+r"(v[45]), "+r"(v[46]), "+r"(v[47]), "+r"(v[48]), "+r"(v[49]), "+r"(v[50]), "+r"(v[51]), "+r"(v[52]), "+r"(v[53]),
                       "+r"(v[54]), "+r"(v[55]), "+r"(v[56]), "+r"(v[57]), "+r"(v[58]), "+r"(v[59]), "+r"(v[60]), "+r"(v[61]), "+r"(v[62]), "+r"(v[63]) :: "memory");
 }
-constexpr uint32_t kMmaNeverHiPk = 0x7FFE7FFEu;   // hi16 - 1 of a padding query (no accumulator can cross it)
 // per-halfword signed max of D and min of D << 9 against the query's two bounds (see hamming_mma_scan_kernel)
 template <int NREG>
 __device__ __forceinline__ bool hamming_mma_hot_test(const uint32_t (&p)[NREG], uint32_t hi_pk, uint32_t lo_pk) {

@@ -128,3 +128,7 @@ __device__ __forceinline__ void tmem_ld64_pack16_async(uint32_t taddr, uint32_t 
 __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : UCFP_RW32(v) :: "memory");
 }
+// ties a second register image to the position of a preceding tmem_ld_wait: no use of it can be scheduled above that wait
+__device__ __forceinline__ void tmem_ld_tie(uint32_t (&v)[32]) {
+    asm volatile("" : UCFP_RW32(v) :: "memory");
+}
