@@ -315,12 +315,17 @@ UCFP_API int ucfp_group_scan_cosine(ucfp_group *g, ucfp_corpus *const *corpora, 
                                     uint64_t *ids_out, float *score_out);
 
 /* Diagnostics of the most recent scan on this context (synchronises the stream): how many of its queries
- * overflowed their candidate list and were recomputed by the exact multi-pass selection.  0 on the fast path. */
+ * overflowed their candidate list and were recomputed.  0 on the fast path.  A Hamming / Jaccard query that overflows
+ * is first scanned again, together with the other flagged queries of its batch, under the bound its truncated lists
+ * produced (at most two such rounds, one streaming pass over the corpus each); only a query that still overflows, and
+ * every overflowing cosine query, goes to the exact multi-pass selection (~10 passes over the corpus per query). */
 UCFP_API int ucfp_ctx_last_scan_fallbacks(ucfp_ctx *ctx, uint64_t *queries_recomputed);
 /* Same, plus the longest candidate list any query of that scan (Hamming / Jaccard) accumulated between two compactions; the
- * lists hold 4096 entries (more for k > 1024), a longer one overflows into the exact multi-pass selection.  A robustness
- * gauge for skewed corpora: clustered near-duplicates, floods of identical codes. */
+ * lists hold 4096 entries (more for k > 1024), a longer one overflows.  A robustness gauge for skewed corpora: clustered
+ * near-duplicates, floods of identical codes. */
 UCFP_API int ucfp_ctx_last_scan_stats(ucfp_ctx *ctx, uint64_t *queries_recomputed, uint64_t *max_list_fill);
+/* How many queries of the most recent scan were left to the exact multi-pass selection (a subset of the above). */
+UCFP_API int ucfp_ctx_last_scan_exact_selects(ucfp_ctx *ctx, uint64_t *queries);
 
 /* Merges `parts` per-shard result lists (each nq x k, best first, as written by a scan) into one
  * nq x k list under the same total order: the step after the NCCL all-gather of per-rank candidates.

@@ -69,17 +69,32 @@ def test_planted_neighbours_and_heavy_ties(ctx):
     _check(ctx, codes, queries, 64, ids=ids)
 
 
-def test_duplicate_flood_takes_exact_fallback(ctx):
-    """All rows identical and ids descending: every row beats the current k-th, the candidate list
-    overflows, and the cooperative exact-selection kernel must still return the k smallest ids."""
+def test_duplicate_flood_is_rescanned(ctx):
+    """All rows identical and ids descending: every row beats the current k-th and the candidate lists overflow.  The flagged
+    queries are scanned again under the bound their (sampled) truncated lists produced and must return the k smallest ids
+    without reaching the exact multi-pass selection."""
     n, k = 300_000, 10
     codes = np.full(n, 0x0123456789ABCDEF, dtype=U64)
     ids = np.arange(n, 0, -1, dtype=U64) * U64(3)
     queries = np.array([0x0123456789ABCDEF, 0x0123456789ABCDEE, 0], dtype=U64)
     _check(ctx, codes, queries, k, ids=ids)
+    assert ctx.last_scan_fallbacks() == 3 and ctx.last_scan_exact_selects() == 0
     codes[::2] ^= U64(1)  # two tie classes
     _check(ctx, codes, queries, 33, ids=ids)
-    assert ctx.last_scan_fallbacks() > 0       # this input must have gone through the exact selection
+    assert ctx.last_scan_fallbacks() > 0 and ctx.last_scan_exact_selects() == 0
+
+
+def test_duplicate_flood_with_large_k(ctx):
+    """k = 1000 of a 4096-entry list: every re-scan round shrinks the flood by only ~cap / 2k; whichever path ends up settling the
+    queries (a second round or the exact selection), the k smallest ids must come back.  (The exact-selection kernel itself is
+    pinned by tests/test_jaccard_gpu.py::test_duplicate_flood_without_rescan_rounds_takes_exact_fallback.)"""
+    n, k = 300_000, 1000
+    codes = np.full(n, 0x0123456789ABCDEF, dtype=U64)
+    codes[::2] ^= U64(1)
+    ids = np.arange(n, 0, -1, dtype=U64) * U64(3)
+    queries = np.array([0x0123456789ABCDEF, 0], dtype=U64)
+    _check(ctx, codes, queries, k, ids=ids)
+    assert ctx.last_scan_fallbacks() == 2
 
 
 # ---- batches of >= 16 queries run chunks of >= 2^19 rows on the int8 tensor pipe (hamming_mma_scan_kernel) ----------
@@ -126,14 +141,14 @@ def test_tensor_path_heavy_ties_explicit_ids(ctx):
     _check(ctx, codes, queries, k, id_base=2**40)
 
 
-def test_tensor_path_duplicate_flood_falls_back(ctx):
+def test_tensor_path_duplicate_flood_is_rescanned(ctx):
     n, k = 1_300_000, 10
     codes = oracle.fill_u64(n, 77)
     codes[700_000:] = U64(0xFEEDFACECAFEBEEF)                       # 600 K identical rows, ids descending
     ids = np.arange(n, 0, -1, dtype=U64)
     queries = np.concatenate([np.array([0xFEEDFACECAFEBEEF, 0xFEEDFACECAFEBEEE], dtype=U64), oracle.fill_u64(30, 78)])
     _check(ctx, codes, queries, k, ids=ids)
-    assert ctx.last_scan_fallbacks() > 0
+    assert ctx.last_scan_fallbacks() > 0 and ctx.last_scan_exact_selects() == 0
 
 
 def test_tensor_path_incremental_appends_rebuild_pair_rows(ctx):

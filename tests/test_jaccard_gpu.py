@@ -70,14 +70,46 @@ def test_byte_collisions_are_not_matches(ctx):
     _check(ctx, sigs, q, 5)
 
 
-def test_duplicate_flood_takes_exact_fallback(ctx):
+def test_duplicate_flood_is_rescanned(ctx):
     n, k = 40_000, 10
     q = oracle.fill_u64(128, 3).reshape(1, 128)
     sigs = np.repeat(q, n, axis=0)
     sigs[::3, 5] ^= U64(1)  # two tie classes: 128 and 127 matches
     ids = np.arange(n, 0, -1, dtype=U64) * U64(5)
     _check(ctx, sigs, np.concatenate([q, q ^ U64(1)]), k, ids=ids)
-    assert ctx.last_scan_fallbacks() > 0       # this input must have gone through the exact selection
+    assert ctx.last_scan_fallbacks() > 0 and ctx.last_scan_exact_selects() == 0   # lists overflowed; the re-scan settled them
+
+
+def test_duplicate_flood_without_rescan_rounds_takes_exact_fallback():
+    """UCFP_RESCAN_ROUNDS=0 (read once per process, hence the subprocess) sends overflowed queries straight to the cooperative
+    exact-selection kernel, which must return the same answer: the backstop for floods the re-scan rounds cannot shrink."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prog = ("import numpy as np, oracle\n"
+            "from ucfp_b200 import Context, Corpus, _ffi\n"
+            "U64 = np.uint64\n"
+            "ctx = Context(0)\n"
+            "n, k = 40_000, 10\n"
+            "q = oracle.fill_u64(128, 3).reshape(1, 128)\n"
+            "sigs = np.repeat(q, n, axis=0); sigs[::3, 5] ^= U64(1)\n"
+            "ids = np.arange(n, 0, -1, dtype=U64) * U64(5)\n"
+            "qq = np.concatenate([q, q ^ U64(1)])\n"
+            "c = Corpus(ctx, _ffi.KIND_MINHASH128, n); c.append(sigs, ids)\n"
+            "gi, gm = c.scan_jaccard(qq, k)\n"
+            "oi, om = oracle.jaccard_topk(sigs, qq, k, ids=ids, threads=oracle.host_threads())\n"
+            "assert (gi == oi).all() and (gm == om).all() and ctx.last_scan_exact_selects() > 0\n"
+            "codes = np.full(300_000, 0x0123456789ABCDEF, dtype=U64); hid = np.arange(300_000, 0, -1, dtype=U64)\n"
+            "h = Corpus(ctx, _ffi.KIND_HAMMING64, len(codes)); h.append(codes, hid)\n"
+            "hq = np.array([0x0123456789ABCDEF, 7], dtype=U64)\n"
+            "gi, gd = h.scan_hamming(hq, k)\n"
+            "oi, od = oracle.hamming_topk(codes, hq, k, ids=hid, threads=oracle.host_threads())\n"
+            "assert (gi == oi).all() and (gd == od).all() and ctx.last_scan_exact_selects() == 2\n"
+            "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=root, UCFP_RESCAN_ROUNDS="0")
+    out = subprocess.run([sys.executable, "-c", prog], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
 def test_fewer_rows_than_k_and_empty(ctx):

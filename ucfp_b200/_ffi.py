@@ -86,6 +86,7 @@ PROTOTYPES = {
     "ucfp_scan_cosine": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "ucfp_ctx_last_scan_fallbacks": (_int, [_vp, C.POINTER(_u64)]),
     "ucfp_ctx_last_scan_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
+    "ucfp_ctx_last_scan_exact_selects": (_int, [_vp, C.POINTER(_u64)]),
     "ucfp_scan_multihash": (_int, [_vp, _vp, _sz, _sz, _sz, C.POINTER(MultiHashConfig), _vp, _vp]),
     "ucfp_multihash_compare": (_int, [_vp, _vp, _vp, _sz, C.POINTER(MultiHashConfig), _vp]),
     "ucfp_batcher_create": (_int, [_vp, _u32, _u32, C.POINTER(_vp)]),

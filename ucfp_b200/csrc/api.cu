@@ -548,6 +548,24 @@ int ucfp_ctx_last_scan_stats(ucfp_ctx *ctx, uint64_t *queries_recomputed, uint64
     UCFP_API_END
 }
 
+int ucfp_ctx_last_scan_exact_selects(ucfp_ctx *ctx, uint64_t *queries) {
+    UCFP_API_BEGIN
+    UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");
+    UCFP_REQUIRE(queries != nullptr, UCFP_E_INVALID, "NULL output");
+    *queries = 0;
+    UCFP_TRY(ucfp_ctx_synchronize(ctx));
+    DeviceGuard dg(ctx->device);
+    void *stats = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        stats = ctx->lanes[ctx->last_scan_lane]->stats.ptr;
+    }
+    if (!stats) return UCFP_OK;
+    UCFP_CUDA_TRY(cudaMemcpy(queries, static_cast<const uint64_t *>(stats) + 2, 8, cudaMemcpyDeviceToHost));
+    return UCFP_OK;
+    UCFP_API_END
+}
+
 int ucfp_ctx_last_scan_fallbacks(ucfp_ctx *ctx, uint64_t *queries_recomputed) {
     UCFP_API_BEGIN
     UCFP_REQUIRE(ctx != nullptr, UCFP_E_INVALID, "null context");

@@ -118,7 +118,7 @@ struct ucfp_lane {
     ucfp::DevBuf spill;                  // Hamming tensor scan: per-CTA queues of admitted pairs (64 KiB per CTA)
     ucfp::DevBuf mh_a, mh_b;             // multi-hash re-rank: query codes + coarse candidates, scored + merged lists
     ucfp::PinnedBuf pin_a, pin_b;
-    ucfp::DevBuf stats;                  // u64[4]: [0] queries recomputed by the exact fallback in this lane's last scan
+    ucfp::DevBuf stats;                  // u64[4] of this lane's last scan: [0] queries whose list overflowed (re-scanned), [1] longest list, [2] queries left to the exact selection
     ucfp_exchange *xch = nullptr;        // non-null during a group scan with more than one rank
 };
 

@@ -108,27 +108,42 @@ __device__ __noinline__ void hamming_survivors(uint4 c01, uint4 c23, uint4 c45, 
         if (d[c] <= s.z && r < row_end) {
             uint64_t id = ids ? ids[r] : id_base + r;
             if (d[c] < s.z || id < kid) {
-                uint32_t pos = atomicAdd(&count[q], 1u);
-                if (pos < cap) cand[(size_t)q * cap + pos] = ((uint64_t)d[c] << 40) | r;
+                cand_append(cand, count, cap, q, ((uint64_t)d[c] << 40) | r);
             }
         }
     }
 }
 
-// Scans rows [row0, row0 + nrows) of the corpus against the nq staged queries.
+// Scans rows [row0, row0 + nrows) of the corpus against the nq staged queries.  kRescan: against the FLAGGED queries only (a
+// re-scan round after a candidate list overflowed, topk_select.cuh); with no flag set every CTA returns at once.
+template <bool kRescan>
 __global__ void __launch_bounds__(kScanThreads, 4)
 hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restrict__ ids, uint64_t id_base,
                     uint64_t row0, uint64_t nrows, const QSlot *__restrict__ slots, const uint64_t *__restrict__ kth_id,
-                    uint32_t nq, uint32_t q_groups, uint64_t *cand, uint32_t *count, uint32_t cap) {
+                    uint32_t nq, uint32_t q_groups, uint64_t *cand, uint32_t *count, uint32_t cap, const uint32_t *__restrict__ flags) {
     extern __shared__ uint4 sq[];  // query slots of this CTA's group
     // Small chunks (the first few of a batch, where the admission bounds are still loose and the cold path runs
     // often) have fewer tiles than the GPU has CTA slots: the queries are then split into q_groups groups and the
     // grid is tiles x groups, one (tile, group) pair per CTA.  Large chunks use q_groups == 1 and a persistent grid.
     const uint32_t grp = q_groups > 1 ? blockIdx.x % q_groups : 0;
     const uint32_t q_lo = (uint32_t)((uint64_t)nq * grp / q_groups), q_hi = (uint32_t)((uint64_t)nq * (grp + 1) / q_groups);
-    const uint32_t nq_mine = q_hi - q_lo;
-    for (uint32_t i = threadIdx.x; i < nq_mine; i += kScanThreads) sq[i] = reinterpret_cast<const uint4 *>(slots)[q_lo + i];
-    __syncthreads();
+    uint32_t nq_mine = q_hi - q_lo;
+    if constexpr (kRescan) {   // slot.pad carries the query's index
+        __shared__ uint32_t s_listed;
+        if (threadIdx.x < 32) {
+            const uint32_t listed = list_flagged_queries(flags, nq, [&](uint32_t pos, uint32_t q) {
+                const QSlot s = slots[q];
+                sq[pos] = make_uint4(s.lo, s.hi, s.thr, q);
+            });
+            if (threadIdx.x == 0) s_listed = listed;
+        }
+        __syncthreads();
+        nq_mine = s_listed;
+        if (nq_mine == 0) return;
+    } else {
+        for (uint32_t i = threadIdx.x; i < nq_mine; i += kScanThreads) sq[i] = reinterpret_cast<const uint4 *>(slots)[q_lo + i];
+        __syncthreads();
+    }
 
     const uint64_t row_end = row0 + nrows;
     const uint64_t ntiles = (nrows + kTileCodes - 1) / kTileCodes;
@@ -156,7 +171,7 @@ hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restri
             }
             if (m <= s.z)  // rare: at least one code of this thread may be within the threshold
                 hamming_survivors(make_uint4(lo[0], hi[0], lo[1], hi[1]), make_uint4(lo[2], hi[2], lo[3], hi[3]),
-                                  make_uint4(lo[4], hi[4], lo[5], hi[5]), make_uint4(lo[6], hi[6], lo[7], hi[7]), s, q_lo + q,
+                                  make_uint4(lo[4], hi[4], lo[5], hi[5]), make_uint4(lo[6], hi[6], lo[7], hi[7]), s, kRescan ? s.w : q_lo + q,
                                   tile_row, row_end, ids, id_base, kth_id, cand, count, cap);
         }
     }
@@ -308,8 +323,7 @@ __device__ __forceinline__ void hamming_mma_settle(const uint32_t (&p)[NREG], ui
             if (r >= A.row_end || d[h] > thr) continue;
             const uint64_t id = A.ids ? (d[h] == thr ? A.ids[r] : 0) : A.id_base + r;
             if (d[h] < thr || id < kid) {
-                const uint32_t pos = atomicAdd(&A.count[q], 1u);
-                if (pos < A.cap) A.cand[(size_t)q * A.cap + pos] = ((uint64_t)d[h] << 40) | r;
+                cand_append(A.cand, A.count, A.cap, q, ((uint64_t)d[h] << 40) | r);
             }
         }
     }
@@ -349,8 +363,7 @@ __global__ void __launch_bounds__(256) recheck_parked_kernel(const uint4 *__rest
             if (r >= row_end || d > s.thr) continue;
             const uint64_t id = ids ? (d == s.thr ? ids[r] : 0) : id_base + r;
             if (d < s.thr || id < kid) {
-                const uint32_t pos = atomicAdd(&count[q], 1u);
-                if (pos < cap) cand[(size_t)q * cap + pos] = ((uint64_t)d << 40) | r;
+                cand_append(cand, count, cap, q, ((uint64_t)d << 40) | r);
             }
         }
     }
@@ -363,7 +376,7 @@ __global__ void __launch_bounds__(256) recheck_parked_kernel(const uint4 *__rest
 #define UCFP_DIAG_NO_TEST(A) false
 #define UCFP_DIAG_NO_LD(A) false
 #endif
-constexpr uint32_t kMmaNeverHiPk = 0x7FFE7FFEu;   // hi16 - 1 (both halfwords) of a query that can never fire: no accumulator crosses it
+[[maybe_unused]] constexpr uint32_t kMmaNeverHiPk = 0x7FFE7FFEu;   // hi16 - 1 (both halfwords) of a query that can never fire: no accumulator crosses it
 // The hot test of one 64-column strip: per-halfword signed max of D and min of D << 9 (VIMNMX3.S16x2: two columns per lane-op)
 // against the query's two bounds; true when some halfword exceeded hi16 - 1 or fell below lo16 + 1.
 __device__ __forceinline__ bool hamming_mma_strip_test(const uint32_t (&p)[32], uint32_t hi_pk, uint32_t lo_pk) {
@@ -635,7 +648,7 @@ int hamming_on_append(ucfp_lane *ctx, ucfp_corpus *c, uint64_t first_row, uint64
 int hamming_device_init(ucfp_ctx *ctx) {
     UCFP_CUDA_TRY(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
     int occ = 0;
-    UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_scan_kernel, kScanThreads, sizeof(QSlot) * kMaxQueriesPerPass));
+    UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_scan_kernel<false>, kScanThreads, sizeof(QSlot) * kMaxQueriesPerPass));
     ctx->ham_scan_occ = occ < 1 ? 1 : occ;
     UCFP_CUDA_TRY((cudaFuncSetAttribute(hamming_mma_scan_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem)));
     UCFP_CUDA_TRY((cudaFuncSetAttribute(hamming_mma_scan_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem)));
@@ -787,8 +800,8 @@ int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
                 }
             } else {
                 ProfScope ps(ctx, UCFP_PROF_HAMMING_SCAN, 8.0 * (double)n * nqp);
-                hamming_scan_kernel<<<(unsigned)grid, kScanThreads, sizeof(QSlot) * nqp, st>>>(
-                    codes, ids, c->id_base, pos, n, slots, kth, nqp, (uint32_t)q_groups, cand, count, cap);
+                hamming_scan_kernel<false><<<(unsigned)grid, kScanThreads, sizeof(QSlot) * nqp, st>>>(
+                    codes, ids, c->id_base, pos, n, slots, kth, nqp, (uint32_t)q_groups, cand, count, cap, nullptr);
             }
             count_launch(ctx);
             pos += n;
@@ -803,8 +816,16 @@ int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
             ctx->xch->done = 0;
         }
         UCFP_TRY(check_launch("hamming scan"));
-        // exact recomputation of any query whose candidate list overflowed (device-side decision, no host sync)
+        // Queries whose candidate list overflowed somewhere (device-side decisions, no host sync): up to kRescanRounds streaming
+        // passes over the corpus for the flagged queries alone, under the bound their truncated lists produced; the launches
+        // return at once when nothing is flagged.  What is still flagged afterwards goes to the exact multi-pass selection.
         UCFP_TRY(stats_add_flags(ctx, flags, nqp));
+        for (int round = 0; round < rescan_rounds(); ++round) {
+            hamming_scan_kernel<true><<<(unsigned)(ctx->sm_count * scan_occ), kScanThreads, sizeof(QSlot) * nqp, st>>>(
+                codes, ids, c->id_base, 0, N, slots, kth, nqp, 1u, cand, count, cap, flags);
+            compact_rescanned(sel, nqp, (uint32_t)k, ids, c->id_base, 0u, ids_out, dist_out, st);
+            count_launch(ctx, 2);
+        }
         UCFP_TRY(exact_select_fallback(ctx, c, ctx->owner->ham_exact_occ, HammingKey{codes, slots, 0, 0}, flags, nqp, (uint32_t)k, 0u, ids_out, dist_out, emit_rows ? 1 : 0));
     }
     return UCFP_OK;

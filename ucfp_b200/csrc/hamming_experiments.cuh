@@ -123,8 +123,7 @@ __device__ __forceinline__ void hamming_mma_recheck(const uint32_t (&p)[NREG], u
             if (r >= A.row_end || d > s.z) continue;
             const uint64_t id = A.ids ? (d == s.z ? A.ids[r] : 0) : A.id_base + r;
             if (d < s.z || id < kid) {
-                const uint32_t pos = atomicAdd(&A.count[q], 1u);
-                if (pos < A.cap) A.cand[(size_t)q * A.cap + pos] = ((uint64_t)d << 40) | r;
+                cand_append(A.cand, A.count, A.cap, q, ((uint64_t)d << 40) | r);
             }
         }
     }

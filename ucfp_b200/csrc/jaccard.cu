@@ -107,6 +107,9 @@ __device__ __forceinline__ uint32_t ne_bytes_8words(const uint32_t *w, uint4 q0,
     return g;   // bit 8 b + j set <=> byte b of word j differs
 }
 
+// kRescan: the launch serves the FLAGGED queries only (a re-scan round after a candidate list overflowed, topk_select.cuh); with no
+// flag set every CTA returns at once.
+template <bool kRescan>
 __global__ void __launch_bounds__(kScanThreads)
 jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint32_t *__restrict__ sketch1, const uint64_t *__restrict__ sigs,
                     const uint64_t *__restrict__ ids, uint64_t id_base, uint64_t row0, uint64_t nrows, const uint64_t *__restrict__ q_all,
@@ -116,17 +119,29 @@ jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint32_t *__restr
     // q_groups groups and the grid is tiles x groups.  Large chunks use q_groups == 1 and a persistent grid.
     const uint32_t grp = q_groups > 1 ? blockIdx.x % q_groups : 0;
     const uint32_t q_lo = (uint32_t)((uint64_t)nq_all * grp / q_groups), q_hi = (uint32_t)((uint64_t)nq_all * (grp + 1) / q_groups);
-    const uint32_t nq = q_hi - q_lo;
-    const uint64_t *q = q_all + (size_t)q_lo * kSlots;
-    uint32_t *sq = smem;                        // [nq][32] query sketches, plane 0 (byte 0 of every slot)
-    uint32_t *sq1 = smem + (size_t)nq * kSketchWords;   // [nq][32] plane 1 (byte 1)
-    uint32_t *sthr = sq1 + (size_t)nq * kSketchWords;   // [nq] admission bound (key = 128 - matches)
-    uint64_t *skid = reinterpret_cast<uint64_t *>(sthr + ((nq + 1) & ~1u));  // [nq] id of the current k-th result
-    for (uint32_t i = threadIdx.x; i < nq * kSketchWords; i += kScanThreads) {
-        sq[i] = qsketch[(size_t)q_lo * kSketchWords + i];
-        sq1[i] = qsketch[(size_t)(nq_all + q_lo) * kSketchWords + i];
+    uint32_t nq = q_hi - q_lo;
+    uint32_t *sidx = smem;                      // kRescan: [nq_all] indices of the flagged queries (the arrays below follow it)
+    if constexpr (kRescan) {
+        __shared__ uint32_t s_listed;
+        if (threadIdx.x < 32) {
+            const uint32_t listed = list_flagged_queries(S.flags, nq_all, [&](uint32_t pos, uint32_t q) { sidx[pos] = q; });
+            if (threadIdx.x == 0) s_listed = listed;
+        }
+        __syncthreads();
+        nq = s_listed;
+        if (nq == 0) return;
     }
-    for (uint32_t i = threadIdx.x; i < nq; i += kScanThreads) { sthr[i] = S.thr[(size_t)(q_lo + i) * S.thr_stride]; skid[i] = S.kth_id[q_lo + i]; }
+    uint32_t *sq = smem + (kRescan ? nq_all : 0u);      // [nq][32] query sketches, plane 0 (byte 0 of every slot)
+    uint32_t *sq1 = sq + (size_t)nq * kSketchWords;     // [nq][32] plane 1 (byte 1)
+    uint32_t *sthr = sq1 + (size_t)nq * kSketchWords;   // [nq] admission bound (key = 128 - matches)
+    uint64_t *skid = reinterpret_cast<uint64_t *>(smem + (((sthr - smem) + nq + 1) & ~(size_t)1));  // [nq] id of the current k-th result
+    auto query_of = [&](uint32_t qi) { return kRescan ? sidx[qi] : q_lo + qi; };
+    for (uint32_t i = threadIdx.x; i < nq * kSketchWords; i += kScanThreads) {
+        const uint32_t qr = query_of(i / kSketchWords), j = i % kSketchWords;
+        sq[i] = qsketch[(size_t)qr * kSketchWords + j];
+        sq1[i] = qsketch[(size_t)(nq_all + qr) * kSketchWords + j];
+    }
+    for (uint32_t i = threadIdx.x; i < nq; i += kScanThreads) { sthr[i] = S.thr[(size_t)query_of(i) * S.thr_stride]; skid[i] = S.kth_id[query_of(i)]; }
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -173,7 +188,7 @@ jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint32_t *__restr
                     // slot (sketch plane 1, the tile's 4 KiB stay in L1 across the query loop) settles 255 of 256 chance
                     // collisions; the 1 KiB row is read only when both bytes agree.
                     const uint64_t *rp = sigs + row * kSlots;
-                    const uint64_t *qp = q + (size_t)qi * kSlots;
+                    const uint64_t *qp = q_all + (size_t)query_of(qi) * kSlots;
                     uint32_t m = 0;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -188,8 +203,7 @@ jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint32_t *__restr
                     }
                     const uint32_t key = 128u - m;
                     if (key < thr || (key == thr && id < kid)) {
-                        uint32_t pos = atomicAdd(&S.count[q_lo + qi], 1u);
-                        if (pos < S.cap) S.cand[(size_t)(q_lo + qi) * S.cap + pos] = ((uint64_t)key << 40) | row;
+                        cand_append(S.cand, S.count, S.cap, query_of(qi), ((uint64_t)key << 40) | row);
                     }
                 }
                 // rows with many agreeing bytes (real neighbours): the whole warp verifies one row at a time
@@ -199,11 +213,10 @@ jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint32_t *__restr
                     hits &= hits - 1;
                     const uint64_t srow = __shfl_sync(0xffffffffu, row, src);
                     const uint64_t sid = __shfl_sync(0xffffffffu, id, src);
-                    const uint32_t m = warp_matches(sigs + srow * kSlots, q + (size_t)qi * kSlots, lane);
+                    const uint32_t m = warp_matches(sigs + srow * kSlots, q_all + (size_t)query_of(qi) * kSlots, lane);
                     const uint32_t key = 128u - m;
                     if (lane == 0 && (key < thr || (key == thr && sid < kid))) {
-                        uint32_t pos = atomicAdd(&S.count[q_lo + qi], 1u);
-                        if (pos < S.cap) S.cand[(size_t)(q_lo + qi) * S.cap + pos] = ((uint64_t)key << 40) | srow;
+                        cand_append(S.cand, S.count, S.cap, query_of(qi), ((uint64_t)key << 40) | srow);
                     }
                 }
             }
@@ -311,9 +324,10 @@ constexpr size_t kJaccardScanSmemMax = (size_t)kMaxQueriesPerPass * (2 * kSketch
 
 int jaccard_device_init(ucfp_ctx *ctx) {
     UCFP_CUDA_TRY(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
-    UCFP_CUDA_TRY(cudaFuncSetAttribute(jaccard_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJaccardScanSmemMax));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(jaccard_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJaccardScanSmemMax));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(jaccard_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kJaccardScanSmemMax + kMaxQueriesPerPass * 4)));
     int occ = 0;
-    UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jaccard_scan_kernel, kScanThreads, kJaccardScanSmemMax));
+    UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jaccard_scan_kernel<false>, kScanThreads, kJaccardScanSmemMax));
     ctx->jac_scan_occ = occ < 1 ? 1 : occ;
     UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exact_select_kernel<JaccardKey>, 256, 0));
     ctx->jac_exact_occ = occ < 1 ? 1 : (occ > 4 ? 4 : occ);
@@ -413,8 +427,8 @@ int jaccard_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
             }
             {
                 ProfScope ps(ctx, UCFP_PROF_JACCARD_SCAN, 1024.0 * (double)n * nqp);
-                jaccard_scan_kernel<<<(unsigned)grid, kScanThreads, smem, st>>>(sketch, sketch1, sigs, ids, c->id_base, pos, n, qp, qsk, nqp,
-                                                                               (uint32_t)q_groups, sel);
+                jaccard_scan_kernel<false><<<(unsigned)grid, kScanThreads, smem, st>>>(sketch, sketch1, sigs, ids, c->id_base, pos, n, qp, qsk, nqp,
+                                                                                      (uint32_t)q_groups, sel);
             }
             count_launch(ctx);
             pos += n;
@@ -430,7 +444,16 @@ int jaccard_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
             ctx->xch->done = 0;
         }
         UCFP_TRY(check_launch("jaccard scan"));
+        // Queries whose candidate list overflowed (device-side decisions, no host sync): up to kRescanRounds passes over the sketches
+        // for the flagged queries alone under the bound their truncated lists produced; the launches return at once when nothing
+        // is flagged.  What is still flagged afterwards goes to the exact multi-pass selection.
         UCFP_TRY(stats_add_flags(ctx, flags, nqp));
+        for (int round = 0; round < rescan_rounds(); ++round) {
+            jaccard_scan_kernel<true><<<(unsigned)(ctx->sm_count * occ), kScanThreads, smem + (size_t)nqp * 4, st>>>(
+                sketch, sketch1, sigs, ids, c->id_base, 0, N, qp, qsk, nqp, 1u, sel);
+            compact_rescanned(sel, nqp, (uint32_t)k, ids, c->id_base, 128u, ids_out, m_out, st);
+            count_launch(ctx, 2);
+        }
         UCFP_TRY(exact_select_fallback(ctx, c, ctx->owner->jac_exact_occ, JaccardKey{sigs, qp, nullptr}, flags, nqp, (uint32_t)k, 128u, ids_out, m_out));
     }
     return UCFP_OK;

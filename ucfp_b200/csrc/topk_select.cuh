@@ -3,8 +3,12 @@
 //
 //   compact_kernel       one CTA per query: bitonic sort of the candidate list by (key, id), keep k, publish
 //                        the new admission bound (thr = key_k, kth_id = id_k); the last call writes results.
+//   re-scan rounds       a query whose list overflowed between two compactions (floods of equal keys arriving in descending id
+//                        order) is scanned again, alone with the other flagged queries, over the whole corpus under the bound
+//                        its truncated lists produced: that bound is the k-th best of real rows, hence an upper bound of the
+//                        true k-th best, and far fewer rows pass it (each round shrinks the flood by ~cap / k).
 //   exact_select_kernel  cooperative multi-pass exact selection (key histogram + 8-bit radix select on ids)
-//                        for queries whose candidate list overflowed; correct for ANY input with bounded memory.
+//                        for queries still flagged after the re-scan rounds; correct for ANY input with bounded memory.
 //
 // Included inside namespace ucfp { namespace { ... } } by each scan's .cu file.
 #pragma once
@@ -17,7 +21,7 @@ struct SelectState {      // per query pass, all device pointers
     uint32_t *thr;        // first query's admission bound; query q at thr[q * thr_stride]
     uint32_t thr_stride;
     uint64_t *kth_id;     // [nq]
-    uint32_t *flags;      // [nq] 1 = list overflowed, needs exact_select
+    uint32_t *flags;      // [nq] 1 = list overflowed: the query is re-scanned (kRescanRounds), then left to exact_select
     uint32_t cap;
     uint32_t *big;        // [nq] list too long for the small compaction launch
     unsigned long long *max_fill = nullptr;   // diagnostics (may be null): longest list any compaction of this scan has seen
@@ -27,7 +31,34 @@ struct SelectState {      // per query pass, all device pointers
                           // histogram of the keys, every entry beyond the k-th key, and sorts the few that are left
 };
 
+// Every CTA of a re-scan launch derives the same list of flagged queries (ascending): warp 0 calls this, emit(position, query)
+// stores whatever the scan needs per listed query; returns the length of the list.
+template <typename Emit>
+__device__ __forceinline__ uint32_t list_flagged_queries(const uint32_t *__restrict__ flags, uint32_t nq, Emit emit) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    for (uint32_t q0 = 0; q0 < nq; q0 += 32) {
+        const uint32_t q = q0 + lane;
+        const bool f = q < nq && flags[q] != 0;
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (f) emit(base + (uint32_t)__popc(b & ((1u << lane) - 1u)), q);
+        base += (uint32_t)__popc(b);
+    }
+    return base;
+}
+
 constexpr uint32_t kSmallList = 1024;   // entries the small compaction launch sorts (16 KiB of shared memory)
+
+// Appends one entry to query q's candidate list.  A full list does not drop the newcomer: it overwrites a pseudo-random slot of the
+// list's upper half, so that what a flooded list holds at the next compaction is a SAMPLE of everything that was admitted rather
+// than its first arrivals.  Under a flood of equal keys arriving in descending id order the first arrivals are the worst rows; the
+// k-th best of a sample of M admitted rows has rank ~ 2 k M / cap among them, which is what makes the re-scan rounds converge.
+// (cap is a power of two; an entry is one 64-bit word, so racing writers leave one of their entries, never a torn one.)
+__device__ __forceinline__ void cand_append(uint64_t *cand, uint32_t *count, uint32_t cap, uint32_t q, uint64_t entry) {
+    uint32_t pos = atomicAdd(&count[q], 1u);
+    if (pos >= cap) pos = (cap >> 1) | (((pos * 0x9E3779B1u) >> 11) & ((cap >> 1) - 1u));
+    cand[(size_t)q * cap + pos] = entry;
+}
 
 __device__ __forceinline__ bool cand_before(uint64_t dra, uint64_t ida, uint64_t drb, uint64_t idb) {
     uint32_t da = (uint32_t)(dra >> 40), db = (uint32_t)(drb >> 40);
@@ -37,7 +68,13 @@ __device__ __forceinline__ bool cand_before(uint64_t dra, uint64_t ida, uint64_t
 // key_flip: 0 -> the reported value is the key itself; otherwise reported = key_flip - key (Jaccard matches).
 // Two launches per step (compact_lists): the first with shared memory for kSmallList entries (many CTAs per SM, one wave)
 // handles the usual short lists and leaves longer ones, marked in S.big, to the second launch (16 B x cap of shared memory),
-// whose other CTAs return at once.
+// whose other CTAs return at once.  second_launch == 2 is the compaction of a re-scan round: it takes exactly the flagged queries,
+// whatever the length of their lists, and clears the flag of every query whose re-scan fitted.
+constexpr int kRescanRounds = 2;
+static inline int rescan_rounds() {   // developer switch UCFP_RESCAN_ROUNDS (read once): 0 sends every overflow straight to exact_select
+    static const int rounds = getenv("UCFP_RESCAN_ROUNDS") ? atoi(getenv("UCFP_RESCAN_ROUNDS")) : kRescanRounds;
+    return rounds < 0 ? 0 : (rounds > 8 ? 8 : rounds);
+}
 __global__ void compact_kernel(SelectState S, uint32_t k, const uint64_t *__restrict__ ids, uint64_t id_base, int final_pass,
                                uint32_t key_flip, uint64_t *ids_out, uint32_t *keys_out, uint32_t smem_entries, int second_launch) {
     extern __shared__ uint64_t sm[];
@@ -45,7 +82,9 @@ __global__ void compact_kernel(SelectState S, uint32_t k, const uint64_t *__rest
     const uint32_t n_raw = S.count[q];
     const uint32_t n = min(n_raw, S.cap);
     if (!second_launch && threadIdx.x == 0 && S.max_fill && n_raw > 64) atomicMax(S.max_fill, (unsigned long long)n_raw);   // short lists: not worth an atomic
-    if (!second_launch) {
+    if (second_launch == 2) {
+        if (!S.flags[q]) return;
+    } else if (!second_launch) {
         const bool big = n > smem_entries;
         if (threadIdx.x == 0) S.big[q] = big ? 1u : 0u;
         if (big) return;
@@ -127,7 +166,8 @@ __global__ void compact_kernel(SelectState S, uint32_t k, const uint64_t *__rest
     }
     if (threadIdx.x == 0) {
         S.count[q] = m;
-        if (n_raw > S.cap) S.flags[q] = 1;
+        if (second_launch == 2) S.flags[q] = n_raw > S.cap ? 1u : 0u;   // a re-scan that fitted is the query's exact answer
+        else if (n_raw > S.cap) S.flags[q] = 1;
         // Publish the k-th entry as the admission bound -- unless the bound in force is already tighter: in a multi-GPU group
         // scan the ranks exchange their bounds between chunks (bounds_min_kernel below), so the bound a shard filters at may
         // come from another shard and be better than anything this list holds.
@@ -136,7 +176,19 @@ __global__ void compact_kernel(SelectState S, uint32_t k, const uint64_t *__rest
             const uint64_t new_kid = s_id[k - 1];
             if (new_thr < cur_thr || (new_thr == cur_thr && new_kid < S.kth_id[q])) { S.thr[(size_t)q * S.thr_stride] = new_thr; S.kth_id[q] = new_kid; }
         }
+        // The scan is over and this query's lists lost entries on the way: what was written above is provisional.  Prepare its
+        // re-scan: an empty list, and the bound made inclusive -- (thr, kth_id + 1) admits the bound's own row, so the rows of
+        // the truncated lists need not be kept and nothing can enter the new list twice.
+        if (final_pass && S.flags[q]) {
+            S.count[q] = 0;
+            if (S.kth_id[q] != UINT64_MAX) S.kth_id[q] += 1;
+        }
     }
+}
+
+static inline void compact_rescanned(const SelectState &S, uint32_t nq, uint32_t k, const uint64_t *ids, uint64_t id_base, uint32_t key_flip,
+                                     uint64_t *ids_out, uint32_t *keys_out, cudaStream_t st) {
+    compact_kernel<<<nq, 512, 16 * (size_t)S.cap, st>>>(S, k, ids, id_base, 1, key_flip, ids_out, keys_out, S.cap, 2);
 }
 
 static inline void compact_lists(const SelectState &S, uint32_t nq, uint32_t k, const uint64_t *ids, uint64_t id_base, bool final_pass,
@@ -205,7 +257,8 @@ template <typename KeyFn>
 __global__ void __launch_bounds__(256)
 exact_select_kernel(KeyFn fn, const uint64_t *__restrict__ ids, uint64_t id_base, uint64_t N,
                     const uint32_t *__restrict__ flags, uint32_t nq, uint32_t k, uint32_t key_flip, ExactScratch *scr,
-                    uint64_t *out_id, uint32_t *out_key, uint64_t *out_row, int emit_rows, uint64_t *ids_out, uint32_t *keys_out) {
+                    uint64_t *out_id, uint32_t *out_key, uint64_t *out_row, int emit_rows, uint64_t *ids_out, uint32_t *keys_out,
+                    unsigned long long *n_selected) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned int s_any;
@@ -221,6 +274,7 @@ exact_select_kernel(KeyFn fn, const uint64_t *__restrict__ ids, uint64_t id_base
 
     for (uint32_t q = 0; q < nq; ++q) {
         if (!flags[q]) continue;
+        if (gtid == 0 && n_selected) atomicAdd(n_selected, 1ULL);
         fn.load_query(q);
         // ---- 1. k-th smallest key: MSB-first 8-bit radix select over KeyFn::kKeyBits bits
         if (gtid == 0) scr->out_count = 0;
@@ -322,7 +376,8 @@ static int exact_select_fallback(ucfp_lane *ctx, ucfp_corpus *c, int occ, KeyFn 
     if (occ < 1) occ = 1;   // measured once per context by the *_device_init functions
     const uint64_t *ids = c->id_mode == 1 ? c->ids : nullptr;
     uint64_t id_base = c->id_base, N = c->size;
-    void *args[] = {&fn, &ids, &id_base, &N, &flags, &nq, &k, &key_flip, &scr, &out_id, &out_key, &out_row, &emit_rows, &ids_out, &keys_out};
+    unsigned long long *n_selected = ctx->stats.ptr ? ctx->stats.as<unsigned long long>() + 2 : nullptr;   // diagnostics: queries that got this far
+    void *args[] = {&fn, &ids, &id_base, &N, &flags, &nq, &k, &key_flip, &scr, &out_id, &out_key, &out_row, &emit_rows, &ids_out, &keys_out, &n_selected};
     UCFP_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)exact_select_kernel<KeyFn>, dim3(ctx->sm_count * occ), dim3(256), args,
                                               0, ctx->stream));
     count_launch(ctx);

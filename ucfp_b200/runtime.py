@@ -87,13 +87,19 @@ class Context:
         return int(self._L.ucfp_ctx_kernel_launches(self._h))
 
     def last_scan_fallbacks(self) -> int:
-        """Queries of the most recent scan that overflowed and were recomputed by the exact selection."""
+        """Queries of the most recent scan whose candidate list overflowed and that were recomputed (re-scan rounds, then exact selection)."""
         n = C.c_uint64(0)
         check(self._L.ucfp_ctx_last_scan_fallbacks(self._h, C.byref(n)))
         return int(n.value)
 
+    def last_scan_exact_selects(self) -> int:
+        """Queries of the most recent scan that the re-scan rounds could not settle and the exact multi-pass selection recomputed."""
+        n = C.c_uint64(0)
+        check(self._L.ucfp_ctx_last_scan_exact_selects(self._h, C.byref(n)))
+        return int(n.value)
+
     def last_scan_stats(self):
-        """-> (queries recomputed by the exact fallback, longest candidate list between two compactions) of the most recent scan."""
+        """-> (queries recomputed after an overflow, longest candidate list between two compactions) of the most recent scan."""
         a, b = C.c_uint64(0), C.c_uint64(0)
         check(self._L.ucfp_ctx_last_scan_stats(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
