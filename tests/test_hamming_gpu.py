@@ -78,10 +78,10 @@ def test_duplicate_flood_is_rescanned(ctx):
     ids = np.arange(n, 0, -1, dtype=U64) * U64(3)
     queries = np.array([0x0123456789ABCDEF, 0x0123456789ABCDEE, 0], dtype=U64)
     _check(ctx, codes, queries, k, ids=ids)
-    assert ctx.last_scan_fallbacks() == 3 and ctx.last_scan_exact_selects() == 0
+    assert (ctx.last_scan_fallbacks(), ctx.last_scan_exact_selects()) == (3, 0)
     codes[::2] ^= U64(1)  # two tie classes
     _check(ctx, codes, queries, 33, ids=ids)
-    assert ctx.last_scan_fallbacks() > 0 and ctx.last_scan_exact_selects() == 0
+    assert (ctx.last_scan_fallbacks(), ctx.last_scan_exact_selects()) == (3, 0)
 
 
 def test_duplicate_flood_with_large_k(ctx):

@@ -204,7 +204,10 @@ constexpr int kMmaImgBytes = kMmaRows * 64;          // pre-built stage image: 1
 constexpr int kMmaMaxImgStages = 8;
 constexpr int kMmaExpWarps = 4, kMmaEpiWarps = 16;
 constexpr int kMmaThreads = 32 * (1 + kMmaExpWarps + kMmaEpiWarps);
-constexpr int kMmaStaggerThreads = 32 * (2 + kMmaEpiWarps);   // two-group epilogue: MMA issuer, one TMA thread, 16 epilogue warps: 112 registers per thread
+// two-group epilogue (two 32-register accumulator images per epilogue thread): at most 20 warps, so that ptxas may use 96 registers.
+// Stage-image form: MMA issuer + one TMA thread + 16 epilogue warps; expansion form: MMA issuer + THREE producer warps + 16.
+constexpr int kMmaStaggerExpWarps = 3;
+constexpr int kMmaStaggerThreads = 32 * (2 + kMmaEpiWarps), kMmaStaggerExpThreads = 32 * (1 + kMmaStaggerExpWarps + kMmaEpiWarps);
 constexpr int kMmaColsPerWarp = kMmaRows / (kMmaEpiWarps / 4);
 constexpr uint32_t kMmaMaxQueries = 1024;
 constexpr uint32_t kMmaMinQueries = 64;              // measured crossover: the POPC scan costs 0.24 ms per query and 1 B rows, the tensor scan >= 15 ms per batch
@@ -411,10 +414,10 @@ __device__ __forceinline__ void hamming_mma_fire(const uint32_t (&p)[32], uint64
 
 
 template <bool kPreExpanded, bool kStagger>
-__global__ void __launch_bounds__(kStagger ? kMmaStaggerThreads : kMmaThreads, 1)
+__global__ void __launch_bounds__(kStagger ? (kPreExpanded ? kMmaStaggerThreads : kMmaStaggerExpThreads) : kMmaThreads, 1)
 hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
-    static_assert(kPreExpanded || !kStagger, "the two-group epilogue exists for the stage-image form only");
-    constexpr int kProdWarps = kStagger ? 1 : kMmaExpWarps;   // warps between the MMA issuer and the epilogue warps
+    constexpr int kProdWarps = kStagger ? (kPreExpanded ? 1 : kMmaStaggerExpWarps) : kMmaExpWarps;   // warps between the MMA issuer and the epilogue warps
+    constexpr int kProdThreads = 32 * kProdWarps, kProdRows = (kMmaRows + kProdThreads - 1) / kProdThreads;   // expansion: operand rows per producer thread and stage
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -459,7 +462,7 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
     }
     if (threadIdx.x == 0) {
         *s_spill_n = 0;
-        for (uint32_t s = 0; s < n_stages; ++s) { mbar_init(&cfull[s], kPreExpanded ? 1 : kMmaExpWarps * 32); mbar_init(&cempty[s], 1); }
+        for (uint32_t s = 0; s < n_stages; ++s) { mbar_init(&cfull[s], kPreExpanded ? 1 : kProdThreads); mbar_init(&cempty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kStagger ? kMmaEpiWarps / 2 : kMmaEpiWarps); }
         mbar_fence_init();
     }
@@ -495,7 +498,7 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
             __syncwarp();
         }
     } else if (warp <= kProdWarps) {
-        // ===== producers: thread t fills operand rows t and t + 128 of a stage =====
+        // ===== producers: thread t fills operand rows t, t + kProdThreads, ... of a stage =====
         const uint32_t t = threadIdx.x - 32;
         uint32_t it = 0;
         if (kPreExpanded) {
@@ -511,30 +514,35 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
                 }
             }
         } else {
-            // thread t expands codes 2r, 2r + 1 (16-byte loads) for r = t and t + 128
-            auto load_tile = [&](uint32_t tile, uint64_t (&c)[4]) {
+            // thread t expands codes 2r, 2r + 1 (16-byte loads) for the operand rows r = t, t + kProdThreads, ... of a stage
+            auto load_tile = [&](uint32_t tile, uint64_t (&c)[2 * kProdRows]) {
                 const uint64_t base = A.row0 + (uint64_t)tile * kMmaTileCodes;
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {   // rows past the end become code 0 and are rejected by the cold path's range check
-                    const uint64_t r0 = base + 2 * (t + 128 * j);
-                    if (r0 + 1 < A.row_end) {
+                for (int j = 0; j < kProdRows; ++j) {   // rows past the end become code 0 and are rejected by the cold path's range check
+                    const uint64_t r0 = base + 2 * (t + kProdThreads * j);
+                    if (kMmaRows % kProdThreads != 0 && t + kProdThreads * j >= (uint32_t)kMmaRows) { c[2 * j] = 0; c[2 * j + 1] = 0; }
+                    else if (r0 + 1 < A.row_end) {
                         const uint4 v = ldg_stream_v4(reinterpret_cast<const uint4 *>(A.codes + r0));
                         c[2 * j] = (uint64_t)v.y << 32 | v.x; c[2 * j + 1] = (uint64_t)v.w << 32 | v.z;
                     } else { c[2 * j] = r0 < A.row_end ? A.codes[r0] : 0; c[2 * j + 1] = 0; }
                 }
             };
-            uint64_t cur[4], nxt[4] = {0, 0, 0, 0};
+            uint64_t cur[2 * kProdRows], nxt[2 * kProdRows];
+#pragma unroll
+            for (int j = 0; j < 2 * kProdRows; ++j) nxt[j] = 0;
             if (blockIdx.x < n_tiles) load_tile(blockIdx.x, cur);
             for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const uint32_t s = it % kMmaStages, ph = (it / kMmaStages) & 1;
                 if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, nxt);   // next tile's codes fly while this one is expanded
                 mbar_wait_sleep(&cempty[s], ph ^ 1);
-                mma_store_code_row(sC + s * kMmaCBytes, t, cur[0], cur[1]);
-                mma_store_code_row(sC + s * kMmaCBytes, t + 128, cur[2], cur[3]);
+#pragma unroll
+                for (int j = 0; j < kProdRows; ++j)
+                    if (kMmaRows % kProdThreads == 0 || t + kProdThreads * j < (uint32_t)kMmaRows)
+                        mma_store_code_row(sC + s * kMmaCBytes, t + kProdThreads * j, cur[2 * j], cur[2 * j + 1]);
                 fence_proxy_async_smem();
                 mbar_arrive(&cfull[s]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+                for (int j = 0; j < 2 * kProdRows; ++j) cur[j] = nxt[j];
             }
         }
     } else {
@@ -653,6 +661,7 @@ int hamming_device_init(ucfp_ctx *ctx) {
     UCFP_CUDA_TRY((cudaFuncSetAttribute(hamming_mma_scan_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem)));
     UCFP_CUDA_TRY((cudaFuncSetAttribute(hamming_mma_scan_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem)));
     UCFP_CUDA_TRY((cudaFuncSetAttribute(hamming_mma_scan_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem)));
+    UCFP_CUDA_TRY((cudaFuncSetAttribute(hamming_mma_scan_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem)));
 #ifdef UCFP_HAMMING_EXPERIMENTS
     UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
     UCFP_CUDA_TRY(cudaFuncSetAttribute(hamming_mma_scan2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmem));
@@ -697,12 +706,12 @@ int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
     static const bool env_no_mma = getenv("UCFP_HAMMING_NO_MMA") != nullptr;   // developer switches: POPC scan only /
     static const bool env_no_ops = getenv("UCFP_HAMMING_NO_OPS") != nullptr;     // expand codes in the kernel although operand rows exist
     static const bool env_no_spill = getenv("UCFP_HAMMING_NO_SPILL") != nullptr;   // developer switch: settle every fire inside the scan (round-1 behaviour)
+    static const bool env_stagger_exp = getenv("UCFP_HAMMING_STAGGER_EXP") ? atol(getenv("UCFP_HAMMING_STAGGER_EXP")) != 0 : true;   // same for the expansion form
     static const bool env_stagger = getenv("UCFP_HAMMING_STAGGER") ? atol(getenv("UCFP_HAMMING_STAGGER")) != 0 : true;   // developer switch: 0 = lock-step epilogue in the image form too
-    // Batches above this size expand the codes in the kernel even when stage images exist.  Measured (scripts/r2/gpu_step26-31.sh, 250 M
-    // codes, whole scan): image form with the two-group epilogue 1.95 / 2.90 / 5.13 ms at 128 / 256 / 512 queries against 1.99 / 2.90 /
-    // 5.50 lock-step; at 1024 queries 9.40 against 9.68 for the expansion form, but over 1 B codes the extra 24 GB of image reads per
-    // batch draw enough power to cost the clock 2 % (1927 vs 1965 MHz under sw_power_cap) and the two forms tie: 897-1024 queries stay
-    // on the expansion form, whose HBM traffic is the algorithmic 8 B per code.
+    // Batches above this size expand the codes in the kernel even when stage images exist: with seven or eight query tiles per stage the
+    // expansion hides behind the MMAs, and its HBM traffic is the algorithmic 8 B per code -- over 1 B codes the image form's extra 24 GB
+    // per batch cost the clock 2 % under sw_power_cap.  Both forms run the two-group epilogue (scripts/r2/gpu_step26-34.sh, 1 024 queries:
+    // 250 M codes 9.73 -> 8.99 ms, 1 B codes 37.97 -> 35.12 ms on the same box).
     static const long env_img_maxq = getenv("UCFP_HAMMING_IMG_MAXQ") ? atol(getenv("UCFP_HAMMING_IMG_MAXQ")) : 7 * kMmaQTile;
 
     for (size_t q0 = 0; q0 < nq; q0 += kMaxQueriesPerPass) {
@@ -793,6 +802,8 @@ int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
                 else if (have_images && (long)nqp <= env_img_maxq) {
                     if (env_stagger) hamming_mma_scan_kernel<true, true><<<mma_grid, kMmaStaggerThreads, kMmaSmem, st>>>(margs);
                     else hamming_mma_scan_kernel<true, false><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
+                } else if (env_stagger_exp && nqp > 5 * kMmaQTile) {   // three producer warps keep up from six query tiles per stage on (measured: 768 queries 7.57 -> 6.95 ms per 250 M codes, 512 queries 5.35 -> 5.84)
+                    hamming_mma_scan_kernel<false, true><<<mma_grid, kMmaStaggerExpThreads, kMmaSmem, st>>>(margs);
                 } else hamming_mma_scan_kernel<false, false><<<mma_grid, kMmaThreads, kMmaSmem, st>>>(margs);
                 if (!launched && !env_no_spill) {   // the strips this launch parked are settled before the compaction
                     recheck_parked_kernel<<<dim3(mma_grid, kRecheckSlices), 256, 0, st>>>(spill, spill_count, kSpillCap, codes, ids, c->id_base, pos + n, slots, kth, cand, count, cap);
