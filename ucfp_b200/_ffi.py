@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libucfp_cuda.so")
+LIB_PATH = os.environ.get("UCFP_CUDA_LIB") or os.path.join(_HERE, "libucfp_cuda.so")   # developer override: A/B runs of two builds on one box
 
 OK, E_INVALID, E_CUDA, E_OOM, E_UNSUPPORTED, E_STATE, E_CAPACITY = 0, -1, -2, -3, -4, -5, -6
 KIND_HAMMING64, KIND_MINHASH128, KIND_COSINE, KIND_MULTIHASH = 1, 2, 3, 4

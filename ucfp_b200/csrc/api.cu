@@ -562,6 +562,11 @@ int ucfp_ctx_last_scan_exact_selects(ucfp_ctx *ctx, uint64_t *queries) {
     }
     if (!stats) return UCFP_OK;
     UCFP_CUDA_TRY(cudaMemcpy(queries, static_cast<const uint64_t *>(stats) + 2, 8, cudaMemcpyDeviceToHost));
+#ifdef UCFP_DEBUG_RESCAN   // developer build: longest re-scan list and number of re-scan compactions in the upper bits
+    uint64_t dbg[2] = {0, 0};
+    UCFP_CUDA_TRY(cudaMemcpy(dbg, static_cast<const uint64_t *>(stats) + 3, 16, cudaMemcpyDeviceToHost));
+    *queries |= dbg[0] << 16 | dbg[1] << 48;
+#endif
     return UCFP_OK;
     UCFP_API_END
 }

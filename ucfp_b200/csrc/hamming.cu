@@ -382,19 +382,45 @@ __global__ void __launch_bounds__(256) recheck_parked_kernel(const uint4 *__rest
 [[maybe_unused]] constexpr uint32_t kMmaNeverHiPk = 0x7FFE7FFEu;   // hi16 - 1 (both halfwords) of a query that can never fire: no accumulator crosses it
 // The hot test of one 64-column strip: per-halfword signed max of D and min of D << 9 (VIMNMX3.S16x2: two columns per lane-op)
 // against the query's two bounds; true when some halfword exceeded hi16 - 1 or fell below lo16 + 1.
+template <bool kMinimalOps>
 __device__ __forceinline__ bool hamming_mma_strip_test(const uint32_t (&p)[32], uint32_t hi_pk, uint32_t lo_pk) {
-    uint32_t mx[4], mn[4];
+    uint32_t mx[4], mn[4];   // four independent chains per test (latency)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { mx[j] = p[j]; mn[j] = p[j] * 512u; }
+    if constexpr (kMinimalOps) {
+        // 32 registers + the bound = 33 inputs per test: sixteen 3-input operations is the minimum.  Two chains of nine and two of seven
+        // registers, so that no chain ends in a 2-input operation: 14 + 2 VIMNMX3 per test instead of 16 + 2.  Measured on one box
+        // (scripts/r2/gpu_step35.sh): expansion form, 1 024 queries x 1 B codes 35.23 -> 34.36 ms; the image form at 512 queries is 2.5 %
+        // SLOWER with it (5.17 -> 5.30 ms per 250 M codes) and keeps the even chains below.
 #pragma unroll
-    for (int c = 4; c < 28; c += 8)
+        for (int i = 0; i < 4; ++i) {   // chains 0 and 1: registers 4..11 and 12..19
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            mx[j] = __vimax3_s16x2(mx[j], p[c + j], p[c + 4 + j]);
-            mn[j] = __vimin3_s16x2(mn[j], p[c + j] * 512u, p[c + 4 + j] * 512u);
+            for (int j = 0; j < 2; ++j) {
+                const int c = 4 + 8 * j + 2 * i;
+                mx[j] = __vimax3_s16x2(mx[j], p[c], p[c + 1]);
+                mn[j] = __vimin3_s16x2(mn[j], p[c] * 512u, p[c + 1] * 512u);
+            }
         }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { mx[j] = __vmaxs2(mx[j], p[28 + j]); mn[j] = __vmins2(mn[j], p[28 + j] * 512u); }
+        for (int i = 0; i < 3; ++i) {   // chains 2 and 3: registers 20..25 and 26..31
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = 20 + 6 * j + 2 * i;
+                mx[2 + j] = __vimax3_s16x2(mx[2 + j], p[c], p[c + 1]);
+                mn[2 + j] = __vimin3_s16x2(mn[2 + j], p[c] * 512u, p[c + 1] * 512u);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int c = 4; c < 28; c += 8)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                mx[j] = __vimax3_s16x2(mx[j], p[c + j], p[c + 4 + j]);
+                mn[j] = __vimin3_s16x2(mn[j], p[c + j] * 512u, p[c + 4 + j] * 512u);
+            }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { mx[j] = __vmaxs2(mx[j], p[28 + j]); mn[j] = __vmins2(mn[j], p[28 + j] * 512u); }
+    }
     const uint32_t m2 = __vimax3_s16x2(__vimax3_s16x2(mx[0], mx[1], mx[2]), mx[3], hi_pk);
     const uint32_t n2 = __vimin3_s16x2(__vimin3_s16x2(mn[0], mn[1], mn[2]), mn[3], lo_pk);
     return (m2 != hi_pk) | (n2 != lo_pk);
@@ -580,9 +606,9 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[grp]);   // both strips have left TMEM: release the stage
                 aph ^= 1;
-                if (!UCFP_DIAG_NO_TEST(A) && hamming_mma_strip_test(p0, bnd.x, bnd.y))
+                if (!UCFP_DIAG_NO_TEST(A) && hamming_mma_strip_test<!kPreExpanded>(p0, bnd.x, bnd.y))
                     hamming_mma_fire(p0, strip_row(ti, 0), mt * kMmaQTile + quad * 32 + lane, A, s_spill_n, s_q, s_kid);
-                if (!UCFP_DIAG_NO_TEST(A) && hamming_mma_strip_test(p1, bnd.x, bnd.y))
+                if (!UCFP_DIAG_NO_TEST(A) && hamming_mma_strip_test<!kPreExpanded>(p1, bnd.x, bnd.y))
                     hamming_mma_fire(p1, strip_row(ti, 1), mt * kMmaQTile + quad * 32 + lane, A, s_spill_n, s_q, s_kid);
                 mt += 2;
             }
@@ -600,7 +626,7 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
                 const uint32_t taddr = taddr0 + as * kMmaRows;
                 uint32_t p[32];   // register c = (D of column 2c+1) << 16 | (D of column 2c) & 0xFFFF
                 if (!UCFP_DIAG_NO_LD(A)) { tmem_ld64_pack16_async(taddr, p); tmem_ld_wait(p); }
-                const bool fired = !UCFP_DIAG_NO_TEST(A) && hamming_mma_strip_test(p, bnd.x, bnd.y);
+                const bool fired = !UCFP_DIAG_NO_TEST(A) && hamming_mma_strip_test<false>(p, bnd.x, bnd.y);
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);   // the accumulators now live in registers: release the stage first
@@ -708,11 +734,12 @@ int hamming_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
     static const bool env_no_spill = getenv("UCFP_HAMMING_NO_SPILL") != nullptr;   // developer switch: settle every fire inside the scan (round-1 behaviour)
     static const bool env_stagger_exp = getenv("UCFP_HAMMING_STAGGER_EXP") ? atol(getenv("UCFP_HAMMING_STAGGER_EXP")) != 0 : true;   // same for the expansion form
     static const bool env_stagger = getenv("UCFP_HAMMING_STAGGER") ? atol(getenv("UCFP_HAMMING_STAGGER")) != 0 : true;   // developer switch: 0 = lock-step epilogue in the image form too
-    // Batches above this size expand the codes in the kernel even when stage images exist: with seven or eight query tiles per stage the
-    // expansion hides behind the MMAs, and its HBM traffic is the algorithmic 8 B per code -- over 1 B codes the image form's extra 24 GB
-    // per batch cost the clock 2 % under sw_power_cap.  Both forms run the two-group epilogue (scripts/r2/gpu_step26-34.sh, 1 024 queries:
-    // 250 M codes 9.73 -> 8.99 ms, 1 B codes 37.97 -> 35.12 ms on the same box).
-    static const long env_img_maxq = getenv("UCFP_HAMMING_IMG_MAXQ") ? atol(getenv("UCFP_HAMMING_IMG_MAXQ")) : 7 * kMmaQTile;
+    // Batches above this size expand the codes in the kernel even when stage images exist: with six or more query tiles per stage the
+    // expansion (three producer warps) hides behind the MMAs, and its HBM traffic is the algorithmic 8 B per code -- over 1 B codes the
+    // image form's extra 24 GB per batch cost the clock 2 % under sw_power_cap.  Both forms run the two-group epilogue.  Measured per
+    // 250 M codes (scripts/r2/gpu_step34-36.sh): 640 queries 6.28 ms on images / 6.54 expanding, 768: 7.31 / 6.87, 896: 8.40 / 7.80,
+    // 1 024: 9.4 / 8.82; 1 B codes x 1 024 queries: 37.97 ms lock-step -> 34.36 ms.
+    static const long env_img_maxq = getenv("UCFP_HAMMING_IMG_MAXQ") ? atol(getenv("UCFP_HAMMING_IMG_MAXQ")) : 5 * kMmaQTile;
 
     for (size_t q0 = 0; q0 < nq; q0 += kMaxQueriesPerPass) {
         const uint32_t nqp = (uint32_t)((nq - q0 < kMaxQueriesPerPass) ? nq - q0 : kMaxQueriesPerPass);

@@ -132,8 +132,8 @@ __global__ void add_flags_kernel(const uint32_t *flags, uint32_t nq, unsigned lo
 }  // namespace
 
 int stats_reset(ucfp_lane *ctx) {
-    UCFP_TRY(ctx->stats.reserve(32));
-    UCFP_CUDA_TRY(cudaMemsetAsync(ctx->stats.ptr, 0, 32, ctx->stream));
+    UCFP_TRY(ctx->stats.reserve(64));
+    UCFP_CUDA_TRY(cudaMemsetAsync(ctx->stats.ptr, 0, 64, ctx->stream));
     return UCFP_OK;
 }
 

@@ -6,7 +6,7 @@
 //   re-scan rounds       a query whose list overflowed between two compactions (floods of equal keys arriving in descending id
 //                        order) is scanned again, alone with the other flagged queries, over the whole corpus under the bound
 //                        its truncated lists produced: that bound is the k-th best of real rows, hence an upper bound of the
-//                        true k-th best, and far fewer rows pass it (each round shrinks the flood by ~cap / k).
+//                        true k-th best, and far fewer rows pass it (each round shrinks the flood by ~0.75 cap / k).
 //   exact_select_kernel  cooperative multi-pass exact selection (key histogram + 8-bit radix select on ids)
 //                        for queries still flagged after the re-scan rounds; correct for ANY input with bounded memory.
 //
@@ -49,14 +49,25 @@ __device__ __forceinline__ uint32_t list_flagged_queries(const uint32_t *__restr
 
 constexpr uint32_t kSmallList = 1024;   // entries the small compaction launch sorts (16 KiB of shared memory)
 
-// Appends one entry to query q's candidate list.  A full list does not drop the newcomer: it overwrites a pseudo-random slot of the
-// list's upper half, so that what a flooded list holds at the next compaction is a SAMPLE of everything that was admitted rather
-// than its first arrivals.  Under a flood of equal keys arriving in descending id order the first arrivals are the worst rows; the
-// k-th best of a sample of M admitted rows has rank ~ 2 k M / cap among them, which is what makes the re-scan rounds converge.
-// (cap is a power of two; an entry is one 64-bit word, so racing writers leave one of their entries, never a torn one.)
+// Appends one entry to query q's candidate list.  A full list does not simply drop the newcomer: positions [cap / 4, cap) are a
+// RESERVOIR (Algorithm R with a hash of the arrival number as its random source), so that what a flooded list holds at the next
+// compaction is a uniform sample of everything that was admitted, whatever the order of arrival.  Neither "first come" nor "last
+// writer wins" is good enough: under a flood of equal keys whose ids descend with the row the first arrivals are the worst rows, and
+// the last ones are the stragglers of the launch's first wave, not its best rows -- a "last writer wins" list produced bounds that still
+// admitted 100 K of 600 K flood rows.  The k-th best of a uniform sample of M admitted rows has rank ~ k M / (0.75 cap) among them; that
+// is what makes the re-scan rounds converge.  The first quarter of the list (the k entries kept by the previous compaction, k <= cap / 4,
+// and the earliest arrivals) is never overwritten.  cap is a power of two; an entry is one 64-bit word, so racing writers leave one of
+// their entries, never a torn one.
 __device__ __forceinline__ void cand_append(uint64_t *cand, uint32_t *count, uint32_t cap, uint32_t q, uint64_t entry) {
     uint32_t pos = atomicAdd(&count[q], 1u);
-    if (pos >= cap) pos = (cap >> 1) | (((pos * 0x9E3779B1u) >> 11) & ((cap >> 1) - 1u));
+    if (pos >= cap) {
+        const uint32_t lo = cap >> 2;
+        uint32_t h = pos * 0x9E3779B1u;
+        h ^= h >> 15; h *= 0x85EBCA6Bu; h ^= h >> 13;
+        const uint32_t j = __umulhi(h, pos - lo + 1u);   // uniform over the arrivals that competed for the reservoir so far
+        if (j >= cap - lo) return;
+        pos = lo + j;
+    }
     cand[(size_t)q * cap + pos] = entry;
 }
 
@@ -167,6 +178,9 @@ __global__ void compact_kernel(SelectState S, uint32_t k, const uint64_t *__rest
     if (threadIdx.x == 0) {
         S.count[q] = m;
         if (second_launch == 2) S.flags[q] = n_raw > S.cap ? 1u : 0u;   // a re-scan that fitted is the query's exact answer
+#ifdef UCFP_DEBUG_RESCAN
+        if (second_launch == 2 && S.max_fill) { atomicMax(S.max_fill + 2, (unsigned long long)n_raw); atomicAdd(S.max_fill + 3, 1ULL); }
+#endif
         else if (n_raw > S.cap) S.flags[q] = 1;
         // Publish the k-th entry as the admission bound -- unless the bound in force is already tighter: in a multi-GPU group
         // scan the ranks exchange their bounds between chunks (bounds_min_kernel below), so the bound a shard filters at may
