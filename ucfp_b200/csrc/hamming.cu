@@ -382,11 +382,24 @@ __global__ void __launch_bounds__(256) recheck_parked_kernel(const uint4 *__rest
 [[maybe_unused]] constexpr uint32_t kMmaNeverHiPk = 0x7FFE7FFEu;   // hi16 - 1 (both halfwords) of a query that can never fire: no accumulator crosses it
 // The hot test of one 64-column strip: per-halfword signed max of D and min of D << 9 (VIMNMX3.S16x2: two columns per lane-op)
 // against the query's two bounds; true when some halfword exceeded hi16 - 1 or fell below lo16 + 1.
+// The low field's view of a packed register: the 7 low bits of each halfword moved to its top.  p * 512 compiles to IMAD.SHL (FMA
+// pipe).  A rotation by 9 (funnel shift SHF.L.W, ALU pipe; the wrapped-in bits land in the 9 junk bits the bounds already mask) is
+// equivalent and was measured because a mixed microbenchmark loop pairs VIMNMX3.S16x2 with ALU-pipe logic at one instruction per clock
+// and with IMAD.SHL at 1.52 (profiles/r02_pipe_rates.txt) -- in the kernel it is slower: 1 024 queries x 1 B codes 35.56 ms with the
+// multiply, 43.40 with the rotation, 37.10 alternating the two (scripts/r2/gpu_step38.sh).  -DUCFP_HAMMING_SHIFT=1|2 rebuilds them.
+#ifndef UCFP_HAMMING_SHIFT
+#define UCFP_HAMMING_SHIFT 0
+#endif
+template <int kWhich>
+__device__ __forceinline__ uint32_t hamming_mma_low_view(uint32_t p) {
+    if (UCFP_HAMMING_SHIFT == 0 || (UCFP_HAMMING_SHIFT == 2 && (kWhich & 1))) return p * 512u;
+    return __funnelshift_l(p, p, 9);
+}
 template <bool kMinimalOps>
 __device__ __forceinline__ bool hamming_mma_strip_test(const uint32_t (&p)[32], uint32_t hi_pk, uint32_t lo_pk) {
     uint32_t mx[4], mn[4];   // four independent chains per test (latency)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { mx[j] = p[j]; mn[j] = p[j] * 512u; }
+    for (int j = 0; j < 4; ++j) { mx[j] = p[j]; mn[j] = hamming_mma_low_view<0>(p[j]); }
     if constexpr (kMinimalOps) {
         // 32 registers + the bound = 33 inputs per test: sixteen 3-input operations is the minimum.  Two chains of nine and two of seven
         // registers, so that no chain ends in a 2-input operation: 14 + 2 VIMNMX3 per test instead of 16 + 2.  Measured on one box
@@ -398,7 +411,7 @@ __device__ __forceinline__ bool hamming_mma_strip_test(const uint32_t (&p)[32], 
             for (int j = 0; j < 2; ++j) {
                 const int c = 4 + 8 * j + 2 * i;
                 mx[j] = __vimax3_s16x2(mx[j], p[c], p[c + 1]);
-                mn[j] = __vimin3_s16x2(mn[j], p[c] * 512u, p[c + 1] * 512u);
+                mn[j] = __vimin3_s16x2(mn[j], hamming_mma_low_view<0>(p[c]), hamming_mma_low_view<1>(p[c + 1]));
             }
         }
 #pragma unroll
@@ -407,7 +420,7 @@ __device__ __forceinline__ bool hamming_mma_strip_test(const uint32_t (&p)[32], 
             for (int j = 0; j < 2; ++j) {
                 const int c = 20 + 6 * j + 2 * i;
                 mx[2 + j] = __vimax3_s16x2(mx[2 + j], p[c], p[c + 1]);
-                mn[2 + j] = __vimin3_s16x2(mn[2 + j], p[c] * 512u, p[c + 1] * 512u);
+                mn[2 + j] = __vimin3_s16x2(mn[2 + j], hamming_mma_low_view<0>(p[c]), hamming_mma_low_view<1>(p[c + 1]));
             }
         }
     } else {
@@ -416,10 +429,10 @@ __device__ __forceinline__ bool hamming_mma_strip_test(const uint32_t (&p)[32], 
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 mx[j] = __vimax3_s16x2(mx[j], p[c + j], p[c + 4 + j]);
-                mn[j] = __vimin3_s16x2(mn[j], p[c + j] * 512u, p[c + 4 + j] * 512u);
+                mn[j] = __vimin3_s16x2(mn[j], hamming_mma_low_view<0>(p[c + j]), hamming_mma_low_view<1>(p[c + 4 + j]));
             }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { mx[j] = __vmaxs2(mx[j], p[28 + j]); mn[j] = __vmins2(mn[j], p[28 + j] * 512u); }
+        for (int j = 0; j < 4; ++j) { mx[j] = __vmaxs2(mx[j], p[28 + j]); mn[j] = __vmins2(mn[j], hamming_mma_low_view<0>(p[28 + j])); }
     }
     const uint32_t m2 = __vimax3_s16x2(__vimax3_s16x2(mx[0], mx[1], mx[2]), mx[3], hi_pk);
     const uint32_t n2 = __vimin3_s16x2(__vimin3_s16x2(mn[0], mn[1], mn[2]), mn[3], lo_pk);
