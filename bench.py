@@ -352,6 +352,19 @@ def secondary_cosine(torch, ctx, group, rank, world, dev, timed, bf16_peak, smal
 
 
 # ---------------------------------------------------------------- main --------------------------------
+def committed_tensor_pipe_active():
+    """sm__pipe_tensor_cycles_active (fraction) of the committed ncu capture of the tensor scan; None when the file is absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_hamming_mma_q1024_ncu.txt")
+    try:
+        with open(path) as f:
+            for line in f:
+                if line.startswith("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"):
+                    return round(float(line.split()[-1]) / 100.0, 4)
+    except OSError:
+        pass
+    return None
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -627,17 +640,18 @@ def main() -> int:
                     "unit": "TFLOP/s", "frac": tops / int8_peak, "traffic": None,
                     "peak_source": f"measured: int8 tcgen05.mma M128xN256xK64 at 256.0 clk/tile (profiles/r02_tmem_port.txt) x {sm_count} SMs x "
                                    f"{sm_mhz:.0f} MHz sampled under load; MEASURED_PEAKS.json holds no int8 figure",
-                    "frac_vs_2x_bf16_sustained": tops / (2 * bf16_peak), "tensor_pipe_active_ncu": 0.39,
+                    "frac_vs_2x_bf16_sustained": tops / (2 * bf16_peak), "tensor_pipe_active_ncu": committed_tensor_pipe_active(),
                     "launches": t_n, "kernel_ms_per_step": t_ms / args.steps,
                     "pairs_per_s": (t_ops / 64.0) / (t_ms / 1e3),
                     "all_scan_launches": {"launches": k_n, "kernel_ms_per_step": k_ms / args.steps,
                                           "pairs_per_s": pairs / (k_ms / 1e3) if k_ms else None},
-                    "note": "achieved counts int8 operations (TOP/s) EXECUTED by the tensor pipe; `frac` agrees with ncu's "
-                            "sm__pipe_tensor_cycles_active (0.39, profiles/r01_hamming_mma_q1024_ncu.txt).  The bound in force is the "
-                            "epilogue: ~420 clk of ALU-pipe min/max per 256-clk accumulator tile plus exposed mbarrier / tcgen05.ld "
-                            "latency (DESIGN.md 4.1, profiles/r02_hamming_schedules.md).  DRAM traffic is 8.02 B per row per batch "
-                            "(ncu, profiles/hamming_scan_traffic.json): not measured live, hence `traffic` null.  `streaming` is "
-                            "hamming_scan_kernel with 1-2 queries per corpus pass, where HBM is the bound",
+                    "note": "achieved counts int8 operations (TOP/s) EXECUTED by the tensor pipe; `tensor_pipe_active_ncu` is "
+                            "sm__pipe_tensor_cycles_active of the committed capture of this kernel (profiles/r02_hamming_mma_q1024_ncu.txt), "
+                            "read from that file, not measured in this run.  The bound in force is the epilogue, not the MMAs: per 128 x 512-pair "
+                            "accumulator item ~134 clk of tcgen05.ld plus ~430 clk of min/max work that do not overlap each other, around a "
+                            "hand-over ring of ~380 clk (DESIGN.md 4.1, profiles/r02_hamming_schedules.md sections 5-6).  DRAM traffic is 8.02 B "
+                            "per row per batch (ncu, profiles/hamming_scan_traffic.json): not measured live, hence `traffic` null.  `streaming` "
+                            "is hamming_scan_kernel with 1-2 queries per corpus pass, where HBM is the bound",
                     "streaming": streaming}
     else:
         roofline = {"bound": "hbm", "kernel": "hamming_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
