@@ -131,7 +131,7 @@ jaccard_scan_kernel(const uint32_t *__restrict__ sketch, const uint32_t *__restr
         nq = s_listed;
         if (nq == 0) return;
     }
-    uint32_t *sq = smem + (kRescan ? nq_all : 0u);      // [nq][32] query sketches, plane 0 (byte 0 of every slot)
+    uint32_t *sq = smem + (kRescan ? (nq_all + 3u) & ~3u : 0u);   // [nq][32] query sketches, plane 0 (byte 0 of every slot); read as uint4: 16-byte aligned
     uint32_t *sq1 = sq + (size_t)nq * kSketchWords;     // [nq][32] plane 1 (byte 1)
     uint32_t *sthr = sq1 + (size_t)nq * kSketchWords;   // [nq] admission bound (key = 128 - matches)
     uint64_t *skid = reinterpret_cast<uint64_t *>(smem + (((sthr - smem) + nq + 1) & ~(size_t)1));  // [nq] id of the current k-th result
@@ -325,7 +325,7 @@ constexpr size_t kJaccardScanSmemMax = (size_t)kMaxQueriesPerPass * (2 * kSketch
 int jaccard_device_init(ucfp_ctx *ctx) {
     UCFP_CUDA_TRY(cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 8192));
     UCFP_CUDA_TRY(cudaFuncSetAttribute(jaccard_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJaccardScanSmemMax));
-    UCFP_CUDA_TRY(cudaFuncSetAttribute(jaccard_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kJaccardScanSmemMax + kMaxQueriesPerPass * 4)));
+    UCFP_CUDA_TRY(cudaFuncSetAttribute(jaccard_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kJaccardScanSmemMax + kMaxQueriesPerPass * 4 + 16)));
     int occ = 0;
     UCFP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jaccard_scan_kernel<false>, kScanThreads, kJaccardScanSmemMax));
     ctx->jac_scan_occ = occ < 1 ? 1 : occ;
@@ -449,7 +449,7 @@ int jaccard_scan(ucfp_lane *ctx, ucfp_corpus *c, const uint64_t *q_dev, size_t n
         // is flagged.  What is still flagged afterwards goes to the exact multi-pass selection.
         UCFP_TRY(stats_add_flags(ctx, flags, nqp));
         for (int round = 0; round < rescan_rounds(); ++round) {
-            jaccard_scan_kernel<true><<<(unsigned)(ctx->sm_count * occ), kScanThreads, smem + (size_t)nqp * 4, st>>>(
+            jaccard_scan_kernel<true><<<(unsigned)(ctx->sm_count * occ), kScanThreads, smem + (size_t)nqp * 4 + 16, st>>>(
                 sketch, sketch1, sigs, ids, c->id_base, 0, N, qp, qsk, nqp, 1u, sel);
             compact_rescanned(sel, nqp, (uint32_t)k, ids, c->id_base, 128u, ids_out, m_out, st);
             count_launch(ctx, 2);
