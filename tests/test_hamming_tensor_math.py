@@ -40,7 +40,7 @@ def s16(v: np.ndarray) -> np.ndarray:
 def bounds(thr_hot):
     """hi16 / lo16 of the kernel prologue for one hot-test bound (None = never)"""
     if thr_hot is None:
-        return 0x7FFF, -0x7FFF
+        return 0x8000, -0x8001     # stored as 0x7FFF / -0x8000: no halfword exceeds the one or falls below the other
     if thr_hot >= 64:
         return -0x7FFF, 0
     tau = 64 - 2 * thr_hot
@@ -102,8 +102,8 @@ def test_hot_test_has_no_false_negatives_and_only_documented_false_positives():
         got[0::2], got[1::2] = fired_lo, fired_hi
         assert not (want & ~got).any(), f"false negative at thr {thr}"
         extra = got & ~want
-        if thr is None:      # never-lanes may still see x_a = +-64 (low halfword only, junk-free): rejected by the exact test later
-            assert (da[: len(D)][extra] % 64 == 0).all()
+        if thr is None:      # never means never: also for x_a = +-64, whose low field is the most negative halfword there is
+            assert not extra.any()
         else:                # false positives: dist_a == 64 (aliases dist 0); the y test may also admit dist_b <= thr when x_a = -64
             assert ((da[: len(D)][extra] == 64) | (db[: len(D)][extra] <= thr + 1)).all(), thr
             assert (da[: len(D)][extra] == 64).all() or thr >= 31

@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256) recheck_parked_kernel(const uint4 *__rest
 #define UCFP_DIAG_NO_TEST(A) false
 #define UCFP_DIAG_NO_LD(A) false
 #endif
-[[maybe_unused]] constexpr uint32_t kMmaNeverHiPk = 0x7FFE7FFEu;   // hi16 - 1 (both halfwords) of a query that can never fire: no accumulator crosses it
+[[maybe_unused]] constexpr uint32_t kMmaNeverHiPk = 0x7FFF7FFFu;   // hi16 - 1 (both halfwords) of a query that can never fire: no accumulator crosses it
 // The hot test of one 64-column strip: per-halfword signed max of D and min of D << 9 (VIMNMX3.S16x2: two columns per lane-op)
 // against the query's two bounds; true when some halfword exceeded hi16 - 1 or fell below lo16 + 1.
 // The low field's view of a packed register: the 7 low bits of each halfword moved to its top.  p * 512 compiles to IMAD.SHL (FMA
@@ -494,7 +494,8 @@ hamming_mma_scan_kernel(const __grid_constant__ MmaScanArgs A) {
         // "max/min against the bound changes the bound".  never: neither bound can be crossed by |D| <= 4160; thr >= 64: always.
         const int32_t tau = 64 - 2 * (int32_t)hot;
         int32_t hi16 = 64 * (tau - 1), lo16 = (-tau * 512) | 0x1FF;
-        if (hot == 0xFFFFFFFFu) { hi16 = 0x7FFF; lo16 = -0x7FFF; }
+        if (hot == 0xFFFFFFFFu) { hi16 = 0x8000; lo16 = -0x8001; }   // bounds 0x7FFF / -0x8000: no halfword exceeds the one or falls below the other
+                                                                      // (-0x7FFF + 1 left a hole: a low field of -64, i.e. an exact duplicate in an even row, still fired)
         else if (hot >= 64) { hi16 = -0x7FFF; lo16 = 0; }
         const uint32_t hi1 = (uint16_t)(hi16 - 1), lo1 = (uint16_t)(lo16 + 1);
         s_bnd[q] = make_uint2(hi1 << 16 | hi1, lo1 << 16 | lo1);   // both halfwords

@@ -165,10 +165,10 @@ hamming_mma_scan2_kernel(const __grid_constant__ MmaScanArgs A) {
         if (q >= A.nq) hot = 0xFFFFFFFFu;
         const int32_t tau = 64 - 2 * (int32_t)hot;
         int32_t hi16 = 64 * (tau - 1), lo16 = (-tau * 512) | 0x1FF;
-        if (hot == 0xFFFFFFFFu) { hi16 = 0x7FFF; lo16 = -0x7FFF; }
+        if (hot == 0xFFFFFFFFu) { hi16 = 0x8000; lo16 = -0x8001; }
         else if (hot >= 64) { hi16 = -0x7FFF; lo16 = 0; }
         const uint32_t hi1 = (uint16_t)(hi16 - 1), lo1 = (uint16_t)(lo16 + 1);
-        s_bnd[q] = make_uint2(hi1 << 16 | hi1, lo1 << 16 | lo1);   // hi1 == 0x7FFE only for "never" (kMmaNeverHiPk)
+        s_bnd[q] = make_uint2(hi1 << 16 | hi1, lo1 << 16 | lo1);   // hi1 == 0x7FFF only for "never" (kMmaNeverHiPk)
     }
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < n_stages; ++s) { mbar_init(&cfull[s], 1); mbar_init(&cempty[s], 1); }
@@ -315,7 +315,7 @@ hamming_mma_scan3_kernel(const __grid_constant__ MmaScanArgs A) {
         if (q >= A.nq) hot = 0xFFFFFFFFu;
         const int32_t tau = 64 - 2 * (int32_t)hot;
         int32_t hi16 = 64 * (tau - 1), lo16 = (-tau * 512) | 0x1FF;
-        if (hot == 0xFFFFFFFFu) { hi16 = 0x7FFF; lo16 = -0x7FFF; }
+        if (hot == 0xFFFFFFFFu) { hi16 = 0x8000; lo16 = -0x8001; }
         else if (hot >= 64) { hi16 = -0x7FFF; lo16 = 0; }
         const uint32_t hi1 = (uint16_t)(hi16 - 1), lo1 = (uint16_t)(lo16 + 1);
         s_bnd[q] = make_uint2(hi1 << 16 | hi1, lo1 << 16 | lo1);
@@ -456,7 +456,7 @@ hamming_mma_scan4_kernel(const __grid_constant__ MmaScanArgs A) {
         if (q >= A.nq) hot = 0xFFFFFFFFu;
         const int32_t tau = 64 - 2 * (int32_t)hot;
         int32_t hi16 = 64 * (tau - 1), lo16 = (-tau * 512) | 0x1FF;
-        if (hot == 0xFFFFFFFFu) { hi16 = 0x7FFF; lo16 = -0x7FFF; }
+        if (hot == 0xFFFFFFFFu) { hi16 = 0x8000; lo16 = -0x8001; }
         else if (hot >= 64) { hi16 = -0x7FFF; lo16 = 0; }
         const uint32_t hi1 = (uint16_t)(hi16 - 1), lo1 = (uint16_t)(lo16 + 1);
         s_bnd[q] = make_uint2(hi1 << 16 | hi1, lo1 << 16 | lo1);

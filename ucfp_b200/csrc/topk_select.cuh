@@ -81,7 +81,9 @@ __device__ __forceinline__ bool cand_before(uint64_t dra, uint64_t ida, uint64_t
 // handles the usual short lists and leaves longer ones, marked in S.big, to the second launch (16 B x cap of shared memory),
 // whose other CTAs return at once.  second_launch == 2 is the compaction of a re-scan round: it takes exactly the flagged queries,
 // whatever the length of their lists, and clears the flag of every query whose re-scan fitted.
-constexpr int kRescanRounds = 2;
+constexpr int kRescanRounds = 2;   // each round divides a flood by ~0.75 cap / k.  (Dropping a flagged query from the tensor scan's hot test for the rest of the
+                                   // main scan was measured too: the first round then meets the whole flood, a third round is needed, and the batch is no faster:
+                                   // 8.65 vs 9.56 ms with 8 of 1 024 queries in a 1 M-row flood, +40 us on every batch that has none.)
 static inline int rescan_rounds() {   // developer switch UCFP_RESCAN_ROUNDS (read once): 0 sends every overflow straight to exact_select
     static const int rounds = getenv("UCFP_RESCAN_ROUNDS") ? atoi(getenv("UCFP_RESCAN_ROUNDS")) : kRescanRounds;
     return rounds < 0 ? 0 : (rounds > 8 ? 8 : rounds);
