@@ -189,10 +189,16 @@ hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restri
 // as 32 registers of s16 pairs (tcgen05.ld ... pack::16b) and keeps a per-halfword signed max of D (the x_b test) and
 // min of D * 512 (x_a's 7 bits at the top of each halfword) with VIMNMX3.S16x2: 1 multiply + 1 min/max lane-op per
 // register = per four (query, code) pairs, and the per-query bounds come ready-made from shared memory.
-// Only when a bound is crossed does that lane take the cold path, which decodes the distances from its registers and
-// applies the same admission rule as hamming_survivors.  Queries stay resident in shared memory as
-// eight 128-row A tiles; operand rows are either expanded from the codes by four producer warps (<false>, used at 897-1024
-// queries) or copied ready-made from corpus->ham_ops by TMA bulk copies (<true>, 64-896 queries).
+// Only when a bound is crossed does that lane take the cold path: it parks its 128-code strip for recheck_parked_kernel (or, when the
+// CTA's queue is full, decodes the distances from its registers) under the same admission rule as hamming_survivors.  Queries stay
+// resident in shared memory as eight 128-row A tiles.  Template parameters:
+//   kPreExpanded  operand rows copied ready-made from corpus->ham_ops by TMA bulk copies (64-640 queries) / expanded from the codes
+//                 by producer warps in the kernel (641-1024 queries, and any corpus without stage images);
+//   kStagger      epilogue as two groups of eight warps, group g serving accumulator stage g (every second item), 128 columns per
+//                 warp as two 64-column strips in two register images -- the product path of both forms (20 warps at most, so that
+//                 96 registers are available) / all sixteen warps in lock-step on the same item, 64 columns each: round 1's schedule,
+//                 kept for batches of 129-640 queries on corpora without stage images (three producer warps do not keep up there) and
+//                 behind UCFP_HAMMING_STAGGER=0 / UCFP_HAMMING_STAGGER_EXP=0.
 constexpr int kMmaQTile = 128;                       // UMMA M: queries per accumulator tile (TMEM lanes)
 constexpr int kMmaRows = 256;                        // UMMA N: operand rows per stage = 512 codes (TMEM columns)
 constexpr int kMmaTileCodes = 2 * kMmaRows;
