@@ -197,7 +197,7 @@ hamming_scan_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restri
 //   kStagger      epilogue as two groups of eight warps, group g serving accumulator stage g (every second item), 128 columns per
 //                 warp as two 64-column strips in two register images -- the product path of both forms (20 warps at most, so that
 //                 96 registers are available) / all sixteen warps in lock-step on the same item, 64 columns each: round 1's schedule,
-//                 kept for batches of 129-640 queries on corpora without stage images (three producer warps do not keep up there) and
+//                 kept for batches of 64-640 queries on corpora without stage images (three producer warps do not keep up there) and
 //                 behind UCFP_HAMMING_STAGGER=0 / UCFP_HAMMING_STAGGER_EXP=0.
 constexpr int kMmaQTile = 128;                       // UMMA M: queries per accumulator tile (TMEM lanes)
 constexpr int kMmaRows = 256;                        // UMMA N: operand rows per stage = 512 codes (TMEM columns)
