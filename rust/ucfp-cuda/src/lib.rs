@@ -69,6 +69,10 @@ pub mod sys {
         pub fn ucfp_group_ctx(g: *mut ucfp_group, local_rank: c_int) -> *mut ucfp_ctx;
         pub fn ucfp_group_scan_hamming(g: *mut ucfp_group, corpora: *const *mut ucfp_corpus, q: *const u64, nq: usize, k: usize,
                                        ids: *mut u64, dist: *mut u32) -> c_int;
+        // gauges of the most recent scan on a context: queries whose candidate list overflowed (and were re-scanned), the longest list,
+        // queries that reached the exact multi-pass selection -- worth exporting next to the reference's own request metrics
+        pub fn ucfp_ctx_last_scan_stats(ctx: *mut ucfp_ctx, queries_recomputed: *mut u64, max_list_fill: *mut u64) -> c_int;
+        pub fn ucfp_ctx_last_scan_exact_selects(ctx: *mut ucfp_ctx, queries: *mut u64) -> c_int;
     }
 }
 
